@@ -1,0 +1,382 @@
+/*
+ * oracle/ref_driver.c  --  TEST INFRASTRUCTURE ONLY.
+ *
+ * Flat C entry points (`sdref_*`, same shapes as include/sdgpu.h) on top of the REFERENCE'S OWN
+ * functions, compiled from the sources where they lie under /root/reference/twoSD_src
+ * (stocUpdate.c, cuts.c, optimal.c, randCost.c) against the header shim in oracle/shim/.  The recipe is
+ * oracle/Makefile; the output is oracle/_ref/libsdref.so (git-ignored, travels to the GPU box).
+ *
+ * Nothing here re-implements table or cut arithmetic: it only builds the reference's structs
+ * (stoc.h:22-97, twoSD.h:69-85) from flat arrays and forwards to
+ *   calcOmega  stocUpdate.c:326   calcLambda stocUpdate.c:264   calcSigma stocUpdate.c:286
+ *   calcDelta  stocUpdate.c:196   computeIstar stocUpdate.c:142 SDCut cuts.c:91
+ *   cutHeight  cuts.c:213         maxCutHeight cuts.c:197       calcVariance cuts.c:366
+ *   reformCuts optimal.c:187      checkBasisFeasibility randCost.c:202
+ * The basis bookkeeping of stochasticUpdates (stocUpdate.c:101-131) needs CPLEX for everything before
+ * it, so the append / dedup step is replayed here from its inputs.
+ */
+#include "twoSD.h"
+#include "../include/sdgpu.h"
+
+configType config;   /* twoSD.c:17 defines it in the real program */
+
+typedef struct {
+	numType      num;
+	coordType    coord;
+	sparseVector bBar;
+	sparseMatrix Cbar;
+	sdgpu_caps   caps;
+	lambdaType  *lambda;
+	sigmaType   *sigma;
+	deltaType   *delta;
+	omegaType   *omega;
+	basisType   *basis;
+} refCtx;
+
+static iVector dupInts(const int32_t *src, int n) {
+	iVector d = arr_alloc(n + 1, int);
+	int i;
+	if (src) for (i = 0; i <= n; i++) d[i] = src[i];
+	return d;
+}
+
+static dVector dupDbls(const double *src, int n) {
+	dVector d = arr_alloc(n + 1, double);
+	int i;
+	if (src) for (i = 0; i <= n; i++) d[i] = src[i];
+	return d;
+}
+
+int sdref_create(const sdgpu_problem *p, const sdgpu_caps *caps, int device, void **out) {
+	refCtx *c = (refCtx *) calloc(1, sizeof(refCtx));
+	(void) device;
+	c->num.rows = p->num.rows;         c->num.cols = p->num.cols;
+	c->num.prevCols = p->num.prevCols; c->num.cntCcols = p->num.cntCcols;
+	c->num.rvRowCnt = p->num.rvRowCnt; c->num.rvbOmCnt = p->num.rvbOmCnt;
+	c->num.rvCOmCnt = p->num.rvCOmCnt; c->num.rvdOmCnt = p->num.rvdOmCnt;
+	c->num.numRV = p->num.numRV;
+	c->coord.CCols     = dupInts(p->coord.CCols, p->num.cntCcols);
+	c->coord.rvRows    = dupInts(p->coord.rvRows, p->num.rvRowCnt);
+	c->coord.rvbOmRows = dupInts(p->coord.rvbOmRows, p->num.rvbOmCnt);
+	c->coord.rvCOmCols = dupInts(p->coord.rvCOmCols, p->num.rvCOmCnt);
+	c->coord.rvCOmRows = dupInts(p->coord.rvCOmRows, p->num.rvCOmCnt);
+	c->coord.rvCols    = dupInts(p->coord.rvCols, p->num.rvCOmCnt);
+	c->coord.rvOffset  = arr_alloc(3, int);
+	c->coord.rvOffset[0] = p->coord.rvOffset[0]; c->coord.rvOffset[1] = p->coord.rvOffset[1];
+	c->coord.rvOffset[2] = p->coord.rvOffset[2];
+	c->bBar.cnt = p->bBar.cnt; c->bBar.col = dupInts(p->bBar.col, p->bBar.cnt); c->bBar.val = dupDbls(p->bBar.val, p->bBar.cnt);
+	c->Cbar.cnt = p->Cbar.cnt; c->Cbar.col = dupInts(p->Cbar.col, p->Cbar.cnt); c->Cbar.row = dupInts(p->Cbar.row, p->Cbar.cnt);
+	c->Cbar.val = dupDbls(p->Cbar.val, p->Cbar.cnt);
+	c->caps = *caps;
+	/* setup.c:140-144 */
+	c->basis  = newBasisType((int) caps->maxBasis, c->num.cols, c->num.rows, WORDLENGTH);
+	c->lambda = newLambda((int) caps->maxLambda, 0, c->num.rvRowCnt);
+	c->sigma  = newSigma((int) caps->maxSigma, c->num.cntCcols, 0);
+	c->delta  = newDelta((int) caps->maxLambda);
+	c->omega  = newOmega(c->num.numRV, (int) caps->maxOmega);
+	*out = c;
+	return 0;
+}
+
+static void dropBases(refCtx *c) {
+	int n;
+	for (n = 0; n < c->basis->cnt; n++) {
+		freeOneBasis(c->basis->vals[n]);
+		if (c->basis->obsFeasible[n]) mem_free(c->basis->obsFeasible[n]);
+		c->basis->vals[n] = NULL; c->basis->obsFeasible[n] = NULL;
+	}
+	c->basis->cnt = 0;
+}
+
+int sdref_reset(void *vc) {
+	refCtx *c = (refCtx *) vc;
+	int n;
+	/* setup.c:242-246 */
+	dropBases(c);
+	freeDeltaType(c->delta, c->lambda->cnt, c->omega->cnt, true);
+	for (n = 0; n < c->lambda->cnt; n++) c->delta->vals[n] = NULL;
+	freeLambdaType(c->lambda, true);
+	freeSigmaType(c->sigma, true);
+	freeOmegaType(c->omega, true);
+	return 0;
+}
+
+void sdref_destroy(void *vc) {
+	refCtx *c = (refCtx *) vc;
+	if (!c) return;
+	sdref_reset(c);
+	freeBasisType(c->basis, false);
+	freeDeltaType(c->delta, 0, 0, false);
+	freeLambdaType(c->lambda, false);
+	freeSigmaType(c->sigma, false);
+	freeOmegaType(c->omega, false);
+	free(c->coord.CCols); free(c->coord.rvRows); free(c->coord.rvbOmRows); free(c->coord.rvCOmCols);
+	free(c->coord.rvCOmRows); free(c->coord.rvCols); free(c->coord.rvOffset);
+	free(c->bBar.col); free(c->bBar.val); free(c->Cbar.col); free(c->Cbar.row); free(c->Cbar.val);
+	free(c);
+}
+
+int sdref_get_counts(void *vc, sdgpu_counts *out) {
+	refCtx *c = (refCtx *) vc;
+	out->omega = c->omega->cnt; out->lambda = c->lambda->cnt; out->sigma = c->sigma->cnt; out->basis = c->basis->cnt;
+	return 0;
+}
+
+int sdref_calc_omega(void *vc, const double *observ, double tol, int *newOmegaFlag) {
+	refCtx *c = (refCtx *) vc;
+	bool flag = false;
+	int idx = calcOmega((dVector) observ, 0, c->num.numRV, c->omega, &flag, tol);   /* algo.c:152 */
+	if (newOmegaFlag) *newOmegaFlag = flag;
+	return idx;
+}
+
+int sdref_calc_lambda(void *vc, const double *Pi, double tol, int *newLambdaFlag) {
+	refCtx *c = (refCtx *) vc;
+	bool flag = false;
+	int idx = calcLambda(&c->num, &c->coord, (dVector) Pi, c->lambda, &flag, tol);
+	if (newLambdaFlag) *newLambdaFlag = flag;
+	return idx;
+}
+
+int sdref_calc_sigma(void *vc, const double *pi, double mubBar, int idxLambda, int newLambdaFlag, int currentIter,
+		double tol, int *newSigmaFlag) {
+	refCtx *c = (refCtx *) vc;
+	bool flag = false;
+	int idx = calcSigma(&c->num, &c->coord, &c->bBar, &c->Cbar, (dVector) pi, mubBar, idxLambda, newLambdaFlag != 0,
+			currentIter, c->sigma, &flag, tol);
+	if (newSigmaFlag) *newSigmaFlag = flag;
+	return idx;
+}
+
+int sdref_calc_delta(void *vc, int newOmegaFlag, int elemIdx) {
+	refCtx *c = (refCtx *) vc;
+	return calcDelta(&c->num, &c->coord, c->lambda, c->delta, (int) c->caps.maxOmega, c->omega, newOmegaFlag != 0, elemIdx);
+}
+
+/* stocUpdate.c:78-85 for one dual vector */
+int sdref_update_dual(void *vc, const double *pi, double mubBar, int currentIter, double tol,
+		int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag) {
+	int nl = 0, ns = 0, li, si;
+	li = sdref_calc_lambda(vc, pi, tol, &nl);
+	si = sdref_calc_sigma(vc, pi, mubBar, li, nl, currentIter, tol, &ns);
+	if (nl) sdref_calc_delta(vc, 0, li);
+	if (lambdaIdx) *lambdaIdx = li;
+	if (newLambdaFlag) *newLambdaFlag = nl;
+	if (sigmaIdx) *sigmaIdx = si;
+	if (newSigmaFlag) *newSigmaFlag = ns;
+	return 0;
+}
+
+static oneBasis *makeBasis(int ck, int feasFlag, int phiLength, const int32_t *sigmaIdx, const int32_t *omegaIdx) {
+	oneBasis *B = (oneBasis *) calloc(1, sizeof(oneBasis));
+	int i;
+	B->ck = ck; B->weight = 1; B->phiLength = phiLength; B->feasFlag = feasFlag != 0;
+	B->sigmaIdx = arr_alloc(phiLength + 1, int);
+	for (i = 0; i <= phiLength; i++) B->sigmaIdx[i] = sigmaIdx[i];
+	if (phiLength > 0) {
+		B->omegaIdx = arr_alloc(phiLength + 1, int);
+		for (i = 1; i <= phiLength; i++) B->omegaIdx[i] = omegaIdx[i];
+	}
+	return B;
+}
+
+static int pushBasis(refCtx *c, oneBasis *B) {
+	int cnt;
+	/* stocUpdate.c:117-131 with checkBasisFeasibility == true (the caller overrides entries afterwards) */
+	c->basis->vals[c->basis->cnt] = B;
+	if (B->feasFlag) {
+		c->basis->obsFeasible[c->basis->cnt] = (bool *) arr_alloc((int) c->caps.maxOmega, bool);
+		for (cnt = 0; cnt < (int) c->caps.maxOmega; cnt++) c->basis->obsFeasible[c->basis->cnt][cnt] = true;
+	}
+	else
+		c->basis->obsFeasible[c->basis->cnt] = NULL;
+	return c->basis->cnt++;
+}
+
+int sdref_basis_append(void *vc, int ck, int feasFlag, int phiLength, const int32_t *sigmaIdx, const int32_t *omegaIdx) {
+	return pushBasis((refCtx *) vc, makeBasis(ck, feasFlag, phiLength, sigmaIdx, omegaIdx));
+}
+
+int sdref_basis_find_or_append(void *vc, int retainBasis, int obsIdx, int ck, int feasFlag, int phiLength,
+		const int32_t *sigmaIdx, const int32_t *omegaIdx, int *newBasisFlag) {
+	refCtx *c = (refCtx *) vc;
+	oneBasis *B = makeBasis(ck, feasFlag, phiLength, sigmaIdx, omegaIdx);
+	int cnt;
+	if (newBasisFlag) *newBasisFlag = 1;
+	if (!retainBasis) {
+		/* replay of stocUpdate.c:101-113 (obsFeasible of an infeasible basis is NULL there: treated as false) */
+		for (cnt = 0; cnt < c->basis->cnt; cnt++) {
+			if (B->phiLength == c->basis->vals[cnt]->phiLength && c->basis->obsFeasible[cnt] && c->basis->obsFeasible[cnt][obsIdx]) {
+				if (equalIntvec(B->sigmaIdx - 1, c->basis->vals[cnt]->sigmaIdx - 1, B->phiLength + 1)) {
+					freeOneBasis(B);
+					c->basis->vals[cnt]->weight++;
+					if (newBasisFlag) *newBasisFlag = 0;
+					return cnt;
+				}
+			}
+		}
+	}
+	return pushBasis(c, B);
+}
+
+int sdref_basis_set_obs_feasible(void *vc, int basisIdx, int obsIdx, int flag) {
+	refCtx *c = (refCtx *) vc;
+	if (basisIdx < 0 || basisIdx >= c->basis->cnt || !c->basis->obsFeasible[basisIdx]) return SDGPU_ERR;
+	c->basis->obsFeasible[basisIdx][obsIdx] = flag != 0;
+	return 0;
+}
+
+int sdref_basis_set_obs_feasible_row(void *vc, int basisIdx, const uint8_t *flags) {
+	refCtx *c = (refCtx *) vc;
+	int o;
+	if (basisIdx < 0 || basisIdx >= c->basis->cnt || !c->basis->obsFeasible[basisIdx]) return SDGPU_ERR;
+	for (o = 0; o < c->omega->cnt; o++) c->basis->obsFeasible[basisIdx][o] = flags[o] != 0;
+	return 0;
+}
+
+int sdref_basis_set_obs_feasible_col(void *vc, int obsIdx, const uint8_t *flags) {
+	refCtx *c = (refCtx *) vc;
+	int b;
+	for (b = 0; b < c->basis->cnt; b++)
+		if (c->basis->obsFeasible[b]) c->basis->obsFeasible[b][obsIdx] = flags[b] != 0;
+	return 0;
+}
+
+int sdref_compute_istar(void *vc, const double *Xvect, int obs, int numSamples, int pi_eval, int isNew, double *argmax) {
+	refCtx *c = (refCtx *) vc;
+	dVector piCbarX = arr_alloc(c->sigma->cnt + 1, double);
+	int s, idx;
+	for (s = 0; s < c->sigma->cnt; s++)     /* cuts.c:105-106 */
+		piCbarX[s] = vXv(c->sigma->vals[s].piC, (dVector) Xvect, c->coord.CCols, c->num.cntCcols);
+	idx = computeIstar(&c->num, &c->coord, c->basis, c->sigma, c->delta, piCbarX, (dVector) Xvect, c->omega->vals[obs],
+			obs, numSamples, pi_eval != 0, argmax, isNew != 0);
+	mem_free(piCbarX);
+	return idx;
+}
+
+/* SDCut with the reference's own config gates.  piRatioOut receives pi_ratio[numSamples % SCAN_LEN]. */
+int sdref_sd_cut_cfg(void *vc, const double *Xvect, int numSamples, int dualStability, int piEvalStart, int piCycle,
+		int scanLen, double lb, sdgpu_cut *cut, double *pi_ratio, int *dualStableFlag) {
+	refCtx *c = (refCtx *) vc;
+	oneCut *rc;
+	bool stable = dualStableFlag ? (*dualStableFlag != 0) : false;
+	int i;
+	config.DUAL_STABILITY = dualStability; config.PI_EVAL_START = piEvalStart; config.PI_CYCLE = piCycle;
+	config.SCAN_LEN = scanLen;
+	rc = SDCut(&c->num, &c->coord, c->basis, c->sigma, c->delta, c->omega, (dVector) Xvect, numSamples, &stable, pi_ratio, lb);
+	if (rc == NULL) return SDGPU_NONE;
+	cut->alpha = rc->alpha; cut->omegaCnt = rc->omegaCnt; cut->numSamples = rc->numSamples;
+	for (i = 0; i <= c->num.prevCols; i++) cut->beta[i] = rc->beta[i];
+	if (cut->iStar) for (i = 0; i < rc->omegaCnt; i++) cut->iStar[i] = rc->iStar[i];
+	if (dualStableFlag) *dualStableFlag = stable;
+	freeOneCut(rc);
+	return 0;
+}
+
+/* Same shape as sdgpu_sd_cut.  The reference only exposes cummOld/cummAll as their ratio, so on return
+ * cut->cummOld holds that ratio and cut->cummAll is 1.0 (0/0 stays NaN as in cuts.c:172). */
+int sdref_sd_cut(void *vc, const double *Xvect, int numSamples, int pi_eval_flag, double lb, sdgpu_cut *cut) {
+	double ratio[1] = { 0.0 };
+	int st;
+	/* SCAN_LEN = 1: slot numSamples % 1 == 0; "numSamples - start > SCAN_LEN" would call calcVariance over one
+	 * element (a no-op loop), harmless. */
+	st = sdref_sd_cut_cfg(vc, Xvect, numSamples, pi_eval_flag != 0, -1, 1, 1, lb, cut, ratio, NULL);
+	cut->cummOld = pi_eval_flag ? ratio[0] : 0.0;
+	cut->cummAll = pi_eval_flag ? 1.0 : 0.0;
+	return st;
+}
+
+double sdref_calc_variance(double *x, int scanLen) {
+	config.SCAN_LEN = scanLen;
+	return calcVariance(x, NULL, NULL, 0);
+}
+
+int sdref_cut_heights(void *vc, int n, const double *alpha, const double *beta, const int32_t *numSamples,
+		const double *alphaIncumb, int currIter, const double *xk, double lb, double *height, double *etaCoef, double *rhs) {
+	refCtx *c = (refCtx *) vc;
+	cutsType *cuts = newCuts(n > 0 ? n : 1);
+	int i, j, best = SDGPU_NONE, n1 = c->num.prevCols;
+	double Sm = -INF;
+	for (i = 0; i < n; i++) {
+		cuts->vals[i] = newCut(n1, 0, numSamples[i]);
+		cuts->vals[i]->alpha = alpha[i];
+		for (j = 0; j <= n1; j++) cuts->vals[i]->beta[j] = beta[(size_t) i * (n1 + 1) + j];
+		cuts->cnt++;
+	}
+	for (i = 0; i < n; i++) {
+		double ht = cutHeight(cuts->vals[i], currIter, (dVector) xk, n1, lb);
+		if (height) height[i] = ht;
+		if (Sm < ht) { Sm = ht; best = i; }     /* order of maxCutHeight cuts.c:201-206 */
+		/* the two aging formulas are inline expressions in master.c:152 and master.c:174 (CPLEX calls around them) */
+		if (etaCoef) etaCoef[i] = (double) (currIter) / (double) numSamples[i];
+		if (rhs) rhs[i] = (alphaIncumb ? alphaIncumb[i] : 0.0) + ((double) currIter / (double) numSamples[i] - 1) * lb;
+	}
+	if (n > 0) {
+		double m = maxCutHeight(cuts, currIter, (dVector) xk, n1, lb);
+		if (best >= 0 && height && m != height[best]) best = SDGPU_ERR;
+	}
+	freeCutsType(cuts, false);
+	return best;
+}
+
+int sdref_reform_cut(void *vc, const int32_t *iStar, int omegaCnt, const int32_t *observ, int k, int lbType, int lb,
+		double *alpha, double *beta) {
+	refCtx *c = (refCtx *) vc;
+	cutsType *g = newCuts(1);
+	int i;
+	g->vals[0] = newCut(c->num.prevCols, omegaCnt, k);
+	for (i = 0; i < omegaCnt; i++) g->vals[0]->iStar[i] = iStar[i];
+	g->cnt = 1;
+	reformCuts(c->basis, c->sigma, c->delta, c->omega, &c->num, &c->coord, g, (int *) observ, k, lbType, lb, c->num.prevCols);
+	*alpha = g->vals[0]->alpha;
+	for (i = 0; i <= c->num.prevCols; i++) beta[i] = g->vals[0]->beta[i];
+	freeCutsType(g, false);
+	return 0;
+}
+
+int sdref_get_omega(void *vc, int idx, double *vals, int *weight) {
+	refCtx *c = (refCtx *) vc;
+	int i;
+	if (idx < 0 || idx >= c->omega->cnt) return SDGPU_ERR;
+	if (vals) for (i = 1; i <= c->num.numRV; i++) vals[i] = c->omega->vals[idx][i];
+	if (weight) *weight = c->omega->weights[idx];
+	return 0;
+}
+
+int sdref_get_lambda(void *vc, int idx, double *vals) {
+	refCtx *c = (refCtx *) vc;
+	int i;
+	if (idx < 0 || idx >= c->lambda->cnt) return SDGPU_ERR;
+	for (i = 1; i <= c->num.rvRowCnt; i++) vals[i] = c->lambda->vals[idx][i];
+	return 0;
+}
+
+int sdref_get_sigma(void *vc, int idx, double *pib, double *piC, int *lambdaIdx, int *ck) {
+	refCtx *c = (refCtx *) vc;
+	int i;
+	if (idx < 0 || idx >= c->sigma->cnt) return SDGPU_ERR;
+	if (pib) *pib = c->sigma->vals[idx].pib;
+	if (piC) for (i = 1; i <= c->num.cntCcols; i++) piC[i] = c->sigma->vals[idx].piC[i];
+	if (lambdaIdx) *lambdaIdx = c->sigma->lambdaIdx[idx];
+	if (ck) *ck = c->sigma->ck[idx];
+	return 0;
+}
+
+int sdref_get_delta(void *vc, int lambdaIdx, int obsIdx, double *pib, double *piC) {
+	refCtx *c = (refCtx *) vc;
+	int i;
+	if (lambdaIdx < 0 || lambdaIdx >= c->lambda->cnt || obsIdx < 0 || obsIdx >= c->omega->cnt) return SDGPU_ERR;
+	if (pib) *pib = c->delta->vals[lambdaIdx][obsIdx].pib;
+	if (piC && c->num.rvCOmCnt > 0) for (i = 1; i <= c->num.rvCOmCnt; i++) piC[i] = c->delta->vals[lambdaIdx][obsIdx].piC[i];
+	return 0;
+}
+
+/* ---- link-time stubs for host functions cuts.c / optimal.c name but the oracle never reaches -------- */
+#define NOT_IN_ORACLE(name) do { fprintf(stderr, "sdref :: %s() is host/CPLEX code outside the oracle\n", name); abort(); } while (0)
+int solveSubprob(probType *prob, oneProblem *subproblem, dVector Xvect, basisType *basis, lambdaType *lambda, sigmaType *sigma,
+		deltaType *delta, int deltaRowLength, omegaType *omega, int omegaIdx, bool *newOmegaFlag, int currentIter, double TOLERANCE,
+		bool *subFeasFlag, bool *newBasisFlag, double *subprobTime, double *argmaxTime) { NOT_IN_ORACLE("solveSubprob"); return 1; }
+int solveQPMaster(numType *num, sparseVector *dBar, cellType *cell, double lb) { NOT_IN_ORACLE("solveQPMaster"); return 1; }
+int addCut2Master(oneProblem *master, oneCut *cut, dVector vectX, int lenX) { NOT_IN_ORACLE("addCut2Master"); return 1; }
+int replaceIncumbent(probType *prob, cellType *cell, double candidEst) { NOT_IN_ORACLE("replaceIncumbent"); return 1; }
+int changeQPproximal(LPptr lp, int numCols, double sigma) { NOT_IN_ORACLE("changeQPproximal"); return 1; }
