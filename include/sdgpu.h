@@ -123,12 +123,17 @@ int  sdgpu_calc_sigma(sdgpu_ctx *ctx, const double *pi, double mubBar, int idxLa
 /* calcDelta stocUpdate.c:196-257: newOmegaFlag != 0 fills column elemIdx for every lambda (case I),
  * else fills row elemIdx for every observation (case II). */
 int  sdgpu_calc_delta(sdgpu_ctx *ctx, int newOmegaFlag, int elemIdx);
+/* calcDelta for every (lambda, observation) pair of the block [l0,l1) x [o0,o1): the bulk form used after the
+ * bulk loaders below (same per-cell arithmetic and order as the one-at-a-time appends). */
+int  sdgpu_calc_delta_block(sdgpu_ctx *ctx, int64_t l0, int64_t l1, int64_t o0, int64_t o1);
 /* calcLambda + calcSigma + calcDelta(row) for one dual vector in one device round trip
  * (stocUpdate.c:78-85 / :90-97).  Outputs may be NULL. */
 int  sdgpu_update_dual(sdgpu_ctx *ctx, const double *pi, double mubBar, int currentIter, double tol,
                        int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag);
-/* bulk load of n dual vectors (rows of rows+1 doubles) through the same find-or-append path but
- * without per-vector host round trips; idx outputs may be NULL.  mubBar may be NULL (zeros). */
+/* bulk load of n dual vectors (rows of rows+1 doubles).  tol >= 0: the same find-or-append chain as
+ * sdgpu_update_dual, vector after vector, without host round trips in between.  tol < 0: synthetic loader,
+ * no dedup scan -- vector i becomes lambda row and sigma row (count + i) and NO delta row is computed
+ * (call sdgpu_calc_delta_block afterwards).  idx outputs and mubBar / iters may be NULL. */
 int  sdgpu_update_dual_bulk(sdgpu_ctx *ctx, int64_t n, const double *pis, const double *mubBar,
                             const int32_t *iters, double tol, int32_t *lambdaIdx, int32_t *sigmaIdx);
 
@@ -196,6 +201,8 @@ int  sdgpu_get_omega(sdgpu_ctx *ctx, int idx, double *vals /* [numRV+1] */, int 
 int  sdgpu_get_lambda(sdgpu_ctx *ctx, int idx, double *vals /* [rvRowCnt+1] */);
 int  sdgpu_get_sigma(sdgpu_ctx *ctx, int idx, double *pib, double *piC /* [cntCcols+1] */, int *lambdaIdx, int *ck);
 int  sdgpu_get_delta(sdgpu_ctx *ctx, int lambdaIdx, int obsIdx, double *pib, double *piC /* [rvCOmCnt+1] */);
+/* one plane (0 = pib, 1..rvCOmCnt = piC) of the block [l0,l1) x [o0,o1) of delta, row-major [l1-l0][o1-o0] */
+int  sdgpu_get_delta_block(sdgpu_ctx *ctx, int64_t l0, int64_t l1, int64_t o0, int64_t o1, int plane, double *out);
 /* device-resident iStar of the most recent cut (int32[omegaCnt]) for callers that keep it on the GPU */
 int  sdgpu_last_istar_device(sdgpu_ctx *ctx, void **devPtr, int *len);
 

@@ -295,6 +295,24 @@ int sdo_calc_delta(oracleCtx *c, int newOmegaFlag, int elemIdx) {
 	return 0;
 }
 
+int sdo_calc_delta_block(oracleCtx *c, int64_t l0, int64_t l1, int64_t o0, int64_t o1) {
+	int Q = c->num.rvCOmCnt;
+	if (l0 < 0 || l1 > c->lambdaCnt || o0 < 0 || o1 > c->omegaCnt || l0 > l1 || o0 > o1) return fail("calc_delta_block: block out of range");
+	double *scratch = (double *) calloc((size_t) c->num.prevCols + 1, sizeof(double));
+	for (int64_t l = l0; l < l1; l++) {
+		if (!c->deltaPib[l]) {
+			c->deltaPib[l] = (double *) calloc((size_t) c->caps.maxOmega, sizeof(double));
+			c->deltaPiC[l] = Q ? (double *) calloc((size_t) c->caps.maxOmega * (Q + 1), sizeof(double)) : NULL;
+		}
+		double *full = expandLambda(c, l);
+		for (int64_t o = o0; o < o1; o++)
+			deltaCell(c, full, o, &c->deltaPib[l][o], Q ? c->deltaPiC[l] + (size_t) o * (Q + 1) : NULL, scratch);
+		free(full);
+	}
+	free(scratch);
+	return 0;
+}
+
 /* stocUpdate.c:78-85 (and :90-97 for a phi column) */
 int sdo_update_dual(oracleCtx *c, const double *pi, double mubBar, int currentIter, double tol,
 		int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag) {
@@ -314,9 +332,19 @@ int sdo_update_dual(oracleCtx *c, const double *pi, double mubBar, int currentIt
 int sdo_update_dual_bulk(oracleCtx *c, int64_t n, const double *pis, const double *mubBar, const int32_t *iters,
 		double tol, int32_t *lambdaIdx, int32_t *sigmaIdx) {
 	for (int64_t i = 0; i < n; i++) {
-		int li, si;
-		int r = sdo_update_dual(c, pis + (size_t) i * (c->num.rows + 1), mubBar ? mubBar[i] : 0.0, iters ? iters[i] : (int) i + 1,
-				tol, &li, NULL, &si, NULL);
+		int li, si, r = 0;
+		const double *pi = pis + (size_t) i * (c->num.rows + 1);
+		if (tol < 0.0) {        /* synthetic loader: append without the dedup scans and without the delta row */
+			int nl = 1, ns = 1;
+			if (c->lambdaCnt >= c->caps.maxLambda) return fail("lambda capacity exceeded");
+			double *row = lambdaRow(c, c->lambdaCnt);
+			for (int k = 1; k <= c->num.rvRowCnt; k++) row[k] = pi[c->rvRows[k]];
+			li = (int) c->lambdaCnt++;
+			si = sdo_calc_sigma(c, pi, mubBar ? mubBar[i] : 0.0, li, nl, iters ? iters[i] : (int) i + 1, 0.0, &ns);
+			if (si < 0) return si;
+		}
+		else
+			r = sdo_update_dual(c, pi, mubBar ? mubBar[i] : 0.0, iters ? iters[i] : (int) i + 1, tol, &li, NULL, &si, NULL);
 		if (r < 0) return r;
 		if (lambdaIdx) lambdaIdx[i] = li;
 		if (sigmaIdx) sigmaIdx[i] = si;
@@ -652,6 +680,15 @@ int sdo_get_sigma(oracleCtx *c, int idx, double *pib, double *piC, int *lambdaId
 	if (ck) *ck = c->sigmaCk[idx];
 	return 0;
 }
+int sdo_get_delta_block(oracleCtx *c, int64_t l0, int64_t l1, int64_t o0, int64_t o1, int plane, double *out) {
+	int Q = c->num.rvCOmCnt;
+	if (l0 < 0 || l1 > c->lambdaCnt || o0 < 0 || o1 > c->omegaCnt || l0 > l1 || o0 > o1 || plane < 0 || plane > Q) return fail("get_delta_block: out of range");
+	for (int64_t l = l0; l < l1; l++)
+		for (int64_t o = o0; o < o1; o++)
+			out[(size_t) (l - l0) * (o1 - o0) + (o - o0)] = plane == 0 ? c->deltaPib[l][o] : c->deltaPiC[l][(size_t) o * (Q + 1) + plane];
+	return 0;
+}
+
 int sdo_get_delta(oracleCtx *c, int lambdaIdx, int obsIdx, double *pib, double *piC) {
 	int Q = c->num.rvCOmCnt;
 	if (lambdaIdx < 0 || lambdaIdx >= c->lambdaCnt || obsIdx < 0 || obsIdx >= c->omegaCnt) return fail("get_delta: index out of range");

@@ -188,6 +188,8 @@ class Api:
             "calc_lambda": (i, [vp, c_f64p, d, c_intp]),
             "calc_sigma": (i, [vp, c_f64p, d, i, i, i, d, c_intp]),
             "calc_delta": (i, [vp, i, i]),
+            "calc_delta_block": (i, [vp, i64, i64, i64, i64]),
+            "get_delta_block": (i, [vp, i64, i64, i64, i64, i, c_f64p]),
             "update_dual": (i, [vp, c_f64p, d, i, d, c_intp, c_intp, c_intp, c_intp]),
             "update_dual_bulk": (i, [vp, i64, c_f64p, c_f64p, c_i32p, d, c_i32p, c_i32p]),
             "basis_append": (i, [vp, i, i, i, c_i32p, c_i32p]),
@@ -305,6 +307,14 @@ class Tables:
 
     def calc_delta(self, newOmegaFlag, elemIdx):
         self._check(self._call("calc_delta", int(newOmegaFlag), elemIdx), "calc_delta")
+
+    def calc_delta_block(self, l0, l1, o0, o1):
+        self._check(self._call("calc_delta_block", l0, l1, o0, o1), "calc_delta_block")
+
+    def get_delta_block(self, l0, l1, o0, o1, plane=0):
+        out = np.zeros((l1 - l0, o1 - o0))
+        self._check(self._call("get_delta_block", l0, l1, o0, o1, plane, _pf64(out)), "get_delta_block")
+        return out
 
     def update_dual(self, pi, mubBar, currentIter, tol):
         p = _f64(pi)

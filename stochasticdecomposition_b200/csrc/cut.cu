@@ -1,0 +1,820 @@
+// cut.cu -- SD cut formation on the device: per-observation argmax over all stored bases (computeIstar,
+// stocUpdate.c:142-190) fused with the weighted reduction into (alpha, beta) and the dual-stability sums
+// (SDCut, cuts.c:91-194), cut heights / aging (cuts.c:197-227, master.c:152,174) and reformCuts
+// (optimal.c:187-236).  Citations are file:line under /root/reference/twoSD_src.
+//
+// Pipeline of one cut (all on the context's stream, one host sync at the end):
+//   k_picbarx      piCbarX[s] = sigma.piC[s] . x[CCols]                      cuts.c:105-106
+//   k_basis_desc   per basis: (sigma.pib, piCbarX, lambda row, window)       stocUpdate.c:151-167
+//   k_sweep_*      2-D grid (observation tile x basis chunk): stream the delta tile, keep running
+//                  (max, first index) per observation for the old and the new window   stocUpdate.c:161-184
+//   k_cut_merge    merge chunk maxima in index order, pick iStar (cuts.c:124-125,136-140), accumulate
+//                  w*(sigma.pib + delta.pib), w*sigma.piC, w*delta.piC, cummOld, cummAll per tile   cuts.c:127-168
+//   k_cut_finalize sum tile partials in tile order, scatter into beta          cuts.c:155-167
+//   [NCCL all-reduce of n1+4 doubles when observations are sharded]
+//   k_cut_normalise alpha/k, beta/k, beta[0] = 1                               cuts.c:184-188
+//
+// Scores are evaluated with the reference's operation order and without FMA contraction, so they are
+// bit-identical to the CPU path; (max, index) merges keep the LOWEST index among equal maxima (strict '>'
+// in stocUpdate.c:178) and the old window wins ties against the new one (cuts.c:125): iStar is bit-exact.
+#include <cfloat>
+#include <climits>
+#include <cstring>
+#include <algorithm>
+
+#include "sdgpu_internal.cuh"
+
+// ======================================================================================================
+// small device helpers
+// ======================================================================================================
+__device__ __forceinline__ double2 ld_stream_f64x2(const double *p) {
+	double2 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+	return v;
+}
+
+__device__ __forceinline__ double sd_warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0
+__device__ __forceinline__ double sd_block_sum(double v, double *s_red) {
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	v = sd_warp_sum(v);
+	__syncthreads();
+	if (lane == 0) s_red[warp] = v;
+	__syncthreads();
+	double t = 0.0;
+	if (warp == 0) {
+		t = lane < nw ? s_red[lane] : 0.0;
+		t = sd_warp_sum(t);
+	}
+	return t;
+}
+
+// ======================================================================================================
+// K5: piCbarX, and the per-basis descriptors of the sweep
+// ======================================================================================================
+__global__ void k_picbarx(const double *__restrict__ piCk, int64_t SP, int n1c, const int32_t *__restrict__ CCols,
+		const double *__restrict__ x, int n1, int sigmaCnt, double *__restrict__ out) {
+	extern __shared__ double s_x[];          // x gathered at CCols, in k order
+	for (int k = threadIdx.x; k < n1c; k += blockDim.x) s_x[k] = x[CCols[k]];
+	__syncthreads();
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= sigmaCnt) return;
+	double acc = 0.0;                        // vXv: left to right from 0.0, product and sum rounded separately
+	for (int k = 0; k < n1c; k++) acc = __dadd_rn(acc, __dmul_rn(piCk[(size_t) k * SP + s], s_x[k]));
+	out[s] = acc;
+}
+
+// window: 0 = not eligible, 1 = "old" (or the only window when pi_eval is off), 2 = "new"   stocUpdate.c:147-163
+__global__ void k_basis_desc(const int32_t *__restrict__ bCk, const int32_t *__restrict__ bFeas, const int32_t *__restrict__ bTermStart,
+		const int32_t *__restrict__ tSigma, const double *__restrict__ sigmaPib, const int32_t *__restrict__ sigmaLam,
+		const double *__restrict__ piCbarX, int basisCnt, int split, int cutoff,
+		double *__restrict__ descA, double *__restrict__ descC, int32_t *__restrict__ descRow, int32_t *__restrict__ descWin) {
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= basisCnt) return;
+	int s = tSigma[bTermStart[b]];
+	int ck = bCk[b], win = 0;
+	if (bFeas[b]) {
+		// "old": basisLow = -INT_MAX < ck <= basisUp = cutoff; "new": cutoff < ck <= INT_MAX (only asked for when split)
+		if (ck <= cutoff) win = (ck > -INT_MAX) ? 1 : 0;
+		else win = split ? 2 : 0;
+	}
+	descA[b] = sigmaPib[s]; descC[b] = piCbarX[s]; descRow[b] = sigmaLam[s]; descWin[b] = win;
+}
+
+// ======================================================================================================
+// K6: the sweep.  Variant 1: plain streaming loads (LDG.128, 8 rows in flight per thread).
+// ======================================================================================================
+struct SweepArgs {
+	const double *delta; int64_t Dcap; int Q;
+	const double *descA, *descC; const int32_t *descRow, *descWin;
+	int basisCnt, chunkSize, nChunks;
+	const uint8_t *mask; int64_t Bcap;
+	const double *x; const int32_t *rvCOmCols;
+	double *partV; int32_t *partI; int64_t NP;
+};
+
+#define SW_BATCH 256    // basis descriptors staged per shared-memory refill
+#define SW_UNROLL 8     // delta rows in flight per thread
+
+template <bool HAS_Q, bool HAS_MASK>
+__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a) {
+	__shared__ double2 s_ac[SW_BATCH];       // (sigma.pib, piCbarX)
+	__shared__ int2 s_rw[SW_BATCH];          // (lambda row, window)
+	__shared__ double s_xq[HAS_Q ? 64 : 1];
+	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride + 2 * tid;
+	if (HAS_Q) {
+		for (int j = tid; j < a.Q; j += blockDim.x) s_xq[j] = a.x[a.rvCOmCols[j]];
+	}
+	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
+	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+
+	for (int base = b0; base < b1; base += SW_BATCH) {
+		__syncthreads();
+		{
+			int b = base + tid;
+			bool ok = b < b1;
+			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
+			s_rw[tid] = ok ? make_int2(a.descRow[b], a.descWin[b]) : make_int2(0, 0);
+		}
+		__syncthreads();
+		const int n = min(SW_BATCH, b1 - base);
+		for (int j = 0; j < n; j += SW_UNROLL) {
+			double2 d[SW_UNROLL];
+#pragma unroll
+			for (int u = 0; u < SW_UNROLL; u++)          // rows past the end alias row s_rw[..].x == 0 and are ignored (window 0)
+				d[u] = ld_stream_f64x2(tileBase + (size_t) s_rw[j + u].x * rowStride);
+#pragma unroll
+			for (int u = 0; u < SW_UNROLL; u++) {
+				const int win = s_rw[j + u].y;
+				if (win == 0) continue;
+				const double2 ac = s_ac[j + u];
+				const int b = base + j + u;
+				// ((sigma.pib + delta.pib) - piCbarX)   stocUpdate.c:174
+				double s0 = __dsub_rn(__dadd_rn(ac.x, d[u].x), ac.y);
+				double s1 = __dsub_rn(__dadd_rn(ac.x, d[u].y), ac.y);
+				if (HAS_Q) {                         // - delta.piC . x[rvCOmCols]   stocUpdate.c:175
+					const double *pc = tileBase + (size_t) s_rw[j + u].x * rowStride;
+					double dx0 = 0.0, dx1 = 0.0;
+					for (int q = 0; q < a.Q; q++) {
+						double2 p = ld_stream_f64x2(pc + (size_t) (1 + q) * SD_TILE_W);
+						dx0 = __dadd_rn(dx0, __dmul_rn(p.x, s_xq[q]));
+						dx1 = __dadd_rn(dx1, __dmul_rn(p.y, s_xq[q]));
+					}
+					s0 = __dsub_rn(__dadd_rn(0.0, s0), dx0);
+					s1 = __dsub_rn(__dadd_rn(0.0, s1), dx1);
+				}
+				bool f0 = true, f1 = true;
+				if (HAS_MASK) {
+					uchar2 m = *reinterpret_cast<const uchar2 *>(a.mask + ((size_t) tile * a.Bcap + b) * SD_TILE_W + 2 * tid);
+					f0 = m.x != 0; f1 = m.y != 0;
+				}
+				if (win == 1) {
+					if (f0 && s0 > oV0) { oV0 = s0; oI0 = b; }
+					if (f1 && s1 > oV1) { oV1 = s1; oI1 = b; }
+				}
+				else {
+					if (f0 && s0 > nV0) { nV0 = s0; nI0 = b; }
+					if (f1 && s1 > nV1) { nV1 = s1; nI1 = b; }
+				}
+			}
+		}
+	}
+	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
+	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
+	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
+	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
+	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
+	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
+}
+
+// General sweep: bases with phi columns (random cost, multi-term score) and/or the feasibility mask.
+//   arg = sum_t m_t * ((sigma.pib[s_t] + delta.pib[l_t][o]) - piCbarX[s_t]) - m_t * (delta.piC[l_t][o] . x)   stocUpdate.c:164-176
+struct SweepGenArgs {
+	const double *delta; int64_t Dcap; int Q;
+	const int32_t *bTermStart, *tSigma, *tOmega, *descWin;
+	const double *sigmaPib, *piCbarX; const int32_t *sigmaLam;
+	const double *omega; int64_t NP; int rvOffset2;
+	int basisCnt, chunkSize, nChunks;
+	const uint8_t *mask; int64_t Bcap;
+	const double *x; const int32_t *rvCOmCols;
+	double *partV; int32_t *partI;
+};
+
+__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general(SweepGenArgs a) {
+	__shared__ double s_xq[64];
+	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	for (int j = tid; j < a.Q; j += blockDim.x) s_xq[j] = a.x[a.rvCOmCols[j]];
+	__syncthreads();
+	double bestV[2][2] = {{-DBL_MAX, -DBL_MAX}, {-DBL_MAX, -DBL_MAX}};
+	int bestI[2][2] = {{-1, -1}, {-1, -1}};
+	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride;
+	for (int b = b0; b < b1; b++) {
+		const int win = a.descWin[b];
+		if (win == 0) continue;
+		const int ts = a.bTermStart[b], te = a.bTermStart[b + 1];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int w = 2 * tid + h;
+			const size_t o = (size_t) tile * SD_TILE_W + w;
+			if (a.mask && !a.mask[((size_t) tile * a.Bcap + b) * SD_TILE_W + w]) continue;
+			double arg = 0.0;
+			for (int t = ts; t < te; t++) {
+				const int s = a.tSigma[t], l = a.sigmaLam[s];
+				const double m = (t == ts) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+				const double *cell = tileBase + (size_t) l * rowStride + w;
+				arg = __dadd_rn(arg, __dmul_rn(m, __dsub_rn(__dadd_rn(a.sigmaPib[s], cell[0]), a.piCbarX[s])));
+				double dx = 0.0;
+				for (int q = 0; q < a.Q; q++) dx = __dadd_rn(dx, __dmul_rn(cell[(size_t) (1 + q) * SD_TILE_W], s_xq[q]));
+				arg = __dsub_rn(arg, __dmul_rn(m, dx));
+			}
+			if (win == 1) { if (arg > bestV[0][h]) { bestV[0][h] = arg; bestI[0][h] = b; } }
+			else          { if (arg > bestV[1][h]) { bestV[1][h] = arg; bestI[1][h] = b; } }
+		}
+	}
+	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
+#pragma unroll
+	for (int wdw = 0; wdw < 2; wdw++) {
+		const size_t at = ((size_t) wdw * a.nChunks + chunk) * a.NP + o;
+		*reinterpret_cast<double2 *>(a.partV + at) = make_double2(bestV[wdw][0], bestV[wdw][1]);
+		*reinterpret_cast<int2 *>(a.partI + at) = make_int2(bestI[wdw][0], bestI[wdw][1]);
+	}
+}
+
+// ======================================================================================================
+// merge + accumulate (one CTA per observation tile, one thread per observation)
+// ======================================================================================================
+struct MergeArgs {
+	const double *partV; const int32_t *partI; int nChunks; int64_t NP;
+	int omegaCnt, pi_eval; double lb;
+	const int32_t *omegaW; const double *omega; int rvOffset2;
+	const double *delta; int64_t Dcap; int Q;
+	const double *sigmaPib, *sigmaPiCr; const int32_t *sigmaLam; int sigmaCnt, n1c, n1cP;
+	const int32_t *bTermStart, *tSigma, *tOmega;
+	int randCost;                 // num->rvdOmCnt > 0: the cuts.c:142-159 branch
+	int32_t *iStar; double *tilePart; int P;
+};
+
+#define MG_THREADS SD_TILE_W
+
+__global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
+	__shared__ int s_istar[SD_TILE_W];
+	__shared__ int s_w[SD_TILE_W];
+	__shared__ double s_red[32];
+	extern __shared__ double s_dyn[];        // [groups][n1c] partial sums of the sigma.piC part
+	const int tile = blockIdx.x, tid = threadIdx.x;
+	const int64_t o = (int64_t) tile * SD_TILE_W + tid;
+	const bool valid = o < a.omegaCnt;
+	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride + tid;
+
+	double oldV = -DBL_MAX, newV = -DBL_MAX;
+	int oldI = -1, newI = -1, istar = -1, wgt = 0;
+	double tAlpha = 0.0, tOld = 0.0, tAll = 0.0, tMiss = 0.0;
+	if (valid) {
+		for (int c = 0; c < a.nChunks; c++) {            // ascending chunks = ascending basis index: strict '>' keeps the first
+			double v = a.partV[((size_t) 0 * a.nChunks + c) * a.NP + o];
+			if (v > oldV) { oldV = v; oldI = a.partI[((size_t) 0 * a.nChunks + c) * a.NP + o]; }
+		}
+		wgt = a.omegaW[o];
+		if (a.pi_eval) {
+			for (int c = 0; c < a.nChunks; c++) {
+				double v = a.partV[((size_t) 1 * a.nChunks + c) * a.NP + o];
+				if (v > newV) { newV = v; newI = a.partI[((size_t) 1 * a.nChunks + c) * a.NP + o]; }
+			}
+			double argmax = fmax(oldV, newV);                     // cuts.c:124
+			istar = (newV > oldV) ? newI : oldI;                  // cuts.c:125 (an empty window carries index -1)
+			tOld = fmax(oldV - a.lb, 0.0) * wgt;                  // cuts.c:127
+			tAll = fmax(argmax - a.lb, 0.0) * wgt;                // cuts.c:128
+		}
+		else
+			istar = oldI;                                         // cuts.c:132
+		a.iStar[o] = istar;
+		if (istar < 0) tMiss = 1.0;                               // cuts.c:136-139
+		else if (!a.randCost) {                                   // cuts.c:160-162: the BASIS index doubles as the sigma index
+			if (istar >= a.sigmaCnt) { tMiss = 1.0e9; istar = -1; }
+			else {
+				int l = a.sigmaLam[istar];
+				tAlpha = __dadd_rn(__dmul_rn(a.sigmaPib[istar], (double) wgt), __dmul_rn(tileBase[(size_t) l * rowStride], (double) wgt));
+			}
+		}
+		else {                                                    // cuts.c:143-152
+			for (int t = a.bTermStart[istar]; t < a.bTermStart[istar + 1]; t++) {
+				int s = a.tSigma[t], l = a.sigmaLam[s];
+				double m = (t == a.bTermStart[istar]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+				tAlpha = __dadd_rn(tAlpha, __dmul_rn(__dmul_rn((double) wgt, m), __dadd_rn(a.sigmaPib[s], tileBase[(size_t) l * rowStride])));
+			}
+		}
+	}
+	s_istar[tid] = valid ? istar : -1;
+	s_w[tid] = wgt;
+	double *out = a.tilePart + (size_t) tile * a.P;
+	double r;
+	r = sd_block_sum(tAlpha, s_red); if (tid == 0) out[0] = r;
+	r = sd_block_sum(tOld, s_red);   if (tid == 0) out[1] = r;
+	r = sd_block_sum(tAll, s_red);   if (tid == 0) out[2] = r;
+	r = sd_block_sum(tMiss, s_red);  if (tid == 0) out[3] = r;
+
+	// delta.piC part of beta: one block sum per random T element   cuts.c:156-157 / :166-167
+	for (int q = 0; q < a.Q; q++) {
+		double v = 0.0;
+		if (valid && istar >= 0) {
+			if (!a.randCost)
+				v = __dmul_rn(tileBase[(size_t) a.sigmaLam[istar] * rowStride + (size_t) (1 + q) * SD_TILE_W], (double) wgt);
+			else
+				for (int t = a.bTermStart[istar]; t < a.bTermStart[istar + 1]; t++) {
+					int s = a.tSigma[t], l = a.sigmaLam[s];
+					double m = (t == a.bTermStart[istar]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+					v = __dadd_rn(v, __dmul_rn(__dmul_rn((double) wgt, m), tileBase[(size_t) l * rowStride + (size_t) (1 + q) * SD_TILE_W]));
+				}
+		}
+		r = sd_block_sum(v, s_red);
+		if (tid == 0) out[4 + a.n1c + q] = r;
+	}
+
+	// sigma.piC part of beta: thread (group g, column k) walks the observations of its group in order   cuts.c:154-155 / :164-165
+	__syncthreads();
+	if (a.n1c > 0) {
+		const int kp = ((a.n1c + 31) / 32) * 32;
+		const int groups = max(1, MG_THREADS / kp);
+		const int g = tid / kp, k = tid % kp;
+		if (g < groups && k < a.n1c) {
+			const int per = (SD_TILE_W + groups - 1) / groups;
+			const int w0 = g * per, w1 = min(SD_TILE_W, w0 + per);
+			double acc = 0.0;
+			for (int w = w0; w < w1; w++) {
+				const int is = s_istar[w];
+				if (is < 0) continue;
+				if (!a.randCost)
+					acc = __dadd_rn(acc, __dmul_rn(a.sigmaPiCr[(size_t) is * a.n1cP + k], (double) s_w[w]));
+				else {
+					const int64_t ow = (int64_t) tile * SD_TILE_W + w;
+					for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
+						int s = a.tSigma[t];
+						double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + ow];
+						acc = __dadd_rn(acc, __dmul_rn(__dmul_rn((double) s_w[w], m), a.sigmaPiCr[(size_t) s * a.n1cP + k]));
+					}
+				}
+			}
+			s_dyn[g * a.n1c + k] = acc;
+		}
+		__syncthreads();
+		if (tid < a.n1c) {
+			double acc = 0.0;
+			for (int gg = 0; gg < groups; gg++) acc = __dadd_rn(acc, s_dyn[gg * a.n1c + tid]);
+			out[4 + tid] = acc;
+		}
+	}
+}
+
+// sum the tile partials in tile order and scatter into the un-normalised cut vector
+// partial = [alpha, beta[1..n1], cummOld, cummAll, missing]
+__global__ void k_cut_finalize(const double *__restrict__ tilePart, int nTiles, int P, int n1, int n1c, int Q,
+		const int32_t *__restrict__ CCols, const int32_t *__restrict__ qCols, double *__restrict__ partial) {
+	extern __shared__ double s_tot[];
+	for (int p = threadIdx.x; p < P; p += blockDim.x) {
+		double acc = 0.0;
+		for (int t = 0; t < nTiles; t++) acc = __dadd_rn(acc, tilePart[(size_t) t * P + p]);
+		s_tot[p] = acc;
+	}
+	for (int c = threadIdx.x; c <= n1 + 3; c += blockDim.x) partial[c] = 0.0;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		partial[0] = s_tot[0];
+		for (int k = 0; k < n1c; k++) partial[CCols[k]] = __dadd_rn(partial[CCols[k]], s_tot[4 + k]);          // cuts.c:155,165
+		for (int q = 0; q < Q; q++) partial[qCols[q]] = __dadd_rn(partial[qCols[q]], s_tot[4 + n1c + q]);      // cuts.c:157,167
+		partial[n1 + 1] = s_tot[1]; partial[n1 + 2] = s_tot[2]; partial[n1 + 3] = s_tot[3];
+	}
+}
+
+// cuts.c:184-188
+__global__ void k_cut_normalise(const double *__restrict__ partial, int n1, int numSamples, double *__restrict__ out) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c > n1 + 3) return;
+	if (c == 0) out[0] = partial[0] / numSamples;
+	else if (c <= n1) out[c] = partial[c] / numSamples;
+	else out[c] = partial[c];
+}
+
+// ======================================================================================================
+// single-observation computeIstar (debug / STOCH_CHECK path)   stocUpdate.c:142-190
+// ======================================================================================================
+__global__ void k_istar_one(SweepGenArgs a, int obs, int isNew, double *outV, int32_t *outI) {
+	__shared__ double s_v[256];
+	__shared__ int s_i[256];
+	const int tile = obs / SD_TILE_W, w = obs % SD_TILE_W;
+	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride;
+	double best = -DBL_MAX; int bi = -1;
+	for (int b = threadIdx.x; b < a.basisCnt; b += blockDim.x) {
+		const int win = a.descWin[b];
+		if (win == 0) continue;
+		if ((isNew && win != 2) || (!isNew && win != 1)) continue;
+		if (a.mask && !a.mask[((size_t) tile * a.Bcap + b) * SD_TILE_W + w]) continue;
+		double arg = 0.0;
+		const int ts = a.bTermStart[b], te = a.bTermStart[b + 1];
+		for (int t = ts; t < te; t++) {
+			const int s = a.tSigma[t], l = a.sigmaLam[s];
+			const double m = (t == ts) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + obs];
+			const double *cell = tileBase + (size_t) l * rowStride + w;
+			arg = __dadd_rn(arg, __dmul_rn(m, __dsub_rn(__dadd_rn(a.sigmaPib[s], cell[0]), a.piCbarX[s])));
+			double dx = 0.0;
+			for (int q = 0; q < a.Q; q++) dx = __dadd_rn(dx, __dmul_rn(cell[(size_t) (1 + q) * SD_TILE_W], a.x[a.rvCOmCols[q]]));
+			arg = __dsub_rn(arg, __dmul_rn(m, dx));
+		}
+		if (arg > best) { best = arg; bi = b; }          // ascending b within a thread: first maximiser kept
+	}
+	s_v[threadIdx.x] = best; s_i[threadIdx.x] = bi;
+	__syncthreads();
+	for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+		if (threadIdx.x < st) {
+			double v2 = s_v[threadIdx.x + st]; int i2 = s_i[threadIdx.x + st];
+			double v1 = s_v[threadIdx.x]; int i1 = s_i[threadIdx.x];
+			bool take = (i2 >= 0) && (i1 < 0 || v2 > v1 || (v2 == v1 && i2 < i1));      // greater value, else lower index
+			if (take) { s_v[threadIdx.x] = v2; s_i[threadIdx.x] = i2; }
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { *outV = s_v[0]; *outI = (s_v[0] == -DBL_MAX) ? -1 : s_i[0]; }
+}
+
+// ======================================================================================================
+// cut heights / aging and reformCuts
+// ======================================================================================================
+__global__ void k_cut_heights(int n, const double *__restrict__ alpha, const double *__restrict__ beta, const int32_t *__restrict__ numSamples,
+		const double *__restrict__ alphaIncumb, int currIter, const double *__restrict__ xk, int n1, double lb,
+		double *__restrict__ height, double *__restrict__ eta, double *__restrict__ rhs, int32_t *__restrict__ best) {
+	extern __shared__ double s_h[];
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		const double *b = beta + (size_t) i * (n1 + 1);
+		double t_over_k = ((double) numSamples[i] / (double) currIter);                 // cuts.c:215
+		double dot = 0.0;
+		for (int c = 1; c <= n1; c++) dot = __dadd_rn(dot, __dmul_rn(b[c], xk[c]));      // vXv cuts.c:218
+		double h = __dsub_rn(alpha[i], dot);
+		h = __dmul_rn(h, t_over_k);                                                      // :221
+		h = __dadd_rn(h, __dmul_rn(__dsub_rn(1.0, t_over_k), lb));                       // :224
+		height[i] = h; s_h[i] = h;
+		double r = (double) currIter / (double) numSamples[i];
+		eta[i] = r;                                                                      // master.c:152
+		rhs[i] = __dadd_rn(alphaIncumb ? alphaIncumb[i] : 0.0, __dmul_rn(__dsub_rn(r, 1.0), lb));   // master.c:174
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double Sm = -1.0e20; int bi = -1;                                                // -INF, cuts.c:198
+		for (int i = 0; i < n; i++) if (Sm < s_h[i]) { Sm = s_h[i]; bi = i; }            // :203-205
+		*best = bi;
+	}
+}
+
+struct ReformArgs {
+	const int32_t *iStar; int omegaCnt; const int32_t *observ; int k;
+	const double *omega; int64_t NP; int rvOffset2;
+	const double *delta; int64_t Dcap; int Q;
+	const double *sigmaPib, *sigmaPiCr; const int32_t *sigmaLam; int n1c, n1cP;
+	const int32_t *bTermStart, *tSigma, *tOmega;
+	int n1, lbType, lb; const int32_t *CCols, *qCols;
+	double *out;        // [0] alpha, [1..n1+1] beta[0..n1]
+};
+
+// optimal.c:203-226 for one cut, one CTA
+__global__ void __launch_bounds__(512) k_reform(ReformArgs a) {
+	__shared__ double s_red[32];
+	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
+	double tAlpha = 0.0, tCount = 0.0;
+	for (int n = threadIdx.x; n < a.k; n += blockDim.x) {
+		const int o = a.observ[n];
+		if (o >= a.omegaCnt) continue;                                  // optimal.c:205
+		const int is = a.iStar[o];
+		const double *cellBase = a.delta + (size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W);
+		for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
+			int s = a.tSigma[t], l = a.sigmaLam[s];
+			double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+			tAlpha = __dadd_rn(tAlpha, __dmul_rn(m, __dadd_rn(a.sigmaPib[s], cellBase[(size_t) l * rowStride])));   // :216
+		}
+		tCount += 1.0;
+	}
+	extern __shared__ double s_part[];      // [0] alpha sum, [1] count, [2..2+n1c) sigma part, [2+n1c..) delta part, then beta[0..n1]
+	double r = sd_block_sum(tAlpha, s_red); if (threadIdx.x == 0) s_part[0] = r;
+	r = sd_block_sum(tCount, s_red);        if (threadIdx.x == 0) s_part[1] = r;
+	for (int c = threadIdx.x; c < a.n1c + a.Q; c += blockDim.x) {
+		double acc = 0.0;
+		for (int n = 0; n < a.k; n++) {
+			const int o = a.observ[n];
+			if (o >= a.omegaCnt) continue;
+			const int is = a.iStar[o];
+			const double *cellBase = a.delta + (size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W);
+			for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
+				int s = a.tSigma[t], l = a.sigmaLam[s];
+				double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+				double v = c < a.n1c ? a.sigmaPiCr[(size_t) s * a.n1cP + c] : cellBase[(size_t) l * rowStride + (size_t) (1 + c - a.n1c) * SD_TILE_W];
+				acc = __dadd_rn(acc, __dmul_rn(m, v));                   // :218-221
+			}
+		}
+		s_part[2 + c] = acc;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {                 // optimal.c:197-199 (zero), :218-221 (scatter), :228-235 (average, lower-bound share)
+		double *beta = s_part + 2 + a.n1c + a.Q;
+		for (int i = 0; i <= a.n1; i++) beta[i] = 0.0;
+		for (int k = 0; k < a.n1c; k++) beta[a.CCols[k]] = __dadd_rn(beta[a.CCols[k]], s_part[2 + k]);
+		for (int q = 0; q < a.Q; q++) beta[a.qCols[q]] = __dadd_rn(beta[a.qCols[q]], s_part[2 + a.n1c + q]);
+		for (int i = 0; i <= a.n1; i++) a.out[1 + i] = beta[i] / (double) a.k;
+		double al = s_part[0] / (double) a.k;
+		if (a.lbType == 1) al = __dadd_rn(al, __dmul_rn(__dsub_rn(1.0, s_part[1] / (double) a.k), (double) a.lb));
+		a.out[0] = al;
+	}
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+static inline int sd_blocks(int64_t n, int t) { return (int) std::max<int64_t>(1, (n + t - 1) / t); }
+
+static int sd_stage_x(sdgpu_ctx *c, const double *X) {
+	memcpy(c->h_pinD, X, ((size_t) c->n1 + 1) * sizeof(double));
+	SD_CUDA(cudaMemcpyAsync(c->d_x, c->h_pinD, ((size_t) c->n1 + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	return 0;
+}
+
+static int sd_window_cutoff(int numSamples, int pi_eval) {
+	if (pi_eval) numSamples -= (int) (0.1 * numSamples + 1);          // stocUpdate.c:147-148
+	return numSamples;
+}
+
+static int sd_launch_desc(sdgpu_ctx *c, int cutoff, int split) {
+	if (c->sigmaCnt > 0) {
+		k_picbarx<<<sd_blocks(c->sigmaCnt, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(c->d_sigmaPiCk, c->SP, c->n1c, c->d_CCols, c->d_x,
+				c->n1, (int) c->sigmaCnt, c->d_piCbarX);
+		sd_count_launch(c);
+	}
+	if (c->basisCnt > 0) {
+		k_basis_desc<<<sd_blocks(c->basisCnt, 128), 128, 0, c->stream>>>(c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaLam,
+				c->d_piCbarX, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin);
+		sd_count_launch(c);
+	}
+	return 0;
+}
+
+static SweepGenArgs sd_gen_args(sdgpu_ctx *c, int chunkSize, int nChunks) {
+	SweepGenArgs g;
+	g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
+	g.bTermStart = c->d_bTermStart; g.tSigma = c->d_tSigma; g.tOmega = c->d_tOmega; g.descWin = c->d_descWin;
+	g.sigmaPib = c->d_sigmaPib; g.piCbarX = c->d_piCbarX; g.sigmaLam = c->d_sigmaLam;
+	g.omega = c->d_omega; g.NP = c->NP; g.rvOffset2 = c->rvOffset[2];
+	g.basisCnt = (int) c->basisCnt; g.chunkSize = chunkSize; g.nChunks = nChunks;
+	g.mask = c->rvd > 0 ? c->d_mask : nullptr; g.Bcap = c->caps.maxBasis;
+	g.x = c->d_x; g.rvCOmCols = c->d_rvCOmCols;
+	g.partV = c->d_partV; g.partI = c->d_partI;
+	return g;
+}
+
+// pick the basis-chunk count: enough CTAs to fill 148 SMs x 4 resident CTAs for a few waves, never more than the
+// scratch allows, never chunks smaller than one descriptor batch
+static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks) {
+	int smCount = 148;
+	cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, c->device);
+	int64_t target = (int64_t) smCount * 4 * 3;
+	int64_t want = std::max<int64_t>(1, (target + tiles - 1) / tiles);
+	want = std::min<int64_t>(want, c->maxChunks);
+	want = std::min<int64_t>(want, std::max<int64_t>(1, (c->basisCnt + 63) / 64));
+	int cs = (int) ((c->basisCnt + want - 1) / want);
+	cs = std::max(cs, 1);
+	*chunkSize = cs;
+	*nChunks = (int) ((c->basisCnt + cs - 1) / cs);
+}
+
+extern "C" int sdgpu_sd_cut_partial(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb) {
+	if (!c || !Xvect) return sdgpu_fail("null argument");
+	if (c->Q > 64) return sdgpu_fail("sd_cut: rvCOmCnt %d exceeds the 64 random T elements this build stages in shared memory", c->Q);
+	SD_CUDA(cudaSetDevice(c->device));
+	int64_t launches0 = c->stats.total_launches;
+	SD_CUDA(cudaEventRecord(c->evA, c->stream));
+	if (sd_stage_x(c, Xvect)) return SDGPU_ERR;
+	const int N = (int) c->omegaCnt;
+	const int tiles = (int) ((N + SD_TILE_W - 1) / SD_TILE_W);
+	const int P = 4 + c->n1c + c->Q;
+	c->lastOmegaCnt = N;
+	if (N > 0 && c->basisCnt > 0) {
+		sd_launch_desc(c, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0);
+		int chunkSize = 1, nChunks = 1;
+		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);
+		dim3 grid((unsigned) tiles, (unsigned) nChunks);
+		SD_CUDA(cudaEventRecord(c->evC, c->stream));
+		const bool general = c->maxPhiLen > 0;
+		if (general) {
+			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
+		}
+		else {
+			SweepArgs a;
+			a.delta = c->d_delta; a.Dcap = c->caps.maxLambda; a.Q = c->Q;
+			a.descA = c->d_descA; a.descC = c->d_descC; a.descRow = c->d_descRow; a.descWin = c->d_descWin;
+			a.basisCnt = (int) c->basisCnt; a.chunkSize = chunkSize; a.nChunks = nChunks;
+			a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
+			a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
+			const bool hasMask = c->rvd > 0;
+			if (c->Q > 0 && hasMask) k_sweep_ldg<true, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
+			else if (c->Q > 0)       k_sweep_ldg<true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
+			else if (hasMask)        k_sweep_ldg<false, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
+			else                     k_sweep_ldg<false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
+		}
+		sd_count_launch(c);
+		SD_CUDA(cudaEventRecord(c->evD, c->stream));
+		// algorithmic bytes of the sweep: delta stream + per-observation weight and iStar + per-basis descriptors
+		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * c->basisCnt * (int64_t) N + (int64_t) N * 8 + c->basisCnt * 16;
+
+		MergeArgs m;
+		m.partV = c->d_partV; m.partI = c->d_partI; m.nChunks = nChunks; m.NP = c->NP;
+		m.omegaCnt = N; m.pi_eval = pi_eval_flag != 0; m.lb = lb;
+		m.omegaW = c->d_omegaW; m.omega = c->d_omega; m.rvOffset2 = c->rvOffset[2];
+		m.delta = c->d_delta; m.Dcap = c->caps.maxLambda; m.Q = c->Q;
+		m.sigmaPib = c->d_sigmaPib; m.sigmaPiCr = c->d_sigmaPiCr; m.sigmaLam = c->d_sigmaLam; m.sigmaCnt = (int) c->sigmaCnt;
+		m.n1c = c->n1c; m.n1cP = c->n1cP;
+		m.bTermStart = c->d_bTermStart; m.tSigma = c->d_tSigma; m.tOmega = c->d_tOmega;
+		m.randCost = c->rvd > 0;
+		m.iStar = c->d_iStar; m.tilePart = c->d_tilePart; m.P = P;
+		const int kp = ((c->n1c + 31) / 32) * 32;
+		const int groups = c->n1c > 0 ? std::max(1, MG_THREADS / kp) : 1;
+		k_cut_merge<<<tiles, MG_THREADS, (size_t) std::max(1, groups * c->n1c) * 8, c->stream>>>(m);
+		sd_count_launch(c);
+	}
+	else {
+		SD_CUDA(cudaEventRecord(c->evC, c->stream));
+		SD_CUDA(cudaEventRecord(c->evD, c->stream));
+		c->stats.last_sweep_bytes = 0;
+	}
+	const int usedTiles = (N > 0 && c->basisCnt > 0) ? tiles : 0;
+	k_cut_finalize<<<1, 256, (size_t) P * 8, c->stream>>>(c->d_tilePart, usedTiles, P, c->n1, c->n1c, c->Q, c->d_CCols,
+			c->rvd > 0 ? c->d_rvCOmCols : c->d_rvCols, c->d_cutPartial);
+	sd_count_launch(c);
+	if (N > 0 && c->basisCnt == 0) {
+		// no basis at all: every observation is missing its maximiser (cuts.c:136-139)
+		double miss = (double) N;
+		SD_CUDA(cudaMemcpyAsync(c->d_cutPartial + c->n1 + 3, &miss, 8, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaMemsetAsync(c->d_iStar, 0xff, (size_t) N * 4, c->stream));
+		SD_CUDA(cudaStreamSynchronize(c->stream));
+	}
+	c->stats.last_cut_launches = c->stats.total_launches - launches0;
+	return 0;
+}
+
+extern "C" int sdgpu_sd_cut_partial_buffer(sdgpu_ctx *c, void **devPtr, int *len) {
+	if (!c || !devPtr || !len) return sdgpu_fail("null argument");
+	*devPtr = c->d_cutPartial; *len = c->n1 + 4;
+	return 0;
+}
+
+extern "C" int sdgpu_sd_cut_finish(sdgpu_ctx *c, int numSamples, sdgpu_cut *cut) {
+	if (!c || !cut || !cut->beta) return sdgpu_fail("null argument");
+	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
+	SD_CUDA(cudaSetDevice(c->device));
+	int64_t launches0 = c->stats.total_launches;
+	k_cut_normalise<<<sd_blocks(c->n1 + 4, 128), 128, 0, c->stream>>>(c->d_cutPartial, c->n1, numSamples, c->d_cutOut);
+	sd_count_launch(c);
+	double *h = c->h_pinD;
+	SD_CUDA(cudaMemcpyAsync(h, c->d_cutOut, ((size_t) c->n1 + 4) * 8, cudaMemcpyDeviceToHost, c->stream));
+	if (cut->iStar && c->lastOmegaCnt > 0)
+		SD_CUDA(cudaMemcpyAsync(cut->iStar, c->d_iStar, (size_t) c->lastOmegaCnt * 4, cudaMemcpyDeviceToHost, c->stream));
+	SD_CUDA(cudaEventRecord(c->evB, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	SD_CUDA(cudaGetLastError());
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->stats.last_cut_ms = ms;
+	if (cudaEventElapsedTime(&ms, c->evC, c->evD) == cudaSuccess) c->stats.last_sweep_ms = ms;
+	c->stats.last_cut_launches += c->stats.total_launches - launches0;
+	cut->omegaCnt = c->lastOmegaCnt; cut->numSamples = numSamples;
+	cut->cummOld = h[c->n1 + 1]; cut->cummAll = h[c->n1 + 2];
+	const double missing = h[c->n1 + 3];
+	if (missing >= 1.0e9) return sdgpu_fail("sd_cut: iStar used as a sigma index is out of range (cuts.c:161)");
+	if (missing > 0.0) { sdgpu_fail("sd_cut: failed to identify maximal Pi for %g observation(s)", missing); return SDGPU_NONE; }
+	cut->alpha = h[0];
+	for (int k = 1; k <= c->n1; k++) cut->beta[k] = h[k];
+	cut->beta[0] = 1.0;                                              // cuts.c:188
+	return 0;
+}
+
+extern "C" int sdgpu_sd_cut(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, sdgpu_cut *cut) {
+	int rc = sdgpu_sd_cut_partial(c, Xvect, numSamples, pi_eval_flag, lb);
+	if (rc != 0) return rc;
+	if (c->ncclComm) {
+		rc = sd_nccl_allreduce(c, c->d_cutPartial, c->n1 + 4);
+		if (rc != 0) return rc;
+	}
+	return sdgpu_sd_cut_finish(c, numSamples, cut);
+}
+
+extern "C" int sdgpu_last_istar_device(sdgpu_ctx *c, void **devPtr, int *len) {
+	if (!c || !devPtr || !len) return sdgpu_fail("null argument");
+	*devPtr = c->d_iStar; *len = c->lastOmegaCnt;
+	return 0;
+}
+
+extern "C" int sdgpu_set_sweep_variant(sdgpu_ctx *c, int variant) {
+	if (!c) return sdgpu_fail("null context");
+	if (variant < 0 || variant > 2) return sdgpu_fail("unknown sweep variant %d", variant);
+	c->sweepVariant = variant;
+	return 0;
+}
+
+extern "C" int sdgpu_compute_istar(sdgpu_ctx *c, const double *Xvect, int obs, int numSamples, int pi_eval, int isNew, double *argmax) {
+	if (!c || !Xvect) return sdgpu_fail("null argument");
+	if (obs < 0 || obs >= c->omegaCnt) return sdgpu_fail("compute_istar: observation %d out of range", obs);
+	if (c->Q > 64) return sdgpu_fail("compute_istar: rvCOmCnt too large");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_stage_x(c, Xvect)) return SDGPU_ERR;
+	// always split at the (possibly shrunk) sample count: isNew asks for the bases above it, !isNew for those at or below
+	sd_launch_desc(c, sd_window_cutoff(numSamples, pi_eval != 0), 1);
+	double *d_v = c->d_cutOut; int32_t *d_i = (int32_t *) (c->d_cutOut + 1);
+	if (c->basisCnt > 0) {
+		k_istar_one<<<1, 256, 0, c->stream>>>(sd_gen_args(c, 1, 1), obs, isNew != 0, d_v, d_i);
+		sd_count_launch(c);
+		SD_CUDA(cudaMemcpyAsync(c->h_pinD, c->d_cutOut, 16, cudaMemcpyDeviceToHost, c->stream));
+		SD_CUDA(cudaStreamSynchronize(c->stream));
+		SD_CUDA(cudaGetLastError());
+		int32_t idx;
+		memcpy(&idx, c->h_pinD + 1, 4);
+		if (argmax) *argmax = c->h_pinD[0];
+		return idx;
+	}
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	if (argmax) *argmax = -DBL_MAX;
+	return SDGPU_NONE;
+}
+
+extern "C" int sdgpu_dual_stability(double cummOld, double cummAll, int numSamples, int piEvalStart, int scanLen, double *pi_ratio) {
+	// cuts.c:171-182 with calcVariance cuts.c:366-396 (host scalar work on <= SCAN_LEN doubles)
+	if (!pi_ratio || scanLen <= 0) return SDGPU_ERR;
+	double variance;
+	pi_ratio[numSamples % scanLen] = cummOld / cummAll;
+	if (numSamples - piEvalStart > scanLen) {
+		double mean = pi_ratio[0], vari = 0.0, temp;
+		for (int count = 1; count < scanLen; count++) {
+			temp = mean;
+			mean = mean + (pi_ratio[count] - mean) / (double) (count + 1);
+			vari = (1 - 1 / (double) count) * vari + (count + 1) * (mean - temp) * (mean - temp);
+		}
+		variance = vari;
+	}
+	else
+		variance = 1.0;
+	double av = variance > 0.0 ? variance : -variance;
+	if (av >= .000002 || pi_ratio[numSamples % scanLen] < 0.95) return 0;
+	return 1;
+}
+
+extern "C" int sdgpu_cut_heights(sdgpu_ctx *c, int n, const double *alpha, const double *beta, const int32_t *numSamples,
+		const double *alphaIncumb, int currIter, const double *xk, double lb, double *height, double *etaCoef, double *rhs) {
+	if (!c) return sdgpu_fail("null context");
+	if (n <= 0) return SDGPU_NONE;
+	if (!alpha || !beta || !numSamples || !xk) return sdgpu_fail("null argument");
+	SD_CUDA(cudaSetDevice(c->device));
+	const size_t n1p = (size_t) c->n1 + 1;
+	size_t nd = (size_t) n * (n1p + 5) + n1p, ni = (size_t) n + 1;
+	double *d_d = nullptr; int32_t *d_i = nullptr;
+	if (cudaMalloc((void **) &d_d, nd * 8) != cudaSuccess || cudaMalloc((void **) &d_i, ni * 4) != cudaSuccess) { if (d_d) cudaFree(d_d); return sdgpu_fail("cut_heights: allocation failed"); }
+	double *d_alpha = d_d, *d_beta = d_alpha + n, *d_ai = d_beta + (size_t) n * n1p, *d_xk = d_ai + n, *d_h = d_xk + n1p, *d_e = d_h + n, *d_r = d_e + n;
+	cudaMemcpyAsync(d_alpha, alpha, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyAsync(d_beta, beta, (size_t) n * n1p * 8, cudaMemcpyHostToDevice, c->stream);
+	if (alphaIncumb) cudaMemcpyAsync(d_ai, alphaIncumb, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyAsync(d_xk, xk, n1p * 8, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyAsync(d_i, numSamples, (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
+	k_cut_heights<<<1, 128, (size_t) n * 8, c->stream>>>(n, d_alpha, d_beta, d_i, alphaIncumb ? d_ai : nullptr, currIter, d_xk, c->n1, lb, d_h, d_e, d_r, d_i + n);
+	sd_count_launch(c);
+	std::vector<double> hh(n), he(n), hr(n);
+	int32_t best = -1;
+	cudaMemcpyAsync(hh.data(), d_h, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
+	cudaMemcpyAsync(he.data(), d_e, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
+	cudaMemcpyAsync(hr.data(), d_r, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
+	cudaMemcpyAsync(&best, d_i + n, 4, cudaMemcpyDeviceToHost, c->stream);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_d); cudaFree(d_i);
+	if (e != cudaSuccess) return sdgpu_fail("cut_heights: %s", cudaGetErrorString(e));
+	if (height) memcpy(height, hh.data(), (size_t) n * 8);
+	if (etaCoef) memcpy(etaCoef, he.data(), (size_t) n * 8);
+	if (rhs) memcpy(rhs, hr.data(), (size_t) n * 8);
+	return best;
+}
+
+extern "C" int sdgpu_reform_cut(sdgpu_ctx *c, const int32_t *iStar, int omegaCnt, const int32_t *observ, int k, int lbType, int lb,
+		double *alpha, double *beta) {
+	if (!c || !observ || !alpha || !beta) return sdgpu_fail("null argument");
+	if (k <= 0) return sdgpu_fail("reform_cut: k must be positive");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (!iStar) omegaCnt = c->lastOmegaCnt;
+	if (omegaCnt > c->omegaCnt) return sdgpu_fail("reform_cut: omegaCnt %d exceeds stored observations", omegaCnt);
+	int32_t *d_is = nullptr, *d_ob = nullptr; double *d_out = nullptr;
+	const int nOut = c->n1 + 2;
+	if (cudaMalloc((void **) &d_ob, (size_t) k * 4) != cudaSuccess || cudaMalloc((void **) &d_out, (size_t) nOut * 8) != cudaSuccess ||
+	    (iStar && cudaMalloc((void **) &d_is, (size_t) std::max(1, omegaCnt) * 4) != cudaSuccess)) {
+		if (d_ob) cudaFree(d_ob); if (d_out) cudaFree(d_out);
+		return sdgpu_fail("reform_cut: allocation failed");
+	}
+	cudaMemcpyAsync(d_ob, observ, (size_t) k * 4, cudaMemcpyHostToDevice, c->stream);
+	if (iStar) cudaMemcpyAsync(d_is, iStar, (size_t) omegaCnt * 4, cudaMemcpyHostToDevice, c->stream);
+	ReformArgs a;
+	a.iStar = iStar ? d_is : c->d_iStar; a.omegaCnt = omegaCnt; a.observ = d_ob; a.k = k;
+	a.omega = c->d_omega; a.NP = c->NP; a.rvOffset2 = c->rvOffset[2];
+	a.delta = c->d_delta; a.Dcap = c->caps.maxLambda; a.Q = c->Q;
+	a.sigmaPib = c->d_sigmaPib; a.sigmaPiCr = c->d_sigmaPiCr; a.sigmaLam = c->d_sigmaLam; a.n1c = c->n1c; a.n1cP = c->n1cP;
+	a.bTermStart = c->d_bTermStart; a.tSigma = c->d_tSigma; a.tOmega = c->d_tOmega;
+	a.n1 = c->n1; a.lbType = lbType; a.lb = lb; a.CCols = c->d_CCols; a.qCols = c->d_rvCOmCols;      // optimal.c:220 scatters with rvCOmCols
+	a.out = d_out;
+	k_reform<<<1, 512, (size_t) (2 + c->n1c + c->Q + c->n1 + 1) * 8, c->stream>>>(a);
+	sd_count_launch(c);
+	std::vector<double> h(nOut);
+	cudaMemcpyAsync(h.data(), d_out, (size_t) nOut * 8, cudaMemcpyDeviceToHost, c->stream);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_ob); cudaFree(d_out); if (d_is) cudaFree(d_is);
+	if (e != cudaSuccess) return sdgpu_fail("reform_cut: %s", cudaGetErrorString(e));
+	*alpha = h[0];
+	memcpy(beta, h.data() + 1, ((size_t) c->n1 + 1) * 8);
+	return 0;
+}

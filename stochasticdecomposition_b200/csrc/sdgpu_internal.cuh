@@ -1,0 +1,143 @@
+// sdgpu_internal.cuh -- context layout and helpers shared by the translation units of libsdgpu.so.
+//
+// HBM layout.  N = observations, D = lambda rows, S = sigma rows, B = bases.
+//   omega    [numRV][NP]            rv-major, NP = observation pitch: thread-per-observation kernels coalesce
+//   lambda   [R][LP]                position-major: thread-per-row scans (calcLambda) and K3 coalesce
+//   sigmaPib [SP], sigmaLam [SP], sigmaCk [SP]
+//   sigmaPiC kept twice: k-major [n1c][SP] (scan + piCbarX, thread per row) and row-major [SP][n1cP]
+//            (beta accumulation, thread per column)
+//   delta    tiled [nTiles][Dcap][1+Q][W]  W = SD_TILE_W observations: for one observation tile the rows of
+//            all duals are back to back, so the sweep of one CTA is a single contiguous HBM stream, a new
+//            dual (row append) writes nTiles contiguous W*8-byte segments, and a new observation (column
+//            append) writes D strided doubles.
+//   mask     tiled [nTiles][Bcap][W] bytes, only when rvdOmCnt > 0 (obsFeasible, stoc.h:95)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "sdgpu.h"
+
+#define SD_TILE_W      512          // observations per delta tile (4 KiB of FP64 per dual per tile)
+#define SD_SWEEP_THREADS 256        // one double2 (two observations) per thread per dual row
+#define SD_MAX_CHUNKS  64           // basis chunks per observation tile in the 2-D sweep grid
+
+extern thread_local std::string g_sdgpu_err;
+int sdgpu_fail(const char *fmt, ...);
+
+#define SD_CUDA(call)                                                                              \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return sdgpu_fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+// Device-resident counters and the result slots of the find-or-append kernels.  Kernels read the counts
+// from here, so a chain of table updates needs no host round trip between its kernels.
+struct SdDevState {
+	int omegaCnt, lambdaCnt, sigmaCnt, basisCnt;
+	int foundLambda, lambdaIdx, newLambda;     // calcLambda result
+	int foundSigma, sigmaIdx, newSigma;        // calcSigma result
+	int foundOmega, omegaIdx, newOmega;        // calcOmega result
+	int overflow;                              // a capacity was exceeded
+	double pibBar;                             // pi x bBar + mubBar of the vector being processed
+};
+
+struct SdHostBasis {
+	int ck, feas, phiLen, weight;
+	std::vector<int32_t> sigmaIdx;   // [phiLen+1]
+	std::vector<int32_t> omegaIdx;   // [phiLen+1], slot 0 unused
+};
+
+struct sdgpu_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool ownStream = true;
+	cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
+
+	sdgpu_num num{};
+	sdgpu_caps caps{};
+	int n1 = 0, n1c = 0, n1cP = 0, R = 0, Rb = 0, Q = 0, rvd = 0, numRV = 0, rows = 0;
+	int32_t rvOffset[3] = {0, 0, 0};
+	int64_t NP = 0, LP = 0, SP = 0, BP = 0, nTiles = 0, termCap = 0;
+
+	// static problem description on the device (0-based internally)
+	int32_t *d_CCols = nullptr;      // [n1c]  1-based position in X
+	int32_t *d_rvRows = nullptr;     // [R]    1-based row in Pi
+	int32_t *d_bLamPos = nullptr;    // [Rb]   position (0..R-1) of rvbOmRows[j] inside a lambda, or -1
+	int32_t *d_cLamPos = nullptr;    // [Q]    position of rvCOmRows[e] inside a lambda, or -1
+	int32_t *d_cListStart = nullptr; // [Q+1]  for output c: the e's with rvCOmCols[e] == rvCOmCols[c], in e order
+	int32_t *d_cList = nullptr;
+	int32_t *d_rvCOmCols = nullptr;  // [Q]    1-based position in X / beta
+	int32_t *d_rvCols = nullptr;     // [Q]    1-based position in beta (plain branch, cuts.c:167)
+	int32_t *d_bBarCol = nullptr; double *d_bBarVal = nullptr; int bBarCnt = 0;
+	int32_t *d_cbStart = nullptr;    // [n1c+1] per CCols[k]: Cbar entries with that column, in nnz order
+	int32_t *d_cbRow = nullptr; double *d_cbVal = nullptr;
+
+	// tables
+	double  *d_omega = nullptr;  int32_t *d_omegaW = nullptr;
+	double  *d_lambda = nullptr;
+	double  *d_sigmaPib = nullptr, *d_sigmaPiCk = nullptr, *d_sigmaPiCr = nullptr;
+	int32_t *d_sigmaLam = nullptr, *d_sigmaCk = nullptr;
+	double  *d_delta = nullptr;
+	uint8_t *d_mask = nullptr;
+	int32_t *d_bCk = nullptr, *d_bFeas = nullptr, *d_bPhiLen = nullptr, *d_bTermStart = nullptr;
+	int32_t *d_tSigma = nullptr, *d_tOmega = nullptr;
+	SdDevState *d_state = nullptr;
+
+	// per-call staging
+	double  *d_vecIn = nullptr;      // a host vector (Pi / observ / X) of up to max(rows, numRV, n1)+1 doubles
+	double  *d_cand = nullptr;       // reduced candidate: lambda [R] / piCBar [n1c] / observation [numRV]
+	double  *d_candC = nullptr;
+	double  *h_pinD = nullptr;       // pinned doubles (inputs and results)
+	int32_t *h_pinI = nullptr;       // pinned ints
+	SdDevState *h_state = nullptr;   // pinned mirror
+	size_t   pinDcap = 0, pinIcap = 0;
+
+	// cut formation scratch
+	double  *d_x = nullptr;          // [n1+1]
+	double  *d_piCbarX = nullptr;    // [SP]
+	double  *d_descA = nullptr, *d_descC = nullptr;   // per basis: sigma.pib, piCbarX of its first sigma
+	int32_t *d_descRow = nullptr, *d_descWin = nullptr; // per basis: lambda row, window (0 skip, 1 old, 2 new)
+	double  *d_partV = nullptr;      // [2][chunks][NP] per-chunk running maxima (old, new)
+	int32_t *d_partI = nullptr;      // [2][chunks][NP]
+	int32_t *d_iStar = nullptr;      // [NP]
+	double  *d_tilePart = nullptr;   // [nTiles][P]  P = 4 + n1c + Q
+	double  *d_cutPartial = nullptr; // [n1+4]  alpha, beta[1..n1], cummOld, cummAll, missing (un-normalised)
+	double  *d_cutOut = nullptr;     // [n1+4]  alpha, beta[1..n1], cummOld, cummAll, missing (normalised)
+	int      maxChunks = 1;
+	int      sweepVariant = 0;
+	int      lastOmegaCnt = 0;
+
+	// host mirrors (bookkeeping only; no table arithmetic happens on the host)
+	int64_t omegaCnt = 0, lambdaCnt = 0, sigmaCnt = 0, basisCnt = 0, termCnt = 0;
+	int     maxPhiLen = 0;
+	bool    anyInfeasibleBasis = false;
+	std::vector<SdHostBasis> basis;
+	std::vector<std::vector<uint8_t>> hostMask;   // [b][NP] only when rvd > 0
+
+	// NCCL (resolved with dlopen so that the library loads on a box without NCCL)
+	void *ncclComm = nullptr;
+	bool  ownComm = false;
+
+	sdgpu_stats stats{};
+};
+
+static inline int64_t sd_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// delta element (l, plane q, observation o) in the tiled layout
+__host__ __device__ static inline size_t sd_delta_off(int64_t Dcap, int Q, int64_t l, int q, int64_t o) {
+	int64_t t = o / SD_TILE_W, w = o % SD_TILE_W;
+	return (((size_t) t * Dcap + l) * (size_t) (1 + Q) + q) * SD_TILE_W + w;
+}
+__host__ __device__ static inline size_t sd_mask_off(int64_t Bcap, int64_t b, int64_t o) {
+	int64_t t = o / SD_TILE_W, w = o % SD_TILE_W;
+	return ((size_t) t * Bcap + b) * SD_TILE_W + w;
+}
+
+int sd_sync_state(sdgpu_ctx *c);                 // D2H of SdDevState + stream sync + mirror update
+int sd_nccl_allreduce(sdgpu_ctx *c, double *buf, int n);
+void sd_nccl_release(sdgpu_ctx *c);
+static inline void sd_count_launch(sdgpu_ctx *c, int n = 1) { c->stats.total_launches += n; }

@@ -1,0 +1,961 @@
+// tables.cu -- device-resident stochastic tables of two-stage SD: omega, lambda, sigma, delta, basis records.
+// Replaces the table half of the reference's stocUpdate.c.  Citations are file:line under
+// /root/reference/twoSD_src.  Built with -fmad=false: every product and every sum is rounded separately and
+// accumulated left to right exactly as the reference's scalar loops do, so table entries are bit-identical
+// to the CPU path and the argmax downstream sees the same scores.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <climits>
+#include <algorithm>
+
+#include "sdgpu_internal.cuh"
+
+thread_local std::string g_sdgpu_err;
+
+int sdgpu_fail(const char *fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_sdgpu_err = buf;
+	return SDGPU_ERR;
+}
+
+extern "C" const char *sdgpu_last_error(void) { return g_sdgpu_err.c_str(); }
+extern "C" int sdgpu_abi_version(void) { return SDGPU_ABI_VERSION; }
+
+// DBL_ABS of the reference: (x) > 0 ? (x) : -(x); a NaN difference therefore never counts as a mismatch
+__device__ __forceinline__ double sd_abs(double x) { return x > 0.0 ? x : -x; }
+
+// ======================================================================================================
+// kernels
+// ======================================================================================================
+
+// Stage the candidate of a find-or-append: cand[i] = vec[idx[i]] (reduceVector, stocUpdate.c:269) or, with
+// idx == nullptr, cand[i] = vec[1 + i] (an observation, stocUpdate.c:331).  Also arms the result slots.
+__global__ void k_stage_candidate(const double *__restrict__ vec, const int32_t *__restrict__ idx, int n,
+		double *__restrict__ cand, SdDevState *st, int which) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) cand[i] = idx ? vec[idx[i]] : vec[1 + i];
+	if (i == 0) {
+		if (which == 0) st->foundLambda = INT_MAX;
+		else st->foundOmega = INT_MAX;
+	}
+}
+
+// calcLambda scan stocUpdate.c:272-277 / calcOmega scan :330-335: one thread per stored row, first mismatch ends
+// the row (most rows differ in their first entry, so the scan mostly touches one column of the table);
+// atomicMin keeps the FIRST matching index, which is what the sequential scan returns.
+__global__ void k_find_row(const double *__restrict__ table, int64_t pitch, int len, const double *__restrict__ cand,
+		double tol, SdDevState *st, int which) {
+	int cnt = which == 0 ? st->lambdaCnt : st->omegaCnt;
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= cnt) return;
+	for (int i = 0; i < len; i++)
+		if (sd_abs(cand[i] - table[(size_t) i * pitch + r]) > tol) return;
+	atomicMin(which == 0 ? &st->foundLambda : &st->foundOmega, r);
+}
+
+// stocUpdate.c:274-283: report the match or append the candidate as a new lambda row.
+__global__ void k_lambda_commit(double *__restrict__ lambda, int64_t LP, int R, const double *__restrict__ cand,
+		int64_t cap, SdDevState *st) {
+	__shared__ int s_cnt, s_found;
+	if (threadIdx.x == 0) { s_cnt = st->lambdaCnt; s_found = st->foundLambda; }
+	__syncthreads();
+	if (s_found != INT_MAX) {
+		if (threadIdx.x == 0) { st->lambdaIdx = s_found; st->newLambda = 0; }
+		return;
+	}
+	if (s_cnt >= cap) { if (threadIdx.x == 0) { st->overflow = 1; st->lambdaIdx = -1; st->newLambda = 0; } return; }
+	for (int i = threadIdx.x; i < R; i += blockDim.x) lambda[(size_t) i * LP + s_cnt] = cand[i];
+	if (threadIdx.x == 0) { st->lambdaIdx = s_cnt; st->newLambda = 1; st->lambdaCnt = s_cnt + 1; }
+}
+
+// stocUpdate.c:332-340,347: bump the weight of the match or append the observation with weight 1.
+__global__ void k_omega_commit(double *__restrict__ omega, int32_t *__restrict__ w, int64_t NP, int numRV,
+		const double *__restrict__ cand, int64_t cap, SdDevState *st, int mode, int weight) {
+	// mode 0: calcOmega (find result decides); mode 1: append unconditionally with `weight`
+	__shared__ int s_cnt, s_found;
+	if (threadIdx.x == 0) { s_cnt = st->omegaCnt; s_found = mode == 0 ? st->foundOmega : INT_MAX; }
+	__syncthreads();
+	if (s_found != INT_MAX) {
+		if (threadIdx.x == 0) { w[s_found] += 1; st->omegaIdx = s_found; st->newOmega = 0; }
+		return;
+	}
+	if (s_cnt >= cap) { if (threadIdx.x == 0) { st->overflow = 1; st->omegaIdx = -1; st->newOmega = 0; } return; }
+	for (int j = threadIdx.x; j < numRV; j += blockDim.x) omega[(size_t) j * NP + s_cnt] = cand[j];
+	if (threadIdx.x == 0) { w[s_cnt] = weight; st->omegaIdx = s_cnt; st->newOmega = 1; st->omegaCnt = s_cnt + 1; }
+}
+
+// calcSigma stocUpdate.c:293-296: pibBar = (sum_e bBar.val[e] * pi[bBar.col[e]]) + mubBar, and for each kept column
+// CCols[k] the entries of pi x Cbar that land in it, accumulated in nnz order from 0.0.
+__global__ void k_sigma_prepare(const double *__restrict__ pi, const int32_t *__restrict__ bCol, const double *__restrict__ bVal,
+		int bCnt, double mubBar, const int32_t *__restrict__ cbStart, const int32_t *__restrict__ cbRow,
+		const double *__restrict__ cbVal, int n1c, double *__restrict__ candC, SdDevState *st,
+		int overrideNewLambda, int overrideLambdaIdx) {
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n1c) {
+		double t = 0.0;
+		for (int e = cbStart[k]; e < cbStart[k + 1]; e++) t += pi[cbRow[e]] * cbVal[e];
+		candC[k] = t;
+	}
+	if (k == n1c || (n1c == 0 && k == 0)) {
+		double s = 0.0;
+		for (int e = 0; e < bCnt; e++) s += bVal[e] * pi[bCol[e]];
+		st->pibBar = s + mubBar;
+		st->foundSigma = INT_MAX;
+		if (overrideNewLambda >= 0) { st->newLambda = overrideNewLambda; st->lambdaIdx = overrideLambdaIdx; }
+	}
+}
+
+// stocUpdate.c:299-310: scan only when the lambda was already known; match = |pib diff| <= tol, every piC entry
+// within tol, and the same lambda index.  First match wins.
+__global__ void k_sigma_find(const double *__restrict__ pib, const double *__restrict__ piCk, const int32_t *__restrict__ lam,
+		int64_t SP, int n1c, const double *__restrict__ candC, double tol, SdDevState *st) {
+	if (st->newLambda) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= st->sigmaCnt) return;
+	if (!(sd_abs(st->pibBar - pib[s]) <= tol)) return;
+	for (int k = 0; k < n1c; k++)
+		if (sd_abs(candC[k] - piCk[(size_t) k * SP + s]) > tol) return;
+	if (lam[s] != st->lambdaIdx) return;
+	atomicMin(&st->foundSigma, s);
+}
+
+// stocUpdate.c:304-318
+__global__ void k_sigma_commit(double *__restrict__ pib, double *__restrict__ piCk, double *__restrict__ piCr, int32_t *__restrict__ lam,
+		int32_t *__restrict__ ck, int64_t SP, int n1c, int n1cP, const double *__restrict__ candC, int iter, int64_t cap,
+		SdDevState *st) {
+	__shared__ int s_cnt, s_found;
+	if (threadIdx.x == 0) { s_cnt = st->sigmaCnt; s_found = st->foundSigma; }
+	__syncthreads();
+	if (s_found != INT_MAX) {
+		if (threadIdx.x == 0) { st->sigmaIdx = s_found; st->newSigma = 0; }
+		return;
+	}
+	if (s_cnt >= cap || st->lambdaIdx < 0) { if (threadIdx.x == 0) { st->overflow = 1; st->sigmaIdx = -1; st->newSigma = 0; } return; }
+	for (int k = threadIdx.x; k < n1c; k += blockDim.x) {
+		piCk[(size_t) k * SP + s_cnt] = candC[k];
+		piCr[(size_t) s_cnt * n1cP + k] = candC[k];
+	}
+	if (threadIdx.x == 0) {
+		pib[s_cnt] = st->pibBar; lam[s_cnt] = st->lambdaIdx; ck[s_cnt] = iter;
+		st->sigmaIdx = s_cnt; st->newSigma = 1; st->sigmaCnt = s_cnt + 1;
+	}
+}
+
+// One delta cell, the arithmetic of stocUpdate.c:218-221 / :244-247:
+//   pib    = sum_{j=1..Rb} omega_o[j] * lambdaFull[rvbOmRows[j]]          (vXvSparse, index order)
+//   piC[c] = sum over the e with rvCOmCols[e] == rvCOmCols[c], in e order, of lambdaFull[rvCOmRows[e]] * omega_o[Rb+e]
+// lambdaFull is the lambda expanded to all rows, zero where the row carries no lambda entry (expandVector).
+// LamAt(p) / OmAt(j) fetch lambda position p and observation entry j (0-based) for the cell at hand.
+template <class LamAt, class OmAt>
+__device__ __forceinline__ void sd_delta_cell(int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos,
+		const int32_t *__restrict__ cListStart, const int32_t *__restrict__ cList, LamAt lamAt, OmAt omAt,
+		double *__restrict__ out, size_t planeStride) {
+	double s = 0.0;
+	for (int j = 0; j < Rb; j++) {
+		int p = bLamPos[j];
+		s += omAt(j) * (p >= 0 ? lamAt(p) : 0.0);
+	}
+	out[0] = s;
+	for (int c = 0; c < Q; c++) {
+		double t = 0.0;
+		for (int n = cListStart[c]; n < cListStart[c + 1]; n++) {
+			int e = cList[n], p = cLamPos[e];
+			t += (p >= 0 ? lamAt(p) : 0.0) * omAt(Rb + e);
+		}
+		out[(size_t) (1 + c) * planeStride] = t;
+	}
+}
+
+// calcDelta case II stocUpdate.c:230-254: a new dual -> one delta row, one thread per observation (coalesced
+// reads of omega, contiguous W-segment writes).  The lambda row sits in shared memory.
+__global__ void k_delta_row(const double *__restrict__ lambda, int64_t LP, int R, const double *__restrict__ omega, int64_t NP,
+		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
+		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedRow) {
+	extern __shared__ double s_lam[];
+	int l = forcedRow >= 0 ? forcedRow : (st->newLambda ? st->lambdaIdx : -1);
+	if (l < 0) return;
+	for (int i = threadIdx.x; i < R; i += blockDim.x) s_lam[i] = lambda[(size_t) i * LP + l];
+	__syncthreads();
+	int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (o >= st->omegaCnt) return;
+	sd_delta_cell(Rb, Q, bLamPos, cLamPos, cListStart, cList,
+			[&](int p) { return s_lam[p]; }, [&](int j) { return omega[(size_t) j * NP + o]; },
+			delta + sd_delta_off(Dcap, Q, l, 0, o), SD_TILE_W);
+}
+
+// calcDelta case I stocUpdate.c:206-229: a new observation -> one delta column, one thread per dual (coalesced
+// reads of lambda, strided 8-byte writes).  The observation sits in shared memory.
+__global__ void k_delta_col(const double *__restrict__ lambda, int64_t LP, const double *__restrict__ omega, int64_t NP, int numRV,
+		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
+		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedCol) {
+	extern __shared__ double s_om[];
+	int o = forcedCol >= 0 ? forcedCol : (st->newOmega ? st->omegaIdx : -1);
+	if (o < 0) return;
+	for (int j = threadIdx.x; j < numRV; j += blockDim.x) s_om[j] = omega[(size_t) j * NP + o];
+	__syncthreads();
+	int64_t l = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (l >= st->lambdaCnt) return;
+	sd_delta_cell(Rb, Q, bLamPos, cLamPos, cListStart, cList,
+			[&](int p) { return lambda[(size_t) p * LP + l]; }, [&](int j) { return s_om[j]; },
+			delta + sd_delta_off(Dcap, Q, l, 0, o), SD_TILE_W);
+}
+
+// calcDelta for a whole block of (dual, observation) pairs -- the bulk loader of synthetic sweeps.  A CTA owns
+// 32 duals x 128 observations; lambda and omega slices for the block are staged in shared memory Rb-chunk by
+// Rb-chunk and every thread carries 4 duals x 4 observations of running sums, each still accumulated in index
+// order j = 1..Rb with separate multiply and add, so the result is bit-identical to the one-at-a-time appends.
+#define DB_L 32
+#define DB_O 128
+#define DB_K 32
+__global__ void __launch_bounds__(256) k_delta_block_rhs(const double *__restrict__ lambda, int64_t LP, const double *__restrict__ omega,
+		int64_t NP, int Rb, const int32_t *__restrict__ bLamPos, double *__restrict__ delta, int64_t Dcap, int Q,
+		int64_t l0, int64_t l1, int64_t o0, int64_t o1) {
+	__shared__ double s_l[DB_K][DB_L + 1];
+	__shared__ double s_o[DB_K][DB_O];
+	int64_t lb = l0 + (int64_t) blockIdx.y * DB_L, ob = o0 + (int64_t) blockIdx.x * DB_O;
+	int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // tx -> 4 observations (strided by 32), ty -> 4 duals (strided by 8)
+	double acc[4][4];
+#pragma unroll
+	for (int a = 0; a < 4; a++)
+#pragma unroll
+		for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+	for (int j0 = 0; j0 < Rb; j0 += DB_K) {
+		int jn = min(DB_K, Rb - j0);
+		for (int n = threadIdx.x; n < DB_K * DB_L; n += 256) {
+			int j = n / DB_L, li = n % DB_L;
+			double v = 0.0;
+			if (j < jn && lb + li < l1) { int p = bLamPos[j0 + j]; v = p >= 0 ? lambda[(size_t) p * LP + lb + li] : 0.0; }
+			s_l[j][li] = v;
+		}
+		for (int n = threadIdx.x; n < DB_K * DB_O; n += 256) {
+			int j = n / DB_O, oi = n % DB_O;
+			s_o[j][oi] = (j < jn && ob + oi < o1) ? omega[(size_t) (j0 + j) * NP + ob + oi] : 0.0;
+		}
+		__syncthreads();
+		for (int j = 0; j < jn; j++) {
+			double lv[4], ov[4];
+#pragma unroll
+			for (int a = 0; a < 4; a++) lv[a] = s_l[j][ty + 8 * a];
+#pragma unroll
+			for (int b = 0; b < 4; b++) ov[b] = s_o[j][tx + 32 * b];
+#pragma unroll
+			for (int a = 0; a < 4; a++)
+#pragma unroll
+				for (int b = 0; b < 4; b++) acc[a][b] = __dadd_rn(acc[a][b], __dmul_rn(ov[b], lv[a]));
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int a = 0; a < 4; a++)
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			int64_t l = lb + ty + 8 * a, o = ob + tx + 32 * b;
+			if (l < l1 && o < o1) delta[sd_delta_off(Dcap, Q, l, 0, o)] = acc[a][b];
+		}
+}
+
+// the piC planes of a block (Q is small): one thread per (dual, observation) pair
+__global__ void k_delta_block_T(const double *__restrict__ lambda, int64_t LP, const double *__restrict__ omega, int64_t NP, int Rb, int Q,
+		const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart, const int32_t *__restrict__ cList,
+		double *__restrict__ delta, int64_t Dcap, int64_t l0, int64_t l1, int64_t o0, int64_t o1) {
+	int64_t o = o0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t l = l0 + blockIdx.y;
+	if (o >= o1 || l >= l1) return;
+	for (int c = 0; c < Q; c++) {
+		double t = 0.0;
+		for (int n = cListStart[c]; n < cListStart[c + 1]; n++) {
+			int e = cList[n], p = cLamPos[e];
+			t += (p >= 0 ? lambda[(size_t) p * LP + l] : 0.0) * omega[(size_t) (Rb + e) * NP + o];
+		}
+		delta[sd_delta_off(Dcap, Q, l, 1 + c, o)] = t;
+	}
+}
+
+// bulk loaders (no dedup scan): n observations / n dual vectors straight into the tables
+__global__ void k_omega_bulk(const double *__restrict__ vals, int64_t n, int numRV, const int32_t *__restrict__ weights,
+		double *__restrict__ omega, int32_t *__restrict__ w, int64_t NP, int64_t base) {
+	int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double *v = vals + (size_t) i * (numRV + 1);
+	for (int j = 0; j < numRV; j++) omega[(size_t) j * NP + base + i] = v[1 + j];
+	w[base + i] = weights ? weights[i] : 1;
+}
+
+__global__ void k_dual_bulk(const double *__restrict__ pis, int64_t n, int rows, const double *__restrict__ mub, const int32_t *__restrict__ iters,
+		const int32_t *__restrict__ rvRows, int R, const int32_t *__restrict__ bCol, const double *__restrict__ bVal, int bCnt,
+		const int32_t *__restrict__ cbStart, const int32_t *__restrict__ cbRow, const double *__restrict__ cbVal, int n1c, int n1cP,
+		double *__restrict__ lambda, int64_t LP, double *__restrict__ pib, double *__restrict__ piCk, double *__restrict__ piCr,
+		int32_t *__restrict__ lam, int32_t *__restrict__ ck, int64_t SP, int64_t lbase, int64_t sbase) {
+	int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double *pi = pis + (size_t) i * (rows + 1);
+	for (int r = 0; r < R; r++) lambda[(size_t) r * LP + lbase + i] = pi[rvRows[r]];
+	double s = 0.0;
+	for (int e = 0; e < bCnt; e++) s += bVal[e] * pi[bCol[e]];
+	pib[sbase + i] = s + (mub ? mub[i] : 0.0);
+	for (int k = 0; k < n1c; k++) {
+		double t = 0.0;
+		for (int e = cbStart[k]; e < cbStart[k + 1]; e++) t += pi[cbRow[e]] * cbVal[e];
+		piCk[(size_t) k * SP + sbase + i] = t;
+		piCr[(size_t) (sbase + i) * n1cP + k] = t;
+	}
+	lam[sbase + i] = (int32_t) (lbase + i);
+	ck[sbase + i] = iters ? iters[i] : (int32_t) (i + 1);
+}
+
+__global__ void k_bump_counts(SdDevState *st, int dOmega, int dLambda, int dSigma, int dBasis) {
+	st->omegaCnt += dOmega; st->lambdaCnt += dLambda; st->sigmaCnt += dSigma; st->basisCnt += dBasis;
+}
+
+__global__ void k_record_pair(const SdDevState *st, int32_t *lamOut, int32_t *sigOut, int64_t i) {
+	if (lamOut) lamOut[i] = st->lambdaIdx;
+	if (sigOut) sigOut[i] = st->sigmaIdx;
+}
+
+__global__ void k_omega_bump(int32_t *w, int idx, int by) { w[idx] += by; }
+
+__global__ void k_mask_fill_row(uint8_t *mask, int64_t Bcap, int64_t b, int64_t NP, const uint8_t *flags, int64_t n, int fillAll) {
+	int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (o >= NP) return;
+	if (fillAll) mask[sd_mask_off(Bcap, b, o)] = 1;
+	else if (o < n) mask[sd_mask_off(Bcap, b, o)] = flags[o] != 0;
+}
+
+__global__ void k_mask_fill_col(uint8_t *mask, int64_t Bcap, int64_t o, const uint8_t *flags, const int32_t *feas, int64_t nb) {
+	int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (b < nb && feas[b]) mask[sd_mask_off(Bcap, b, o)] = flags[b] != 0;
+}
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+
+template <class T>
+static int sd_alloc(T **p, size_t n) {
+	if (n == 0) n = 1;
+	cudaError_t e = cudaMalloc((void **) p, n * sizeof(T));
+	if (e != cudaSuccess) return sdgpu_fail("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+	return 0;
+}
+
+template <class T>
+static int sd_upload(T **p, const std::vector<T> &h) {
+	if (sd_alloc(p, h.size())) return SDGPU_ERR;
+	if (!h.empty()) SD_CUDA(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+int sd_sync_state(sdgpu_ctx *c) {
+	SD_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SdDevState), cudaMemcpyDeviceToHost, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	c->omegaCnt = c->h_state->omegaCnt; c->lambdaCnt = c->h_state->lambdaCnt;
+	c->sigmaCnt = c->h_state->sigmaCnt;
+	if (c->h_state->overflow) {
+		SD_CUDA(cudaMemsetAsync(&c->d_state->overflow, 0, sizeof(int), c->stream));
+		return sdgpu_fail("table capacity exceeded (omega %lld/%lld, lambda %lld/%lld, sigma %lld/%lld)",
+				(long long) c->omegaCnt, (long long) c->caps.maxOmega, (long long) c->lambdaCnt, (long long) c->caps.maxLambda,
+				(long long) c->sigmaCnt, (long long) c->caps.maxSigma);
+	}
+	return 0;
+}
+
+static int sd_stage_vec(sdgpu_ctx *c, const double *h, int n) {       // host vector -> d_vecIn through pinned memory
+	memcpy(c->h_pinD, h, (size_t) n * sizeof(double));
+	SD_CUDA(cudaMemcpyAsync(c->d_vecIn, c->h_pinD, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	return 0;
+}
+
+static inline int sd_blocks(int64_t n, int t) { return (int) std::max<int64_t>(1, (n + t - 1) / t); }
+
+extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int device, sdgpu_ctx **out) {
+	if (!p || !caps || !out) return sdgpu_fail("sdgpu_create: null argument");
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return sdgpu_fail("sdgpu_create: no CUDA device -- this library has no CPU fallback");
+	if (device < 0 || device >= ndev) return sdgpu_fail("sdgpu_create: device %d out of range (%d devices)", device, ndev);
+	const sdgpu_num &nm = p->num;
+	if (nm.rvRowCnt < 0 || nm.rvbOmCnt < 0 || nm.rvCOmCnt < 0 || nm.cntCcols < 0 || nm.prevCols < 0 || nm.rows <= 0)
+		return sdgpu_fail("sdgpu_create: negative dimension");
+	if (caps->maxLambda <= 0 || caps->maxSigma <= 0 || caps->maxBasis <= 0 || caps->maxOmega <= 0)
+		return sdgpu_fail("sdgpu_create: capacities must be positive");
+	SD_CUDA(cudaSetDevice(device));
+
+	sdgpu_ctx *c = new sdgpu_ctx();
+	c->device = device; c->num = nm; c->caps = *caps;
+	if (c->caps.maxTerms < 1) c->caps.maxTerms = 1;
+	c->n1 = nm.prevCols; c->n1c = nm.cntCcols; c->n1cP = std::max(1, nm.cntCcols); c->R = nm.rvRowCnt; c->Rb = nm.rvbOmCnt;
+	c->Q = nm.rvCOmCnt; c->rvd = nm.rvdOmCnt; c->numRV = nm.numRV; c->rows = nm.rows;
+	memcpy(c->rvOffset, p->coord.rvOffset, sizeof c->rvOffset);
+	c->NP = sd_round_up(caps->maxOmega, SD_TILE_W); c->nTiles = c->NP / SD_TILE_W;
+	c->LP = sd_round_up(caps->maxLambda, 32); c->SP = sd_round_up(caps->maxSigma, 32); c->BP = sd_round_up(caps->maxBasis, 32);
+	c->termCap = caps->maxBasis * (int64_t) c->caps.maxTerms;
+
+#define SD_TRY(x) do { if ((x) != 0) { sdgpu_destroy(c); return SDGPU_ERR; } } while (0)
+	cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (ce != cudaSuccess) { sdgpu_fail("cudaStreamCreate: %s", cudaGetErrorString(ce)); sdgpu_destroy(c); return SDGPU_ERR; }
+	cudaEventCreate(&c->evA); cudaEventCreate(&c->evB); cudaEventCreate(&c->evC); cudaEventCreate(&c->evD);
+
+	// ---- static maps (host, once) ---------------------------------------------------------------------
+	auto lamPosOfRow = [&](int row) {          // expandVector: the LAST lambda entry written to that row wins
+		int pos = -1;
+		for (int i = 1; i <= c->R; i++) if (p->coord.rvRows[i] == row) pos = i - 1;
+		return pos;
+	};
+	std::vector<int32_t> CCols(c->n1c), rvRows(c->R), bLamPos(c->Rb), cLamPos(c->Q), cListStart(c->Q + 1, 0), cList, rvCOmCols(c->Q), rvCols(c->Q);
+	for (int k = 0; k < c->n1c; k++) { CCols[k] = p->coord.CCols[k + 1]; if (CCols[k] < 1 || CCols[k] > c->n1) { sdgpu_fail("CCols[%d]=%d outside 1..%d", k + 1, CCols[k], c->n1); sdgpu_destroy(c); return SDGPU_ERR; } }
+	for (int i = 0; i < c->R; i++) { rvRows[i] = p->coord.rvRows[i + 1]; if (rvRows[i] < 1 || rvRows[i] > c->rows) { sdgpu_fail("rvRows[%d]=%d outside 1..%d", i + 1, rvRows[i], c->rows); sdgpu_destroy(c); return SDGPU_ERR; } }
+	for (int j = 0; j < c->Rb; j++) bLamPos[j] = lamPosOfRow(p->coord.rvbOmRows[j + 1]);
+	for (int e = 0; e < c->Q; e++) {
+		cLamPos[e] = lamPosOfRow(p->coord.rvCOmRows[e + 1]);
+		rvCOmCols[e] = p->coord.rvCOmCols[e + 1];
+		rvCols[e] = p->coord.rvCols ? p->coord.rvCols[e + 1] : rvCOmCols[e];
+		if (rvCOmCols[e] < 1 || rvCOmCols[e] > c->n1 || rvCols[e] < 1 || rvCols[e] > c->n1) { sdgpu_fail("random T column outside 1..%d", c->n1); sdgpu_destroy(c); return SDGPU_ERR; }
+	}
+	for (int k = 0; k < c->Q; k++) {
+		for (int e = 0; e < c->Q; e++) if (rvCOmCols[e] == rvCOmCols[k]) cList.push_back(e);
+		cListStart[k + 1] = (int32_t) cList.size();
+	}
+	std::vector<int32_t> bCol(p->bBar.cnt), cbStart(c->n1c + 1, 0), cbRow;
+	std::vector<double> bVal(p->bBar.cnt), cbVal;
+	for (int e = 0; e < p->bBar.cnt; e++) { bCol[e] = p->bBar.col[e + 1]; bVal[e] = p->bBar.val[e + 1]; }
+	for (int k = 0; k < c->n1c; k++) {
+		for (int e = 1; e <= p->Cbar.cnt; e++)
+			if (p->Cbar.col[e] == CCols[k]) { cbRow.push_back(p->Cbar.row[e]); cbVal.push_back(p->Cbar.val[e]); }
+		cbStart[k + 1] = (int32_t) cbRow.size();
+	}
+	c->bBarCnt = p->bBar.cnt;
+	SD_TRY(sd_upload(&c->d_CCols, CCols)); SD_TRY(sd_upload(&c->d_rvRows, rvRows)); SD_TRY(sd_upload(&c->d_bLamPos, bLamPos));
+	SD_TRY(sd_upload(&c->d_cLamPos, cLamPos)); SD_TRY(sd_upload(&c->d_cListStart, cListStart)); SD_TRY(sd_upload(&c->d_cList, cList));
+	SD_TRY(sd_upload(&c->d_rvCOmCols, rvCOmCols)); SD_TRY(sd_upload(&c->d_rvCols, rvCols));
+	SD_TRY(sd_upload(&c->d_bBarCol, bCol)); SD_TRY(sd_upload(&c->d_bBarVal, bVal));
+	SD_TRY(sd_upload(&c->d_cbStart, cbStart)); SD_TRY(sd_upload(&c->d_cbRow, cbRow)); SD_TRY(sd_upload(&c->d_cbVal, cbVal));
+
+	// ---- tables -----------------------------------------------------------------------------------------
+	SD_TRY(sd_alloc(&c->d_omega, (size_t) c->numRV * c->NP)); SD_TRY(sd_alloc(&c->d_omegaW, (size_t) c->NP));
+	SD_TRY(sd_alloc(&c->d_lambda, (size_t) c->R * c->LP));
+	SD_TRY(sd_alloc(&c->d_sigmaPib, (size_t) c->SP)); SD_TRY(sd_alloc(&c->d_sigmaPiCk, (size_t) c->n1cP * c->SP));
+	SD_TRY(sd_alloc(&c->d_sigmaPiCr, (size_t) c->SP * c->n1cP));
+	SD_TRY(sd_alloc(&c->d_sigmaLam, (size_t) c->SP)); SD_TRY(sd_alloc(&c->d_sigmaCk, (size_t) c->SP));
+	SD_TRY(sd_alloc(&c->d_delta, (size_t) c->nTiles * caps->maxLambda * (1 + c->Q) * SD_TILE_W));
+	if (c->rvd > 0) SD_TRY(sd_alloc(&c->d_mask, (size_t) c->nTiles * caps->maxBasis * SD_TILE_W));
+	SD_TRY(sd_alloc(&c->d_bCk, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bFeas, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bPhiLen, (size_t) c->BP));
+	SD_TRY(sd_alloc(&c->d_bTermStart, (size_t) c->BP + 1)); SD_TRY(sd_alloc(&c->d_tSigma, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_tOmega, (size_t) c->termCap));
+	SD_TRY(sd_alloc(&c->d_state, 1));
+	cudaMemset(c->d_state, 0, sizeof(SdDevState));
+	cudaMemset(c->d_omegaW, 0, (size_t) c->NP * sizeof(int32_t));
+	cudaMemset(c->d_bTermStart, 0, ((size_t) c->BP + 1) * sizeof(int32_t));
+
+	// ---- staging ----------------------------------------------------------------------------------------
+	size_t vecLen = (size_t) std::max(std::max(c->rows, c->numRV), c->n1) + 2;
+	SD_TRY(sd_alloc(&c->d_vecIn, vecLen)); SD_TRY(sd_alloc(&c->d_cand, (size_t) std::max(c->R, c->numRV) + 1)); SD_TRY(sd_alloc(&c->d_candC, (size_t) c->n1cP));
+	c->pinDcap = vecLen + (size_t) c->n1 + 16; c->pinIcap = 64;
+	if (cudaMallocHost((void **) &c->h_pinD, c->pinDcap * sizeof(double)) != cudaSuccess ||
+	    cudaMallocHost((void **) &c->h_pinI, c->pinIcap * sizeof(int32_t)) != cudaSuccess ||
+	    cudaMallocHost((void **) &c->h_state, sizeof(SdDevState)) != cudaSuccess) {
+		sdgpu_fail("cudaMallocHost failed"); sdgpu_destroy(c); return SDGPU_ERR;
+	}
+
+	// ---- cut scratch -------------------------------------------------------------------------------------
+	c->maxChunks = SD_MAX_CHUNKS;
+	{   // the per-chunk partial maxima cost 2 * chunks * NP * 12 bytes; keep them below 1/16 of the delta table or 64 MiB
+		size_t deltaBytes = (size_t) c->nTiles * caps->maxLambda * (1 + c->Q) * SD_TILE_W * 8;
+		size_t budget = std::max<size_t>(deltaBytes / 16, (size_t) 64 << 20);
+		while (c->maxChunks > 1 && (size_t) 2 * c->maxChunks * c->NP * 12 > budget) c->maxChunks /= 2;
+	}
+	SD_TRY(sd_alloc(&c->d_x, (size_t) c->n1 + 2)); SD_TRY(sd_alloc(&c->d_piCbarX, (size_t) c->SP));
+	SD_TRY(sd_alloc(&c->d_descA, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_descC, (size_t) c->BP));
+	SD_TRY(sd_alloc(&c->d_descRow, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_descWin, (size_t) c->BP));
+	SD_TRY(sd_alloc(&c->d_partV, (size_t) 2 * c->maxChunks * c->NP)); SD_TRY(sd_alloc(&c->d_partI, (size_t) 2 * c->maxChunks * c->NP));
+	SD_TRY(sd_alloc(&c->d_iStar, (size_t) c->NP));
+	SD_TRY(sd_alloc(&c->d_tilePart, (size_t) c->nTiles * (4 + c->n1c + c->Q)));
+	SD_TRY(sd_alloc(&c->d_cutPartial, (size_t) c->n1 + 4)); SD_TRY(sd_alloc(&c->d_cutOut, (size_t) c->n1 + 4));
+#undef SD_TRY
+	if (cudaDeviceSynchronize() != cudaSuccess) { sdgpu_fail("device error during create"); sdgpu_destroy(c); return SDGPU_ERR; }
+	*out = c;
+	return 0;
+}
+
+extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	sd_nccl_release(c);
+	void *dev[] = { c->d_CCols, c->d_rvRows, c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_rvCOmCols, c->d_rvCols, c->d_bBarCol,
+		c->d_bBarVal, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->d_omega, c->d_omegaW, c->d_lambda, c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr,
+		c->d_sigmaLam, c->d_sigmaCk, c->d_delta, c->d_mask, c->d_bCk, c->d_bFeas, c->d_bPhiLen, c->d_bTermStart, c->d_tSigma, c->d_tOmega, c->d_state,
+		c->d_vecIn, c->d_cand, c->d_candC, c->d_x, c->d_piCbarX, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin, c->d_partV, c->d_partI,
+		c->d_iStar, c->d_tilePart, c->d_cutPartial, c->d_cutOut };
+	for (void *p : dev) if (p) cudaFree(p);
+	if (c->h_pinD) cudaFreeHost(c->h_pinD);
+	if (c->h_pinI) cudaFreeHost(c->h_pinI);
+	if (c->h_state) cudaFreeHost(c->h_state);
+	if (c->evA) cudaEventDestroy(c->evA);
+	if (c->evB) cudaEventDestroy(c->evB);
+	if (c->evC) cudaEventDestroy(c->evC);
+	if (c->evD) cudaEventDestroy(c->evD);
+	if (c->stream && c->ownStream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+// setup.c:242-246: counts back to zero, every allocation kept
+extern "C" int sdgpu_reset(sdgpu_ctx *c) {
+	if (!c) return sdgpu_fail("null context");
+	SD_CUDA(cudaSetDevice(c->device));
+	SD_CUDA(cudaMemsetAsync(c->d_state, 0, sizeof(SdDevState), c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	c->omegaCnt = c->lambdaCnt = c->sigmaCnt = c->basisCnt = c->termCnt = 0;
+	c->maxPhiLen = 0; c->anyInfeasibleBasis = false; c->lastOmegaCnt = 0;
+	c->basis.clear(); c->hostMask.clear();
+	return 0;
+}
+
+extern "C" int sdgpu_get_counts(sdgpu_ctx *c, sdgpu_counts *out) {
+	if (!c || !out) return sdgpu_fail("null argument");
+	out->omega = c->omegaCnt; out->lambda = c->lambdaCnt; out->sigma = c->sigmaCnt; out->basis = c->basisCnt;
+	return 0;
+}
+
+extern "C" int sdgpu_set_stream(sdgpu_ctx *c, void *stream) {
+	if (!c) return sdgpu_fail("null context");
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+	c->stream = (cudaStream_t) stream; c->ownStream = false;
+	return 0;
+}
+
+extern "C" int sdgpu_get_stats(sdgpu_ctx *c, sdgpu_stats *out) {
+	if (!c || !out) return sdgpu_fail("null argument");
+	*out = c->stats;
+	return 0;
+}
+
+// ---- omega -------------------------------------------------------------------------------------------------
+static int sd_omega_stage(sdgpu_ctx *c, const double *observ) {
+	if (sd_stage_vec(c, observ, c->numRV + 1)) return SDGPU_ERR;
+	k_stage_candidate<<<sd_blocks(c->numRV, 128), 128, 0, c->stream>>>(c->d_vecIn, nullptr, c->numRV, c->d_cand, c->d_state, 1);
+	sd_count_launch(c);
+	return 0;
+}
+
+extern "C" int sdgpu_calc_omega(sdgpu_ctx *c, const double *observ, double tol, int *newOmegaFlag) {
+	if (!c || !observ) return sdgpu_fail("null argument");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_omega_stage(c, observ)) return SDGPU_ERR;
+	if (c->omegaCnt > 0) {
+		k_find_row<<<sd_blocks(c->omegaCnt, 256), 256, 0, c->stream>>>(c->d_omega, c->NP, c->numRV, c->d_cand, tol, c->d_state, 1);
+		sd_count_launch(c);
+	}
+	k_omega_commit<<<1, 128, 0, c->stream>>>(c->d_omega, c->d_omegaW, c->NP, c->numRV, c->d_cand, c->caps.maxOmega, c->d_state, 0, 1);
+	sd_count_launch(c);
+	if (sd_sync_state(c)) return SDGPU_ERR;
+	if (newOmegaFlag) *newOmegaFlag = c->h_state->newOmega;
+	return c->h_state->omegaIdx;
+}
+
+extern "C" int sdgpu_omega_find(sdgpu_ctx *c, const double *observ, double tol) {
+	if (!c || !observ) return sdgpu_fail("null argument");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_omega_stage(c, observ)) return SDGPU_ERR;
+	if (c->omegaCnt > 0) {
+		k_find_row<<<sd_blocks(c->omegaCnt, 256), 256, 0, c->stream>>>(c->d_omega, c->NP, c->numRV, c->d_cand, tol, c->d_state, 1);
+		sd_count_launch(c);
+	}
+	if (sd_sync_state(c)) return SDGPU_ERR;
+	return c->h_state->foundOmega == INT_MAX ? SDGPU_NONE : c->h_state->foundOmega;
+}
+
+extern "C" int sdgpu_omega_append(sdgpu_ctx *c, const double *observ, int weight) {
+	if (!c || !observ) return sdgpu_fail("null argument");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_omega_stage(c, observ)) return SDGPU_ERR;
+	k_omega_commit<<<1, 128, 0, c->stream>>>(c->d_omega, c->d_omegaW, c->NP, c->numRV, c->d_cand, c->caps.maxOmega, c->d_state, 1, weight);
+	sd_count_launch(c);
+	if (sd_sync_state(c)) return SDGPU_ERR;
+	return c->h_state->omegaIdx;
+}
+
+extern "C" int sdgpu_omega_bump(sdgpu_ctx *c, int idx, int by) {
+	if (!c) return sdgpu_fail("null context");
+	if (idx < 0 || idx >= c->omegaCnt) return sdgpu_fail("omega_bump: index %d out of range", idx);
+	SD_CUDA(cudaSetDevice(c->device));
+	k_omega_bump<<<1, 1, 0, c->stream>>>(c->d_omegaW, idx, by);
+	sd_count_launch(c);
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" int sdgpu_omega_append_bulk(sdgpu_ctx *c, int64_t n, const double *vals, const int32_t *weights) {
+	if (!c || (!vals && n > 0)) return sdgpu_fail("null argument");
+	if (n <= 0) return 0;
+	if (c->omegaCnt + n > c->caps.maxOmega) return sdgpu_fail("omega_append_bulk: %lld + %lld exceeds capacity %lld", (long long) c->omegaCnt, (long long) n, (long long) c->caps.maxOmega);
+	SD_CUDA(cudaSetDevice(c->device));
+	const int64_t chunk = std::max<int64_t>(1, ((int64_t) 64 << 20) / ((c->numRV + 1) * 8));
+	double *d_vals = nullptr; int32_t *d_w = nullptr;
+	if (sd_alloc(&d_vals, (size_t) std::min(chunk, n) * (c->numRV + 1))) return SDGPU_ERR;
+	if (weights && sd_alloc(&d_w, (size_t) std::min(chunk, n))) { cudaFree(d_vals); return SDGPU_ERR; }
+	int rc = 0;
+	for (int64_t i0 = 0; i0 < n && rc == 0; i0 += chunk) {
+		int64_t m = std::min(chunk, n - i0);
+		cudaError_t e = cudaMemcpyAsync(d_vals, vals + (size_t) i0 * (c->numRV + 1), (size_t) m * (c->numRV + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+		if (e == cudaSuccess && weights) e = cudaMemcpyAsync(d_w, weights + i0, (size_t) m * 4, cudaMemcpyHostToDevice, c->stream);
+		if (e != cudaSuccess) { rc = sdgpu_fail("omega_append_bulk copy: %s", cudaGetErrorString(e)); break; }
+		k_omega_bulk<<<sd_blocks(m, 128), 128, 0, c->stream>>>(d_vals, m, c->numRV, weights ? d_w : nullptr, c->d_omega, c->d_omegaW, c->NP, c->omegaCnt + i0);
+		sd_count_launch(c);
+		if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = sdgpu_fail("omega_append_bulk kernel failed");
+	}
+	if (rc == 0) {
+		k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, (int) n, 0, 0, 0);
+		sd_count_launch(c);
+		rc = sd_sync_state(c);
+	}
+	cudaFree(d_vals); if (d_w) cudaFree(d_w);
+	return rc;
+}
+
+// ---- lambda / sigma / delta --------------------------------------------------------------------------------
+static void sd_launch_lambda(sdgpu_ctx *c, const double *d_pi, double tol, int64_t lambdaUpper) {
+	k_stage_candidate<<<sd_blocks(c->R, 128), 128, 0, c->stream>>>(d_pi, c->d_rvRows, c->R, c->d_cand, c->d_state, 0);
+	if (lambdaUpper > 0)
+		k_find_row<<<sd_blocks(lambdaUpper, 256), 256, 0, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_cand, tol, c->d_state, 0);
+	k_lambda_commit<<<1, 256, 0, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_cand, c->caps.maxLambda, c->d_state);
+	sd_count_launch(c, lambdaUpper > 0 ? 3 : 2);
+}
+
+static void sd_launch_sigma(sdgpu_ctx *c, const double *d_pi, double mubBar, int iter, double tol, int64_t sigmaUpper,
+		int overrideNew, int overrideIdx) {
+	k_sigma_prepare<<<sd_blocks(c->n1c + 1, 128), 128, 0, c->stream>>>(d_pi, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart,
+			c->d_cbRow, c->d_cbVal, c->n1c, c->d_candC, c->d_state, overrideNew, overrideIdx);
+	if (sigmaUpper > 0)
+		k_sigma_find<<<sd_blocks(sigmaUpper, 256), 256, 0, c->stream>>>(c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaLam, c->SP, c->n1c, c->d_candC, tol, c->d_state);
+	k_sigma_commit<<<1, 128, 0, c->stream>>>(c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr, c->d_sigmaLam, c->d_sigmaCk, c->SP, c->n1c, c->n1cP,
+			c->d_candC, iter, c->caps.maxSigma, c->d_state);
+	sd_count_launch(c, sigmaUpper > 0 ? 3 : 2);
+}
+
+static void sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
+	if (omegaUpper <= 0) return;
+	k_delta_row<<<sd_blocks(omegaUpper, 128), 128, (size_t) std::max(1, c->R) * 8, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow);
+	sd_count_launch(c);
+}
+
+static void sd_launch_delta_col(sdgpu_ctx *c, int forcedCol, int64_t lambdaUpper) {
+	if (lambdaUpper <= 0) return;
+	k_delta_col<<<sd_blocks(lambdaUpper, 128), 128, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol);
+	sd_count_launch(c);
+}
+
+extern "C" int sdgpu_calc_lambda(sdgpu_ctx *c, const double *Pi, double tol, int *newLambdaFlag) {
+	if (!c || !Pi) return sdgpu_fail("null argument");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_stage_vec(c, Pi, c->rows + 1)) return SDGPU_ERR;
+	sd_launch_lambda(c, c->d_vecIn, tol, c->lambdaCnt);
+	if (sd_sync_state(c)) return SDGPU_ERR;
+	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
+	return c->h_state->lambdaIdx;
+}
+
+extern "C" int sdgpu_calc_sigma(sdgpu_ctx *c, const double *pi, double mubBar, int idxLambda, int newLambdaFlag, int currentIter,
+		double tol, int *newSigmaFlag) {
+	if (!c || !pi) return sdgpu_fail("null argument");
+	if (idxLambda < 0 || idxLambda >= c->lambdaCnt) return sdgpu_fail("calc_sigma: lambda index %d out of range", idxLambda);
+	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
+	sd_launch_sigma(c, c->d_vecIn, mubBar, currentIter, tol, c->sigmaCnt, newLambdaFlag != 0, idxLambda);
+	if (sd_sync_state(c)) return SDGPU_ERR;
+	if (newSigmaFlag) *newSigmaFlag = c->h_state->newSigma;
+	return c->h_state->sigmaIdx;
+}
+
+extern "C" int sdgpu_calc_delta(sdgpu_ctx *c, int newOmegaFlag, int elemIdx) {
+	if (!c) return sdgpu_fail("null context");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (newOmegaFlag) {
+		if (elemIdx < 0 || elemIdx >= c->omegaCnt) return sdgpu_fail("calc_delta: observation %d out of range", elemIdx);
+		sd_launch_delta_col(c, elemIdx, c->lambdaCnt);
+	}
+	else {
+		if (elemIdx < 0 || elemIdx >= c->lambdaCnt) return sdgpu_fail("calc_delta: lambda %d out of range", elemIdx);
+		sd_launch_delta_row(c, elemIdx, c->omegaCnt);
+	}
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	SD_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int sdgpu_update_dual(sdgpu_ctx *c, const double *pi, double mubBar, int currentIter, double tol,
+		int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag) {
+	if (!c || !pi) return sdgpu_fail("null argument");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
+	sd_launch_lambda(c, c->d_vecIn, tol, c->lambdaCnt);                    // stocUpdate.c:78
+	sd_launch_sigma(c, c->d_vecIn, mubBar, currentIter, tol, c->sigmaCnt, -1, 0);   // :81
+	sd_launch_delta_row(c, -1, c->omegaCnt);                               // :84-85 (kernel no-op unless the lambda was new)
+	if (sd_sync_state(c)) return SDGPU_ERR;
+	if (lambdaIdx) *lambdaIdx = c->h_state->lambdaIdx;
+	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
+	if (sigmaIdx) *sigmaIdx = c->h_state->sigmaIdx;
+	if (newSigmaFlag) *newSigmaFlag = c->h_state->newSigma;
+	return 0;
+}
+
+extern "C" int sdgpu_update_dual_bulk(sdgpu_ctx *c, int64_t n, const double *pis, const double *mubBar, const int32_t *iters,
+		double tol, int32_t *lambdaIdx, int32_t *sigmaIdx) {
+	if (!c || (!pis && n > 0)) return sdgpu_fail("null argument");
+	if (n <= 0) return 0;
+	SD_CUDA(cudaSetDevice(c->device));
+	const size_t stride = (size_t) c->rows + 1;
+	const int64_t chunk = std::max<int64_t>(1, ((int64_t) 64 << 20) / (int64_t) (stride * 8));
+	double *d_pis = nullptr, *d_mub = nullptr; int32_t *d_it = nullptr, *d_li = nullptr, *d_si = nullptr;
+	int64_t cm = std::min(chunk, n);
+	int rc = 0;
+	if (sd_alloc(&d_pis, (size_t) cm * stride) || sd_alloc(&d_mub, (size_t) cm) || sd_alloc(&d_it, (size_t) cm) ||
+	    sd_alloc(&d_li, (size_t) cm) || sd_alloc(&d_si, (size_t) cm)) rc = SDGPU_ERR;
+	std::vector<int32_t> defIters;
+	for (int64_t i0 = 0; i0 < n && rc == 0; i0 += chunk) {
+		int64_t m = std::min(chunk, n - i0);
+		cudaError_t e = cudaMemcpyAsync(d_pis, pis + (size_t) i0 * stride, (size_t) m * stride * 8, cudaMemcpyHostToDevice, c->stream);
+		if (e == cudaSuccess && mubBar) e = cudaMemcpyAsync(d_mub, mubBar + i0, (size_t) m * 8, cudaMemcpyHostToDevice, c->stream);
+		if (e == cudaSuccess && iters) e = cudaMemcpyAsync(d_it, iters + i0, (size_t) m * 4, cudaMemcpyHostToDevice, c->stream);
+		if (e != cudaSuccess) { rc = sdgpu_fail("update_dual_bulk copy: %s", cudaGetErrorString(e)); break; }
+		if (tol < 0.0) {
+			// synthetic loader: no dedup scan, vector i becomes lambda row / sigma row (count + i); delta rows are the
+			// caller's to build (sdgpu_calc_delta_block)
+			if (c->lambdaCnt + m > c->caps.maxLambda || c->sigmaCnt + m > c->caps.maxSigma) { rc = sdgpu_fail("update_dual_bulk: capacity exceeded"); break; }
+			k_dual_bulk<<<sd_blocks(m, 64), 64, 0, c->stream>>>(d_pis, m, c->rows, mubBar ? d_mub : nullptr, iters ? d_it : nullptr, c->d_rvRows, c->R,
+					c->d_bBarCol, c->d_bBarVal, c->bBarCnt, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->n1c, c->n1cP, c->d_lambda, c->LP,
+					c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr, c->d_sigmaLam, c->d_sigmaCk, c->SP, c->lambdaCnt, c->sigmaCnt);
+			k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, 0, (int) m, (int) m, 0);
+			sd_count_launch(c, 2);
+			for (int64_t i = 0; i < m; i++) {
+				if (lambdaIdx) lambdaIdx[i0 + i] = (int32_t) (c->lambdaCnt + i);
+				if (sigmaIdx) sigmaIdx[i0 + i] = (int32_t) (c->sigmaCnt + i);
+			}
+			rc = sd_sync_state(c);
+		}
+		else {
+			// the real find-or-append chain, vector after vector, with no host round trip in between: counts and
+			// flags live in SdDevState, grids are sized by the host's upper bound on the counts
+			for (int64_t i = 0; i < m; i++) {
+				const double *d_pi = d_pis + (size_t) i * stride;
+				double mb = mubBar ? mubBar[i0 + i] : 0.0;
+				int it = iters ? iters[i0 + i] : (int) (i0 + i + 1);
+				sd_launch_lambda(c, d_pi, tol, c->lambdaCnt + i);
+				sd_launch_sigma(c, d_pi, mb, it, tol, c->sigmaCnt + i, -1, 0);
+				sd_launch_delta_row(c, -1, c->omegaCnt);
+				k_record_pair<<<1, 1, 0, c->stream>>>(c->d_state, d_li, d_si, i);
+				sd_count_launch(c);
+			}
+			rc = sd_sync_state(c);
+			if (rc == 0 && lambdaIdx) if (cudaMemcpy(lambdaIdx + i0, d_li, (size_t) m * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = sdgpu_fail("copy back failed");
+			if (rc == 0 && sigmaIdx) if (cudaMemcpy(sigmaIdx + i0, d_si, (size_t) m * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = sdgpu_fail("copy back failed");
+		}
+	}
+	cudaFree(d_pis); cudaFree(d_mub); cudaFree(d_it); cudaFree(d_li); cudaFree(d_si);
+	return rc;
+}
+
+extern "C" int sdgpu_calc_delta_block(sdgpu_ctx *c, int64_t l0, int64_t l1, int64_t o0, int64_t o1) {
+	if (!c) return sdgpu_fail("null context");
+	if (l0 < 0 || l1 > c->lambdaCnt || o0 < 0 || o1 > c->omegaCnt || l0 > l1 || o0 > o1) return sdgpu_fail("calc_delta_block: block out of range");
+	if (l0 == l1 || o0 == o1) return 0;
+	SD_CUDA(cudaSetDevice(c->device));
+	const int64_t maxY = 32768;
+	for (int64_t lb = l0; lb < l1; lb += maxY * DB_L) {
+		int64_t le = std::min(l1, lb + maxY * DB_L);
+		dim3 grid((unsigned) ((o1 - o0 + DB_O - 1) / DB_O), (unsigned) ((le - lb + DB_L - 1) / DB_L));
+		k_delta_block_rhs<<<grid, 256, 0, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->Rb, c->d_bLamPos, c->d_delta, c->caps.maxLambda, c->Q, lb, le, o0, o1);
+		sd_count_launch(c);
+	}
+	if (c->Q > 0) {
+		for (int64_t lb = l0; lb < l1; lb += maxY) {
+			int64_t le = std::min(l1, lb + maxY);
+			dim3 grid((unsigned) ((o1 - o0 + 127) / 128), (unsigned) (le - lb));
+			k_delta_block_T<<<grid, 128, 0, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->Rb, c->Q, c->d_cLamPos, c->d_cListStart, c->d_cList,
+					c->d_delta, c->caps.maxLambda, lb, le, o0, o1);
+			sd_count_launch(c);
+		}
+	}
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	SD_CUDA(cudaGetLastError());
+	return 0;
+}
+
+// ---- basis records (host bookkeeping mirrored to the device for the argmax) -----------------------------------
+extern "C" int sdgpu_basis_append(sdgpu_ctx *c, int ck, int feasFlag, int phiLength, const int32_t *sigmaIdx, const int32_t *omegaIdx) {
+	if (!c || !sigmaIdx) return sdgpu_fail("null argument");
+	if (phiLength < 0 || phiLength + 1 > c->caps.maxTerms) return sdgpu_fail("basis_append: phiLength %d exceeds maxTerms %d", phiLength, c->caps.maxTerms);
+	if (phiLength > 0 && !omegaIdx) return sdgpu_fail("basis_append: omegaIdx required when phiLength > 0");
+	if (c->basisCnt >= c->caps.maxBasis) return sdgpu_fail("basis capacity %lld exceeded", (long long) c->caps.maxBasis);
+	for (int t = 0; t <= phiLength; t++) {
+		if (sigmaIdx[t] < 0 || sigmaIdx[t] >= c->sigmaCnt) return sdgpu_fail("basis_append: sigma index %d out of range", sigmaIdx[t]);
+		if (t > 0 && (omegaIdx[t] < 1 || c->rvOffset[2] + omegaIdx[t] > c->numRV)) return sdgpu_fail("basis_append: omegaIdx %d out of range", omegaIdx[t]);
+	}
+	SD_CUDA(cudaSetDevice(c->device));
+	int b = (int) c->basisCnt;
+	SdHostBasis hb;
+	hb.ck = ck; hb.feas = feasFlag != 0; hb.phiLen = phiLength; hb.weight = 1;
+	hb.sigmaIdx.assign(sigmaIdx, sigmaIdx + phiLength + 1);
+	hb.omegaIdx.assign(phiLength + 1, 0);
+	for (int t = 1; t <= phiLength; t++) hb.omegaIdx[t] = omegaIdx[t];
+	int32_t *pi = c->h_pinI;      // [ck, feas, phiLen, termStart, termEnd, sigma..., omega...]
+	int nT = phiLength + 1;
+	if ((size_t) (5 + 2 * nT) > c->pinIcap) return sdgpu_fail("basis_append: too many terms for the staging buffer");
+	pi[0] = ck; pi[1] = hb.feas; pi[2] = phiLength; pi[3] = (int32_t) c->termCnt; pi[4] = (int32_t) (c->termCnt + nT);
+	for (int t = 0; t < nT; t++) { pi[5 + t] = hb.sigmaIdx[t]; pi[5 + nT + t] = hb.omegaIdx[t]; }
+	SD_CUDA(cudaMemcpyAsync(c->d_bCk + b, pi + 0, 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_bFeas + b, pi + 1, 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_bPhiLen + b, pi + 2, 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_bTermStart + b, pi + 3, 8, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_tSigma + c->termCnt, pi + 5, (size_t) nT * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_tOmega + c->termCnt, pi + 5 + nT, (size_t) nT * 4, cudaMemcpyHostToDevice, c->stream));
+	if (c->rvd > 0) {
+		c->hostMask.emplace_back(hb.feas ? std::vector<uint8_t>((size_t) c->NP, 1) : std::vector<uint8_t>());
+		if (hb.feas) {
+			k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, b, c->NP, nullptr, 0, 1);
+			sd_count_launch(c);
+		}
+	}
+	k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, 0, 0, 0, 1);
+	sd_count_launch(c);
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	c->basis.push_back(std::move(hb));
+	c->termCnt += nT; c->basisCnt++;
+	c->maxPhiLen = std::max(c->maxPhiLen, phiLength);
+	if (!feasFlag) c->anyInfeasibleBasis = true;
+	return b;
+}
+
+extern "C" int sdgpu_basis_find_or_append(sdgpu_ctx *c, int retainBasis, int obsIdx, int ck, int feasFlag, int phiLength,
+		const int32_t *sigmaIdx, const int32_t *omegaIdx, int *newBasisFlag) {
+	if (!c || !sigmaIdx) return sdgpu_fail("null argument");
+	if (newBasisFlag) *newBasisFlag = 1;
+	if (!retainBasis) {                                   // stocUpdate.c:101-113
+		if (obsIdx < 0 || obsIdx >= c->omegaCnt) return sdgpu_fail("basis_find_or_append: observation %d out of range", obsIdx);
+		for (int64_t b = 0; b < c->basisCnt; b++) {
+			const SdHostBasis &hb = c->basis[b];
+			bool feasAtObs = hb.feas && (c->rvd == 0 || c->hostMask[b][obsIdx]);
+			if (hb.phiLen == phiLength && feasAtObs && std::equal(hb.sigmaIdx.begin(), hb.sigmaIdx.end(), sigmaIdx)) {
+				c->basis[b].weight++;
+				if (newBasisFlag) *newBasisFlag = 0;
+				return (int) b;
+			}
+		}
+	}
+	return sdgpu_basis_append(c, ck, feasFlag, phiLength, sigmaIdx, omegaIdx);
+}
+
+extern "C" int sdgpu_basis_set_obs_feasible_row(sdgpu_ctx *c, int basisIdx, const uint8_t *flags) {
+	if (!c || !flags) return sdgpu_fail("null argument");
+	if (basisIdx < 0 || basisIdx >= c->basisCnt || !c->basis[basisIdx].feas) return sdgpu_fail("set_obs_feasible_row: bad basis %d", basisIdx);
+	if (c->rvd == 0) return 0;          // checkBasisFeasibility is constant true without random costs (randCost.c:208)
+	SD_CUDA(cudaSetDevice(c->device));
+	uint8_t *d_f = nullptr;
+	if (sd_alloc(&d_f, (size_t) std::max<int64_t>(1, c->omegaCnt))) return SDGPU_ERR;
+	cudaMemcpyAsync(d_f, flags, (size_t) c->omegaCnt, cudaMemcpyHostToDevice, c->stream);
+	k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, basisIdx, c->NP, d_f, c->omegaCnt, 0);
+	sd_count_launch(c);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_f);
+	if (e != cudaSuccess) return sdgpu_fail("set_obs_feasible_row: %s", cudaGetErrorString(e));
+	for (int64_t o = 0; o < c->omegaCnt; o++) c->hostMask[basisIdx][o] = flags[o] != 0;
+	return 0;
+}
+
+extern "C" int sdgpu_basis_set_obs_feasible_col(sdgpu_ctx *c, int obsIdx, const uint8_t *flags) {
+	if (!c || !flags) return sdgpu_fail("null argument");
+	if (obsIdx < 0 || obsIdx >= c->caps.maxOmega) return sdgpu_fail("set_obs_feasible_col: bad observation %d", obsIdx);
+	if (c->rvd == 0 || c->basisCnt == 0) return 0;
+	SD_CUDA(cudaSetDevice(c->device));
+	uint8_t *d_f = nullptr;
+	if (sd_alloc(&d_f, (size_t) c->basisCnt)) return SDGPU_ERR;
+	cudaMemcpyAsync(d_f, flags, (size_t) c->basisCnt, cudaMemcpyHostToDevice, c->stream);
+	k_mask_fill_col<<<sd_blocks(c->basisCnt, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, obsIdx, d_f, c->d_bFeas, c->basisCnt);
+	sd_count_launch(c);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_f);
+	if (e != cudaSuccess) return sdgpu_fail("set_obs_feasible_col: %s", cudaGetErrorString(e));
+	for (int64_t b = 0; b < c->basisCnt; b++) if (c->basis[b].feas) c->hostMask[b][obsIdx] = flags[b] != 0;
+	return 0;
+}
+
+extern "C" int sdgpu_basis_set_obs_feasible(sdgpu_ctx *c, int basisIdx, int obsIdx, int flag) {
+	if (!c) return sdgpu_fail("null context");
+	if (basisIdx < 0 || basisIdx >= c->basisCnt || !c->basis[basisIdx].feas) return sdgpu_fail("set_obs_feasible: bad basis %d", basisIdx);
+	if (obsIdx < 0 || obsIdx >= c->caps.maxOmega) return sdgpu_fail("set_obs_feasible: bad observation %d", obsIdx);
+	if (c->rvd == 0) return 0;
+	SD_CUDA(cudaSetDevice(c->device));
+	uint8_t v = flag != 0;
+	SD_CUDA(cudaMemcpyAsync(c->d_mask + sd_mask_off(c->caps.maxBasis, basisIdx, obsIdx), &v, 1, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	c->hostMask[basisIdx][obsIdx] = v;
+	return 0;
+}
+
+// ---- readers --------------------------------------------------------------------------------------------------
+extern "C" int sdgpu_get_omega(sdgpu_ctx *c, int idx, double *vals, int *weight) {
+	if (!c) return sdgpu_fail("null context");
+	if (idx < 0 || idx >= c->omegaCnt) return sdgpu_fail("get_omega: index %d out of range", idx);
+	SD_CUDA(cudaSetDevice(c->device));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	if (vals && c->numRV > 0) SD_CUDA(cudaMemcpy2D(vals + 1, 8, c->d_omega + idx, (size_t) c->NP * 8, 8, c->numRV, cudaMemcpyDeviceToHost));
+	if (weight) { int32_t w; SD_CUDA(cudaMemcpy(&w, c->d_omegaW + idx, 4, cudaMemcpyDeviceToHost)); *weight = w; }
+	return 0;
+}
+
+extern "C" int sdgpu_get_lambda(sdgpu_ctx *c, int idx, double *vals) {
+	if (!c || !vals) return sdgpu_fail("null argument");
+	if (idx < 0 || idx >= c->lambdaCnt) return sdgpu_fail("get_lambda: index %d out of range", idx);
+	SD_CUDA(cudaSetDevice(c->device));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	if (c->R > 0) SD_CUDA(cudaMemcpy2D(vals + 1, 8, c->d_lambda + idx, (size_t) c->LP * 8, 8, c->R, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int sdgpu_get_sigma(sdgpu_ctx *c, int idx, double *pib, double *piC, int *lambdaIdx, int *ck) {
+	if (!c) return sdgpu_fail("null context");
+	if (idx < 0 || idx >= c->sigmaCnt) return sdgpu_fail("get_sigma: index %d out of range", idx);
+	SD_CUDA(cudaSetDevice(c->device));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	if (pib) SD_CUDA(cudaMemcpy(pib, c->d_sigmaPib + idx, 8, cudaMemcpyDeviceToHost));
+	if (piC && c->n1c > 0) SD_CUDA(cudaMemcpy(piC + 1, c->d_sigmaPiCr + (size_t) idx * c->n1cP, (size_t) c->n1c * 8, cudaMemcpyDeviceToHost));
+	if (lambdaIdx) { int32_t v; SD_CUDA(cudaMemcpy(&v, c->d_sigmaLam + idx, 4, cudaMemcpyDeviceToHost)); *lambdaIdx = v; }
+	if (ck) { int32_t v; SD_CUDA(cudaMemcpy(&v, c->d_sigmaCk + idx, 4, cudaMemcpyDeviceToHost)); *ck = v; }
+	return 0;
+}
+
+extern "C" int sdgpu_get_delta(sdgpu_ctx *c, int lambdaIdx, int obsIdx, double *pib, double *piC) {
+	if (!c) return sdgpu_fail("null context");
+	if (lambdaIdx < 0 || lambdaIdx >= c->lambdaCnt || obsIdx < 0 || obsIdx >= c->omegaCnt) return sdgpu_fail("get_delta: (%d, %d) out of range", lambdaIdx, obsIdx);
+	SD_CUDA(cudaSetDevice(c->device));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	const double *base = c->d_delta + sd_delta_off(c->caps.maxLambda, c->Q, lambdaIdx, 0, obsIdx);
+	if (pib) SD_CUDA(cudaMemcpy(pib, base, 8, cudaMemcpyDeviceToHost));
+	if (piC && c->Q > 0) SD_CUDA(cudaMemcpy2D(piC + 1, 8, base + SD_TILE_W, (size_t) SD_TILE_W * 8, 8, c->Q, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// a rectangular block of delta.pib (row-major [l1-l0][o1-o0]) for host code that walks the table (optimal.c:203-221)
+extern "C" int sdgpu_get_delta_block(sdgpu_ctx *c, int64_t l0, int64_t l1, int64_t o0, int64_t o1, int plane, double *out) {
+	if (!c || !out) return sdgpu_fail("null argument");
+	if (l0 < 0 || l1 > c->lambdaCnt || o0 < 0 || o1 > c->omegaCnt || l0 > l1 || o0 > o1 || plane < 0 || plane > c->Q) return sdgpu_fail("get_delta_block: out of range");
+	SD_CUDA(cudaSetDevice(c->device));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	for (int64_t l = l0; l < l1; l++) {
+		int64_t o = o0;
+		while (o < o1) {
+			int64_t tEnd = std::min<int64_t>(o1, (o / SD_TILE_W + 1) * SD_TILE_W);
+			SD_CUDA(cudaMemcpy(out + (size_t) (l - l0) * (o1 - o0) + (o - o0), c->d_delta + sd_delta_off(c->caps.maxLambda, c->Q, l, plane, o),
+					(size_t) (tEnd - o) * 8, cudaMemcpyDeviceToHost));
+			o = tEnd;
+		}
+	}
+	return 0;
+}

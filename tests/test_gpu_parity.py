@@ -1,0 +1,184 @@
+"""GPU parity (run on the B200 box with -m gpu): the CUDA library against the CPU oracle through the same C
+ABI, on the same seeded traces.  Bar (BASELINE.json north_star): every index bit-exact (observation, lambda,
+sigma, basis, iStar with the reference's tie-break), tables bit-identical (same operation order, no FMA),
+cut coefficients / cummOld / cummAll within 1e-9 relative (the only place the summation order differs)."""
+import numpy as np
+import pytest
+
+import oracle_loader
+import stochasticdecomposition_b200 as sd
+from replay import assert_records_match, assert_tables_identical, replay
+from stochasticdecomposition_b200._abi import Caps
+from stochasticdecomposition_b200.synthetic import make_problem, make_trace, problem_for
+from test_oracle_vs_ref import CASES, roomy_caps
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9   # BASELINE.json: "cut coefficients ... within 1e-9 relative"
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_trace_parity(name):
+    pk, K, dpool, opool, phi_len, rk = CASES[name]
+    prob = make_problem(1000 + len(name), **pk)
+    trace = make_trace(prob, K, seed=77 + K, dual_pool=dpool, obs_pool=opool, phi_len=phi_len)
+    caps = roomy_caps(K, phi_len)
+    port = replay(oracle_loader.oracle(), prob, trace, caps, **rk)
+    gpu = replay(sd.load_library(), prob, trace, caps, **rk)
+    assert_records_match(port, gpu, exact_cut=False, rtol=RTOL)
+    assert_tables_identical(port.tables, gpu.tables)
+
+
+@pytest.mark.parametrize("shape", ["pgp2", "20term_T", "ssn"])
+def test_named_shapes(shape):
+    prob = problem_for(shape)
+    K = 40
+    trace = make_trace(prob, K, seed=5, dual_pool=9, obs_pool=14)
+    caps = roomy_caps(K)
+    port = replay(oracle_loader.oracle(), prob, trace, caps)
+    gpu = replay(sd.load_library(), prob, trace, caps)
+    assert_records_match(port, gpu, exact_cut=False, rtol=RTOL)
+
+
+def _bulk_tables(api, prob, pis, mub, iters, obs, weights, caps, tol=-1.0):
+    t = api.create(prob, caps)
+    t.omega_append_bulk(obs, weights)
+    li, si = t.update_dual_bulk(pis, mub, iters, tol)
+    c = t.counts()
+    if tol < 0:
+        t.calc_delta_block(0, c["lambda"], 0, c["omega"])
+    for s in si if tol < 0 else sorted(set(si.tolist())):
+        t.basis_append(int(iters[0]) if tol >= 0 else int(iters[s]), True, [int(s)])
+    return t, li, si
+
+
+@pytest.mark.parametrize("D,N,Q", [(700, 1500, 0), (300, 1100, 3), (2100, 600, 0)])
+def test_bulk_multi_tile_multi_chunk(D, N, Q):
+    """Several observation tiles and several basis chunks; ties forced by duplicated duals (lowest index must
+    win) and all-zero observations; both pi_eval modes; weights > 1."""
+    prob = make_problem(9, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=Q)
+    rng = np.random.default_rng(D + N)
+    pis = rng.uniform(-1, 1, (D, prob.rows + 1)) * (rng.random((D, prob.rows + 1)) > 0.3)
+    dup = rng.choice(np.arange(1, D), size=max(1, D // 50), replace=False)
+    for d in dup:
+        pis[d] = pis[rng.integers(0, d)]                       # exact copy of an earlier dual -> equal scores
+    mub = np.zeros(D)
+    iters = np.ceil((np.arange(D) + 1) * (1.25 * N) / D).astype(np.int32)   # monotone ck, ~90/10 window split
+    obs = rng.normal(0, 1, (N, prob.numRV + 1)); obs[:, 0] = 0
+    obs[rng.choice(N, 16, replace=False)] = 0.0
+    weights = (1 + rng.poisson(0.25, N)).astype(np.int32)
+    k = int(weights.sum())
+    caps = Caps(D + 2, D + 2, D + 2, N + 3, 1)
+    to, lo, so = _bulk_tables(oracle_loader.oracle(), prob, pis, mub, iters, obs, weights, caps)
+    tg, lg, sg = _bulk_tables(sd.load_library(), prob, pis, mub, iters, obs, weights, caps)
+    assert np.array_equal(lo, lg) and np.array_equal(so, sg)
+    for plane in range(Q + 1):
+        a = to.get_delta_block(0, D, 0, N, plane); b = tg.get_delta_block(0, D, 0, N, plane)
+        assert np.array_equal(a.view(np.int64), b.view(np.int64)), f"delta plane {plane} differs"
+    x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
+    for pi_eval in (0, 1):
+        co = to.sd_cut(x, k, pi_eval, 0.0); cg = tg.sd_cut(x, k, pi_eval, 0.0)
+        assert co is not None and cg is not None
+        assert np.array_equal(co.iStar, cg.iStar), np.nonzero(co.iStar != cg.iStar)[0][:10]
+        assert len(set(co.iStar.tolist())) > 3
+        scale = max(abs(co.alpha), np.abs(co.beta[1:]).max())
+        assert abs(co.alpha - cg.alpha) <= RTOL * abs(co.alpha)
+        assert np.abs(co.beta - cg.beta).max() <= RTOL * scale
+        assert abs(co.cummOld - cg.cummOld) <= RTOL * max(abs(co.cummOld), 1e-300)
+        assert abs(co.cummAll - cg.cummAll) <= RTOL * max(abs(co.cummAll), 1e-300)
+    # the one-at-a-time appends after a bulk load agree with the bulk block (same cell arithmetic)
+    newobs = rng.normal(0, 1, prob.numRV + 1)
+    for t in (to, tg):
+        oi, new = t.calc_omega(newobs, 1e-3)
+        assert new and oi == N
+        t.calc_delta(True, oi)
+    a = to.get_delta_block(0, D, N, N + 1); b = tg.get_delta_block(0, D, N, N + 1)
+    assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+def test_bulk_dedup_chain_matches_single_calls():
+    prob = make_problem(4, rows=30, cols=40, n1=10, n1c=8, R=12, Rb=9, Q=2)
+    rng = np.random.default_rng(3)
+    pool = rng.uniform(-1, 1, (25, prob.rows + 1))
+    pis = pool[rng.integers(0, 25, 120)] + rng.uniform(-3e-4, 3e-4, (120, prob.rows + 1))
+    obs = rng.normal(0, 1, (70, prob.numRV + 1))
+    iters = np.arange(1, 121, dtype=np.int32)
+    caps = Caps(130, 130, 130, 80, 1)
+    res = []
+    for api in (oracle_loader.oracle(), sd.load_library()):
+        t = api.create(prob, caps)
+        t.omega_append_bulk(obs, None)
+        li, si = t.update_dual_bulk(pis, None, iters, 1e-3)
+        res.append((t, li, si))
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    assert res[0][0].counts() == res[1][0].counts()
+    assert res[0][0].counts()["lambda"] < 120
+    assert_tables_identical(res[0][0], res[1][0])
+
+
+def test_reset_and_reuse():
+    """cleanCellType (setup.c:242-246): tables are emptied between replications and must refill identically."""
+    prob = problem_for("pgp2")
+    K = 30
+    trace = make_trace(prob, K, seed=12, dual_pool=5, obs_pool=6)
+    caps = roomy_caps(K)
+    api = sd.load_library()
+    first = replay(api, prob, trace, caps)
+    t = first.tables
+    t.reset()
+    assert t.counts() == {"omega": 0, "lambda": 0, "sigma": 0, "basis": 0}
+    second = replay(api, prob, trace, caps)
+    assert_records_match(first, second, exact_cut=True)
+
+
+def test_null_cut_and_errors():
+    prob = problem_for("pgp2")
+    api = sd.load_library()
+    t = api.create(prob, Caps(8, 8, 8, 8, 1))
+    x = np.zeros(prob.prevCols + 1)
+    obs = np.arange(prob.numRV + 1, dtype=float)
+    t.calc_omega(obs, 1e-3)
+    assert t.sd_cut(x, 1, 0, 0.0) is None                      # no basis at all -> NULL cut (cuts.c:136-139)
+    pi = np.linspace(-1, 1, prob.rows + 1)
+    t.stochastic_updates(0, True, pi, 0.0, 5, 1e-3)            # ck = 5 > numSamples = 1: not eligible
+    assert t.sd_cut(x, 1, 0, 0.0) is None
+    assert t.sd_cut(x, 5, 0, 0.0) is not None
+    with pytest.raises(sd.SdError, match="capacity"):
+        for i in range(20):
+            t.calc_omega(obs + i + 1, 1e-3)
+    with pytest.raises(sd.SdError):
+        t.calc_delta(True, 99)
+
+
+def test_heights_reform_istar_single():
+    prob = make_problem(21, rows=20, cols=30, n1=8, n1c=6, R=9, Rb=6, Q=3)
+    K = 30
+    trace = make_trace(prob, K, seed=4, dual_pool=9, obs_pool=12)
+    caps = roomy_caps(K)
+    port = replay(oracle_loader.oracle(), prob, trace, caps, lb=-2.0)
+    gpu = replay(sd.load_library(), prob, trace, caps, lb=-2.0)
+    cuts = [c for c in port.cuts if c is not None][-6:]
+    alpha = np.array([c.alpha for c in cuts]); beta = np.stack([c.beta for c in cuts])
+    ns = np.array([c.numSamples for c in cuts], np.int32); ai = alpha - 1.0
+    xk = trace.xs[-1, 0]
+    a = port.tables.cut_heights(alpha, beta, ns, ai, K, xk, -2.0)
+    b = gpu.tables.cut_heights(alpha, beta, ns, ai, K, xk, -2.0)
+    assert a[0] == b[0] >= 0
+    for u, v in zip(a[1:], b[1:]):
+        assert np.array_equal(u.view(np.int64), v.view(np.int64))      # sequential per cut: bit-identical
+    rng = np.random.default_rng(8)
+    last = cuts[-1]
+    for lbtype, lbv in ((0, 0.0), (1, -7.9)):
+        observ = rng.integers(0, port.counts["omega"] + 3, size=K).astype(np.int32)
+        ar, br = port.tables.reform_cut(last.iStar, observ, K, lbtype, lbv)
+        ag, bg = gpu.tables.reform_cut(last.iStar, observ, K, lbtype, lbv)
+        assert abs(ar - ag) <= RTOL * max(abs(ar), 1e-300)
+        assert np.abs(br - bg).max() <= RTOL * max(np.abs(br).max(), 1e-300)
+    x = trace.xs[3, 0]
+    for obs in range(port.counts["omega"]):
+        for pi_eval in (0, 1):
+            for is_new in (0, 1):
+                p = port.tables.compute_istar(x, obs, K, pi_eval, is_new)
+                g = gpu.tables.compute_istar(x, obs, K, pi_eval, is_new)
+                assert p[0] == g[0]
+                if p[0] >= 0:
+                    assert np.float64(p[1]).tobytes() == np.float64(g[1]).tobytes()
