@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- SD cut formation throughput (dual x observation argmax pairs / second) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (libsdgpu.so)
+    python bench.py --impl reference [...]                          # the reference's own CPU SDCut (oracle/_ref)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, observations sharded
+
+Workload (BASELINE.json config 5, the synthetic cut-formation sweep): `--duals` stored dual vertices x
+`--obs-per-gpu` observations per GPU x `--rv` random right-hand-side elements, weak scaling in the observation
+count -- the default 65 536 x 131 072 per GPU is the 64K x 1M x 256 configuration at 8 GPUs and a 64 GiB delta
+table per GPU.  One "step" is one SDCut (two-window pi_eval mode, the shipped default config.sd) over the
+resident tables: `value` times exactly that with CUDA events; `e2e` times one whole SD iteration through the
+C ABI with host buffers (new observation -> calcOmega + delta column, new dual vertex -> calcLambda / calcSigma
+/ delta row, then SDCut with x from the host and alpha / beta / iStar back on the host), wall clock.
+The delta table (64 GiB) is far larger than L2 (126 MB), so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "dual x observation argmax pairs/sec (SD cut formation)"
+UNIT = "pairs/s"
+SEED = 20240607
+
+
+# --------------------------------------------------------------------------------------------------------------
+# synthetic tables
+# --------------------------------------------------------------------------------------------------------------
+def make_workload(duals: int, obs: int, rv: int, n1: int, rank: int, extra: int):
+    """Same duals on every rank (replicated lambda / sigma), a rank-specific shard of observations."""
+    from stochasticdecomposition_b200.synthetic import make_problem
+    rows = max(rv, 8)
+    prob = make_problem(SEED, rows=rows, cols=2 * rows, n1=n1, n1c=n1, R=rv, Rb=rv, Q=0, rvd=0)
+    rng = np.random.default_rng(SEED)
+    pis = rng.uniform(-1.0, 1.0, (duals + extra, rows + 1))
+    pis[rng.random(pis.shape) < 0.3] = 0.0                         # 30 % exact zeros
+    ncopy = max(1, duals // 100)                                   # tie stress: 1 % exact copies of an earlier dual
+    dst = rng.choice(np.arange(1, duals), size=ncopy, replace=False)
+    for d in dst:
+        pis[d] = pis[rng.integers(0, d)]
+    pis[:, 0] = 0.0
+    orng = np.random.default_rng(SEED + 1000 * (rank + 1))
+    obsv = orng.normal(0.0, 1.0, (obs + extra, prob.numRV + 1))
+    obsv[:, 0] = 0.0
+    if rank == 0:
+        obsv[orng.choice(obs, size=min(16, obs), replace=False)] = 0.0    # 16 all-zero observations
+    weights = (1 + orng.poisson(0.25, obs)).astype(np.int32)
+    xs = rng.uniform(0.0, 1.0, (64, n1 + 1))
+    xs[:, 0] = 0.0
+    return prob, pis, obsv, weights, xs
+
+
+def load_tables(api, prob, pis, obsv, weights, duals, obs, k_total, extra, device=0):
+    from stochasticdecomposition_b200._abi import Caps
+    caps = Caps(duals + extra + 8, duals + extra + 8, duals + extra + 8, obs + extra + 8, 1)
+    t = api.create(prob, caps, device)
+    t.omega_append_bulk(obsv[:obs], weights)
+    iters = np.ceil((np.arange(duals) + 1) * (k_total / duals)).astype(np.int32)      # monotone ck: ~90/10 window split
+    t.update_dual_bulk(pis[:duals], None, iters, -1.0)
+    t.calc_delta_block(0, duals, 0, obs)
+    t.basis_append_bulk(iters, np.arange(duals, dtype=np.int32))   # one basis per sigma (plain branch: basis index == sigma index)
+    return t
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(duals, obs):
+    """dram bytes per sweep launch from the committed ncu capture, if one exists for this shape."""
+    path = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    try:
+        with open(path) as fh:
+            rec = json.load(fh)
+        for r in rec.get("captures", []):
+            if r.get("duals") == duals and r.get("obs") == obs:
+                return r.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU legs (test infrastructure used as the measured-beside baseline only)
+# --------------------------------------------------------------------------------------------------------------
+def cpu_sample_dims(args):
+    return min(args.cpu_duals, args.duals), min(args.cpu_obs, args.obs_per_gpu)
+
+
+def run_cpu(kind: str, args, steps: int, warmup: int):
+    """Times SDCut on a bounded sample of the workload.  kind = "reference": the reference's own cuts.c /
+    stocUpdate.c (oracle/_ref, single thread -- the reference has no threading); "port_omp": the restated
+    oracle with OpenMP over observations on all host cores."""
+    import oracle_loader
+    from stochasticdecomposition_b200._abi import CCut, Caps, _pf64, _pi32
+    import ctypes as C
+    D, N = cpu_sample_dims(args)
+    prob, pis, obsv, weights, xs = make_workload(D, N, args.rv, args.n1, 0, 0)
+    k_total = int(weights.sum())
+    iters = np.ceil((np.arange(D) + 1) * (k_total / D)).astype(np.int32)
+    caps = Caps(D + 8, D + 8, D + 8, N + 8, 1)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        api = oracle_loader.reference()
+        t = api.create(prob, caps)
+        li, si = np.zeros(D, np.int32), np.zeros(D, np.int32)
+        o, p = np.ascontiguousarray(obsv[:N]), np.ascontiguousarray(pis[:D])
+        st = api._fn("bulk_load")(t.ctx, N, _pf64(o), _pi32(weights), D, _pf64(p), None, _pi32(iters), -1.0, _pi32(li), _pi32(si))
+        assert st == 0
+        cores, variant = 1, "sd_cut"
+    else:
+        api = oracle_loader.oracle()
+        t = api.create(prob, caps)
+        t.omega_append_bulk(obsv[:N], weights)
+        li, si = t.update_dual_bulk(pis[:D], None, iters, -1.0)
+        t.calc_delta_block(0, D, 0, N)
+        cores, variant = os.cpu_count() or 1, "sd_cut_omp"
+    for b in range(int(si.max()) + 1):
+        t.basis_append(int(iters[b]), True, [b])          # (the reference build has no bulk form; a few thousand calls)
+    nb = t.counts()["basis"]
+    build_s = time.perf_counter() - t0
+    beta = np.zeros(prob.prevCols + 1)
+    istar = np.zeros(N, np.int32)
+    cut = CCut(0.0, _pf64(beta), _pi32(istar), 0, 0, 0.0, 0.0)
+    fn = api._fn(variant)
+    nt = C.c_int(0)
+    times = []
+    for s in range(warmup + steps):
+        x = np.ascontiguousarray(xs[s % len(xs)])
+        t1 = time.perf_counter()
+        if variant == "sd_cut_omp":
+            st = fn(t.ctx, _pf64(x), k_total, 1, 0.0, C.byref(cut), C.byref(nt))
+        else:
+            st = fn(t.ctx, _pf64(x), k_total, 1, 0.0, C.byref(cut))
+        dt = time.perf_counter() - t1
+        assert st == 0, st
+        if s >= warmup:
+            times.append(dt)
+    if variant == "sd_cut_omp":
+        cores = nt.value
+    sec = float(np.mean(times))
+    return {"value": nb * N / sec, "unit": UNIT, "cores": cores, "kind": "reference" if kind == "reference" else "port",
+            "sample": f"{nb} duals x {N} observations x {args.rv} random elements, pi_eval on, {steps} SDCut calls "
+                      f"({sec * 1e3:.1f} ms each; table build {build_s:.1f} s not timed)",
+            "ms_per_step": sec * 1e3, "pairs_per_step": nb * N}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    res = run_cpu("reference", args, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": res["sample"],
+                       "note": "reference's own SDCut/computeIstar (cuts.c, stocUpdate.c) built from /root/reference against the header "
+                               "shim; single thread because the reference is single-threaded"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"synthetic cut-formation sweep: {args.duals} dual vertices x {args.obs_per_gpu} observations per GPU x "
+            f"{args.rv} random elements, n1={args.n1}, Q=0, pi_eval two-window mode")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import stochasticdecomposition_b200 as sd
+    from stochasticdecomposition_b200._abi import CCut, _pf64, _pi32
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+
+    api = sd.load_library()
+    D, N = args.duals, args.obs_per_gpu
+    extra = args.steps + args.warmup + 4
+    prob, pis, obsv, weights, xs = make_workload(D, N, args.rv, args.n1, rank, extra)
+    k_local = int(weights.sum())
+    k_total = k_local
+    if world > 1:
+        kt = torch.tensor([k_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(kt)
+        k_total = int(kt.item())
+    t_setup = time.perf_counter()
+    t = load_tables(api, prob, pis, obsv, weights, D, N, k_total, extra, local)
+    setup_s = time.perf_counter() - t_setup
+    if world > 1:                                                   # hand the library its own NCCL communicator
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            assert api._fn("nccl_unique_id")(raw) == 0, api.error()
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_char * 128).from_buffer_copy(bytes(idbuf.cpu().numpy().tobytes()))
+        assert api._fn("nccl_init")(t.ctx, world, rank, raw) == 0, api.error()
+
+    stream = torch.cuda.Stream()
+    t._check(api._fn("set_stream")(t.ctx, C.c_void_p(stream.cuda_stream)), "set_stream")
+    beta = np.zeros(prob.prevCols + 1)
+    istar = np.zeros(N + extra + 8, np.int32)
+    cut_dev = CCut(0.0, _pf64(beta), None, 0, 0, 0.0, 0.0)           # iStar stays device-resident
+    cut_host = CCut(0.0, _pf64(beta), _pi32(istar), 0, 0, 0.0, 0.0)
+    sd_cut = api._fn("sd_cut")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_cut(step, cut):
+        x = np.ascontiguousarray(xs[step % len(xs)])
+        st = sd_cut(t.ctx, _pf64(x), k_total, 1, 0.0, C.byref(cut))
+        if st != 0:
+            raise RuntimeError(f"sd_cut failed ({st}): {api.error()}")
+
+    # ---- value: K cuts over resident tables, CUDA events on the library's stream -------------------------------
+    for s in range(args.warmup):
+        one_cut(s, cut_dev)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = t.stats()["total_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    sweep_ms = []
+    for s in range(args.steps):
+        one_cut(args.warmup + s, cut_dev)
+        sweep_ms.append(t.stats()["last_sweep_ms"])
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    st = t.stats()
+    launches = st["total_launches"] - l0
+    ms_total = ev0.elapsed_time(ev1)
+    if dist is not None:
+        mt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        ms_total = float(mt.item())
+    ms_step = ms_total / args.steps
+    nb = t.counts()["basis"]
+    pairs_step = nb * N * world
+    value = pairs_step / (ms_step * 1e-3)
+    sweep_bytes = st["last_sweep_bytes"]
+    sweep_avg_ms = float(np.mean(sweep_ms))
+    peak, peak_src = measured_peak()
+    achieved = sweep_bytes / (sweep_avg_ms * 1e-3) / 1e9
+
+    # ---- e2e: whole SD iterations through the C ABI with host buffers, wall clock --------------------------------
+    def one_iteration(i):
+        ob = np.ascontiguousarray(obsv[N + i])
+        oi, onew = t.calc_omega(ob, 1e-3)
+        bi, bnew = t.stochastic_updates(oi, onew, np.ascontiguousarray(pis[D + i]), 0.0, k_total, 1e-3)
+        one_cut(i, cut_host)
+        return oi, bi
+
+    one_iteration(0)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(1, 1 + args.steps):
+        one_iteration(i)
+    barrier()
+    e2e_s = (time.perf_counter() - w0)
+    if dist is not None:
+        mt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        e2e_s = float(mt.item())
+    cnt = t.counts()
+    e2e_pairs = cnt["basis"] * cnt["omega"] * world          # tables grew by one per iteration; use the final size (upper bound within 0.01 %)
+    e2e_value = (nb * N * world) / (e2e_s / args.steps)
+    h2d = 8 * (prob.numRV + 1) + 8 * (prob.rows + 1) + 8 * (prob.prevCols + 1)
+    d2h = 8 * (prob.prevCols + 4) + 4 * cnt["omega"] + 64
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu("reference", args, 3, 1)
+        cpu_omp = run_cpu("port_omp", args, 3, 1)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "duals": nb, "observations_total": N * world, "delta_table_GiB_per_gpu": round(8 * nb * N / 2**30, 2),
+                       "l2_policy": "inputs (64 GiB delta stream per step) far exceed the 126 MB L2; no flush needed",
+                       "timing": "value: CUDA events on the library stream around K SDCut calls; e2e: wall clock around K full SD iterations "
+                                 "(calcOmega, calcLambda/calcSigma/calcDelta, SDCut) with host buffers",
+                       "sharding": "observations split across ranks, lambda/sigma/basis replicated, one NCCL all-reduce of n1+4 doubles per cut" if world > 1 else "single GPU",
+                       "setup_s": round(setup_s, 2)},
+            "roofline": {"bound": "hbm", "kernel": "k_sweep_ldg", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": ncu_traffic(nb, N), "bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_avg_ms,
+                         "sweep_share_of_step": sweep_avg_ms / ms_step},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline_omp_port"] = {k: cpu_omp[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    t.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--duals", type=int, default=65536)
+    ap.add_argument("--obs-per-gpu", type=int, default=131072)
+    ap.add_argument("--rv", type=int, default=256)
+    ap.add_argument("--n1", type=int, default=89)
+    ap.add_argument("--cpu-duals", type=int, default=4096)
+    ap.add_argument("--cpu-obs", type=int, default=16384)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

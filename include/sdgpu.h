@@ -143,6 +143,9 @@ int  sdgpu_update_dual_bulk(sdgpu_ctx *ctx, int64_t n, const double *pis, const 
  * an obsFeasible row initialised to all-true (checkBasisFeasibility with rvdOmCnt == 0, randCost.c:208). */
 int  sdgpu_basis_append(sdgpu_ctx *ctx, int ck, int feasFlag, int phiLength, const int32_t *sigmaIdx,
                         const int32_t *omegaIdx);
+/* n single-term bases (phiLength == 0) at once: basis i gets ck[i], feasFlag feas[i] (NULL = all feasible) and
+ * sigmaIdx[i].  Bulk form of sdgpu_basis_append for table loaders.  Returns the index of the first one. */
+int  sdgpu_basis_append_bulk(sdgpu_ctx *ctx, int64_t n, const int32_t *ck, const int32_t *feas, const int32_t *sigmaIdx);
 /* stocUpdate.c:101-131: when retainBasis == 0 return the first stored basis with the same phiLength,
  * obsFeasible[b][obsIdx] set and the same sigmaIdx list (newBasisFlag = 0), else append. */
 int  sdgpu_basis_find_or_append(sdgpu_ctx *ctx, int retainBasis, int obsIdx, int ck, int feasFlag,

@@ -167,6 +167,36 @@ int sdref_update_dual(void *vc, const double *pi, double mubBar, int currentIter
 	return 0;
 }
 
+/* Bulk loader for the timing harness (bench.py): every table entry is still produced by the reference's own
+ * calcLambda / calcSigma / calcDelta; only the loop over NEW lambda rows of calcDelta case II (rows are
+ * independent, stocUpdate.c:230-254) is spread over OpenMP threads so that building a timing sample does not
+ * take longer than timing it.  Observations are appended without the calcOmega scan. */
+int sdref_bulk_load(void *vc, int nObs, const double *obsVals, const int32_t *weights, int nDuals, const double *pis,
+		const double *mubBar, const int32_t *iters, double tol, int32_t *lambdaIdx, int32_t *sigmaIdx) {
+	refCtx *c = (refCtx *) vc;
+	int i, nNew = 0, *newRows = arr_alloc(nDuals + 1, int);
+	for (i = 0; i < nObs; i++) {
+		if (c->omega->cnt >= (int) c->caps.maxOmega) return SDGPU_ERR;
+		c->omega->vals[c->omega->cnt] = duplicVector((dVector) (obsVals + (size_t) i * (c->num.numRV + 1)), c->num.numRV + 1);
+		c->omega->weights[c->omega->cnt++] = weights ? weights[i] : 1;
+	}
+	for (i = 0; i < nDuals; i++) {
+		const double *pi = pis + (size_t) i * (c->num.rows + 1);
+		bool nl = false, ns = false;
+		int li = calcLambda(&c->num, &c->coord, (dVector) pi, c->lambda, &nl, tol);
+		int si = calcSigma(&c->num, &c->coord, &c->bBar, &c->Cbar, (dVector) pi, mubBar ? mubBar[i] : 0.0, li, nl,
+				iters ? iters[i] : i + 1, c->sigma, &ns, tol);
+		if (nl) newRows[nNew++] = li;
+		if (lambdaIdx) lambdaIdx[i] = li;
+		if (sigmaIdx) sigmaIdx[i] = si;
+	}
+#pragma omp parallel for schedule(dynamic, 4)
+	for (i = 0; i < nNew; i++)
+		calcDelta(&c->num, &c->coord, c->lambda, c->delta, (int) c->caps.maxOmega, c->omega, false, newRows[i]);
+	mem_free(newRows);
+	return 0;
+}
+
 static oneBasis *makeBasis(int ck, int feasFlag, int phiLength, const int32_t *sigmaIdx, const int32_t *omegaIdx) {
 	oneBasis *B = (oneBasis *) calloc(1, sizeof(oneBasis));
 	int i;

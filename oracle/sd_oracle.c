@@ -298,8 +298,10 @@ int sdo_calc_delta(oracleCtx *c, int newOmegaFlag, int elemIdx) {
 int sdo_calc_delta_block(oracleCtx *c, int64_t l0, int64_t l1, int64_t o0, int64_t o1) {
 	int Q = c->num.rvCOmCnt;
 	if (l0 < 0 || l1 > c->lambdaCnt || o0 < 0 || o1 > c->omegaCnt || l0 > l1 || o0 > o1) return fail("calc_delta_block: block out of range");
-	double *scratch = (double *) calloc((size_t) c->num.prevCols + 1, sizeof(double));
+	/* rows are independent (stocUpdate.c:230-254): spread them over threads, arithmetic per cell unchanged */
+#pragma omp parallel for schedule(dynamic, 4)
 	for (int64_t l = l0; l < l1; l++) {
+		double *scratch = (double *) calloc((size_t) c->num.prevCols + 1, sizeof(double));
 		if (!c->deltaPib[l]) {
 			c->deltaPib[l] = (double *) calloc((size_t) c->caps.maxOmega, sizeof(double));
 			c->deltaPiC[l] = Q ? (double *) calloc((size_t) c->caps.maxOmega * (Q + 1), sizeof(double)) : NULL;
@@ -308,8 +310,8 @@ int sdo_calc_delta_block(oracleCtx *c, int64_t l0, int64_t l1, int64_t o0, int64
 		for (int64_t o = o0; o < o1; o++)
 			deltaCell(c, full, o, &c->deltaPib[l][o], Q ? c->deltaPiC[l] + (size_t) o * (Q + 1) : NULL, scratch);
 		free(full);
+		free(scratch);
 	}
-	free(scratch);
 	return 0;
 }
 
@@ -372,6 +374,15 @@ int sdo_basis_append(oracleCtx *c, int ck, int feasFlag, int phiLength, const in
 	else
 		c->obsFeasible[b] = NULL;                              /* :129 */
 	return (int) c->basisCnt++;
+}
+
+int sdo_basis_append_bulk(oracleCtx *c, int64_t n, const int32_t *ck, const int32_t *feas, const int32_t *sigmaIdx) {
+	int first = (int) c->basisCnt;
+	for (int64_t i = 0; i < n; i++) {
+		int r = sdo_basis_append(c, ck[i], feas ? feas[i] : 1, 0, sigmaIdx + i, NULL);
+		if (r < 0) return r;
+	}
+	return first;
 }
 
 int sdo_basis_find_or_append(oracleCtx *c, int retainBasis, int obsIdx, int ck, int feasFlag, int phiLength,

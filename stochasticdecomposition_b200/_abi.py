@@ -190,9 +190,11 @@ class Api:
             "calc_delta": (i, [vp, i, i]),
             "calc_delta_block": (i, [vp, i64, i64, i64, i64]),
             "get_delta_block": (i, [vp, i64, i64, i64, i64, i, c_f64p]),
+            "bulk_load": (i, [vp, i, c_f64p, c_i32p, i, c_f64p, c_f64p, c_i32p, d, c_i32p, c_i32p]),
             "update_dual": (i, [vp, c_f64p, d, i, d, c_intp, c_intp, c_intp, c_intp]),
             "update_dual_bulk": (i, [vp, i64, c_f64p, c_f64p, c_i32p, d, c_i32p, c_i32p]),
             "basis_append": (i, [vp, i, i, i, c_i32p, c_i32p]),
+            "basis_append_bulk": (i, [vp, i64, c_i32p, c_i32p, c_i32p]),
             "basis_find_or_append": (i, [vp, i, i, i, i, i, c_i32p, c_i32p, c_intp]),
             "basis_set_obs_feasible": (i, [vp, i, i, i]),
             "basis_set_obs_feasible_row": (i, [vp, i, c_u8p]), "basis_set_obs_feasible_col": (i, [vp, i, c_u8p]),
@@ -338,6 +340,11 @@ class Tables:
         phi = len(s) - 1
         om = None if omegaIdx is None else _i32(list(omegaIdx))
         return self._check(self._call("basis_append", ck, int(feasFlag), phi, _pi32(s), _pi32(om)), "basis_append")
+
+    def basis_append_bulk(self, ck, sigmaIdx, feas=None):
+        c, s = _i32(ck), _i32(sigmaIdx)
+        f = None if feas is None else _i32(feas)
+        return self._check(self._call("basis_append_bulk", len(c), _pi32(c), _pi32(f), _pi32(s)), "basis_append_bulk")
 
     def basis_find_or_append(self, retainBasis, obsIdx, ck, feasFlag=True, sigmaIdx=(0,), omegaIdx=None):
         s = _i32(list(sigmaIdx))

@@ -833,6 +833,40 @@ extern "C" int sdgpu_basis_append(sdgpu_ctx *c, int ck, int feasFlag, int phiLen
 	return b;
 }
 
+extern "C" int sdgpu_basis_append_bulk(sdgpu_ctx *c, int64_t n, const int32_t *ck, const int32_t *feas, const int32_t *sigmaIdx) {
+	if (!c || (n > 0 && (!ck || !sigmaIdx))) return sdgpu_fail("null argument");
+	if (n <= 0) return (int) c->basisCnt;
+	if (c->basisCnt + n > c->caps.maxBasis) return sdgpu_fail("basis capacity %lld exceeded", (long long) c->caps.maxBasis);
+	for (int64_t i = 0; i < n; i++)
+		if (sigmaIdx[i] < 0 || sigmaIdx[i] >= c->sigmaCnt) return sdgpu_fail("basis_append_bulk: sigma index %d out of range", sigmaIdx[i]);
+	SD_CUDA(cudaSetDevice(c->device));
+	const int b0 = (int) c->basisCnt;
+	std::vector<int32_t> zeros((size_t) n, 0), ones((size_t) n, 1), starts((size_t) n + 1);
+	for (int64_t i = 0; i <= n; i++) starts[i] = (int32_t) (c->termCnt + i);
+	SD_CUDA(cudaMemcpyAsync(c->d_bCk + b0, ck, (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_bFeas + b0, feas ? feas : ones.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_bPhiLen + b0, zeros.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_bTermStart + b0, starts.data(), ((size_t) n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_tSigma + c->termCnt, sigmaIdx, (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_tOmega + c->termCnt, zeros.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
+	k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, 0, 0, 0, (int) n);
+	sd_count_launch(c);
+	for (int64_t i = 0; i < n; i++) {
+		SdHostBasis hb;
+		hb.ck = ck[i]; hb.feas = feas ? (feas[i] != 0) : 1; hb.phiLen = 0; hb.weight = 1;
+		hb.sigmaIdx.assign(1, sigmaIdx[i]); hb.omegaIdx.assign(1, 0);
+		if (!hb.feas) c->anyInfeasibleBasis = true;
+		if (c->rvd > 0) {
+			c->hostMask.emplace_back(hb.feas ? std::vector<uint8_t>((size_t) c->NP, 1) : std::vector<uint8_t>());
+			if (hb.feas) { k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, b0 + i, c->NP, nullptr, 0, 1); sd_count_launch(c); }
+		}
+		c->basis.push_back(std::move(hb));
+	}
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	c->termCnt += n; c->basisCnt += n;
+	return b0;
+}
+
 extern "C" int sdgpu_basis_find_or_append(sdgpu_ctx *c, int retainBasis, int obsIdx, int ck, int feasFlag, int phiLength,
 		const int32_t *sigmaIdx, const int32_t *omegaIdx, int *newBasisFlag) {
 	if (!c || !sigmaIdx) return sdgpu_fail("null argument");
