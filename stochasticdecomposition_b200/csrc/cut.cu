@@ -54,36 +54,40 @@ __device__ __forceinline__ double sd_block_sum(double v, double *s_red) {
 	return t;
 }
 
-// ======================================================================================================
-// K5: piCbarX, and the per-basis descriptors of the sweep
-// ======================================================================================================
-__global__ void k_picbarx(const double *__restrict__ piCk, int64_t SP, int n1c, const int32_t *__restrict__ CCols,
-		const double *__restrict__ x, int n1, int sigmaCnt, double *__restrict__ out) {
-	extern __shared__ double s_x[];          // x gathered at CCols, in k order
-	for (int k = threadIdx.x; k < n1c; k += blockDim.x) s_x[k] = x[CCols[k]];
-	__syncthreads();
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= sigmaCnt) return;
-	double acc = 0.0;                        // vXv: left to right from 0.0, product and sum rounded separately
-	for (int k = 0; k < n1c; k++) acc = __dadd_rn(acc, __dmul_rn(piCk[(size_t) k * SP + s], s_x[k]));
-	out[s] = acc;
-}
+// Fused prologue of a cut: x arrives as a kernel parameter (no H2D copy), thread i computes piCbarX of sigma i (only
+// when the general sweep needs the whole vector) and the descriptor of basis i, whose piCbarX is recomputed from its
+// own sigma row with the same left-to-right sum, hence the same bits.
+struct SdXParam { double v[256]; };
 
-// window: 0 = not eligible, 1 = "old" (or the only window when pi_eval is off), 2 = "new"   stocUpdate.c:147-163
-__global__ void k_basis_desc(const int32_t *__restrict__ bCk, const int32_t *__restrict__ bFeas, const int32_t *__restrict__ bTermStart,
+__global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, double *__restrict__ xDevOut, int n1,
+		const double *__restrict__ piCk, int64_t SP, int n1c, const int32_t *__restrict__ CCols, int sigmaCnt, double *__restrict__ piCbarXAll,
+		const int32_t *__restrict__ bCk, const int32_t *__restrict__ bFeas, const int32_t *__restrict__ bTermStart,
 		const int32_t *__restrict__ tSigma, const double *__restrict__ sigmaPib, const int32_t *__restrict__ sigmaLam,
-		const double *__restrict__ piCbarX, int basisCnt, int split, int cutoff,
+		int basisCnt, int split, int cutoff,
 		double *__restrict__ descA, double *__restrict__ descC, int32_t *__restrict__ descRow, int32_t *__restrict__ descWin) {
-	int b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= basisCnt) return;
-	int s = tSigma[bTermStart[b]];
-	int ck = bCk[b], win = 0;
-	if (bFeas[b]) {
-		// "old": basisLow = -INT_MAX < ck <= basisUp = cutoff; "new": cutoff < ck <= INT_MAX (only asked for when split)
-		if (ck <= cutoff) win = (ck > -INT_MAX) ? 1 : 0;
-		else win = split ? 2 : 0;
+	extern __shared__ double s_x[];
+	for (int k = threadIdx.x; k < n1c; k += blockDim.x) s_x[k] = xDevIn ? xDevIn[CCols[k]] : xp.v[CCols[k]];
+	if (blockIdx.x == 0 && !xDevIn)
+		for (int i = threadIdx.x; i <= n1; i += blockDim.x) xDevOut[i] = xp.v[i];
+	__syncthreads();
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (piCbarXAll && i < sigmaCnt) {
+		double acc = 0.0;
+		for (int k = 0; k < n1c; k++) acc = __dadd_rn(acc, __dmul_rn(piCk[(size_t) k * SP + i], s_x[k]));
+		piCbarXAll[i] = acc;
 	}
-	descA[b] = sigmaPib[s]; descC[b] = piCbarX[s]; descRow[b] = sigmaLam[s]; descWin[b] = win;
+	if (i < basisCnt) {
+		const int s = tSigma[bTermStart[i]];
+		double acc = 0.0;
+		for (int k = 0; k < n1c; k++) acc = __dadd_rn(acc, __dmul_rn(piCk[(size_t) k * SP + s], s_x[k]));
+		const int ck = bCk[i];
+		int win = 0;
+		if (bFeas[i]) {
+			if (ck <= cutoff) win = (ck > -INT_MAX) ? 1 : 0;
+			else win = split ? 2 : 0;
+		}
+		descA[i] = sigmaPib[s]; descC[i] = acc; descRow[i] = sigmaLam[s]; descWin[i] = win;
+	}
 }
 
 // ======================================================================================================
@@ -242,6 +246,8 @@ struct MergeArgs {
 	const int32_t *bTermStart, *tSigma, *tOmega;
 	int randCost;                 // num->rvdOmCnt > 0: the cuts.c:142-159 branch
 	int32_t *iStar; double *tilePart; int P;
+	// epilogue run by the last block: tile partials -> un-normalised cut [-> normalised cut in mapped host memory]
+	int n1; const int32_t *CCols, *qCols; double *partial; int fuseNormalise, numSamples; double *hostRes; SdDevState *st;
 };
 
 #define MG_THREADS SD_TILE_W
@@ -354,35 +360,39 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 			out[4 + tid] = acc;
 		}
 	}
-}
 
-// sum the tile partials in tile order and scatter into the un-normalised cut vector
-// partial = [alpha, beta[1..n1], cummOld, cummAll, missing]
-__global__ void k_cut_finalize(const double *__restrict__ tilePart, int nTiles, int P, int n1, int n1c, int Q,
-		const int32_t *__restrict__ CCols, const int32_t *__restrict__ qCols, double *__restrict__ partial) {
-	extern __shared__ double s_tot[];
-	for (int p = threadIdx.x; p < P; p += blockDim.x) {
+	// ---- epilogue: the last tile to finish sums the tile partials in tile order (cuts.c:155-167) and, on a single GPU,
+	// applies cuts.c:184-188 and hands the cut to the host through mapped pinned memory
+	if (!sd_is_last_block(&a.st->cutTicket)) return;
+	double *s_tot = s_dyn;                                   // [P], then the cut vector [n1+4]
+	double *s_cut = s_dyn + a.P;
+	const int nT = gridDim.x;
+	for (int p = tid; p < a.P; p += blockDim.x) {
 		double acc = 0.0;
-		for (int t = 0; t < nTiles; t++) acc = __dadd_rn(acc, tilePart[(size_t) t * P + p]);
+		for (int t = 0; t < nT; t++) acc = __dadd_rn(acc, __ldcg(a.tilePart + (size_t) t * a.P + p));
 		s_tot[p] = acc;
 	}
-	for (int c = threadIdx.x; c <= n1 + 3; c += blockDim.x) partial[c] = 0.0;
+	for (int c = tid; c <= a.n1 + 3; c += blockDim.x) s_cut[c] = 0.0;
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		partial[0] = s_tot[0];
-		for (int k = 0; k < n1c; k++) partial[CCols[k]] = __dadd_rn(partial[CCols[k]], s_tot[4 + k]);          // cuts.c:155,165
-		for (int q = 0; q < Q; q++) partial[qCols[q]] = __dadd_rn(partial[qCols[q]], s_tot[4 + n1c + q]);      // cuts.c:157,167
-		partial[n1 + 1] = s_tot[1]; partial[n1 + 2] = s_tot[2]; partial[n1 + 3] = s_tot[3];
+	if (tid == 0) {
+		s_cut[0] = s_tot[0];
+		for (int k = 0; k < a.n1c; k++) s_cut[a.CCols[k]] = __dadd_rn(s_cut[a.CCols[k]], s_tot[4 + k]);
+		for (int q = 0; q < a.Q; q++) s_cut[a.qCols[q]] = __dadd_rn(s_cut[a.qCols[q]], s_tot[4 + a.n1c + q]);
+		s_cut[a.n1 + 1] = s_tot[1]; s_cut[a.n1 + 2] = s_tot[2]; s_cut[a.n1 + 3] = s_tot[3];
 	}
+	__syncthreads();
+	for (int c = tid; c <= a.n1 + 3; c += blockDim.x) {
+		a.partial[c] = s_cut[c];
+		if (a.fuseNormalise) a.hostRes[c] = (c <= a.n1) ? s_cut[c] / a.numSamples : s_cut[c];
+	}
+	if (a.fuseNormalise) __threadfence_system();
 }
 
 // cuts.c:184-188
 __global__ void k_cut_normalise(const double *__restrict__ partial, int n1, int numSamples, double *__restrict__ out) {
 	int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c > n1 + 3) return;
-	if (c == 0) out[0] = partial[0] / numSamples;
-	else if (c <= n1) out[c] = partial[c] / numSamples;
-	else out[c] = partial[c];
+	if (c <= n1 + 3) out[c] = (c <= n1) ? partial[c] / numSamples : partial[c];
+	__threadfence_system();
 }
 
 // ======================================================================================================
@@ -519,29 +529,28 @@ __global__ void __launch_bounds__(512) k_reform(ReformArgs a) {
 // ======================================================================================================
 static inline int sd_blocks(int64_t n, int t) { return (int) std::max<int64_t>(1, (n + t - 1) / t); }
 
-static int sd_stage_x(sdgpu_ctx *c, const double *X) {
-	memcpy(c->h_pinD, X, ((size_t) c->n1 + 1) * sizeof(double));
-	SD_CUDA(cudaMemcpyAsync(c->d_x, c->h_pinD, ((size_t) c->n1 + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+// piCbarX + basis descriptors (+ x onto the device) in one launch.  x travels as a kernel parameter when it fits
+// (n1 < 256, every reference problem), otherwise through one H2D copy.
+static int sd_launch_prep(sdgpu_ctx *c, const double *X, int cutoff, int split, bool wantAllPiCbarX) {
+	SdXParam xp;
+	const double *xDevIn = nullptr;
+	if (c->n1 + 1 <= 256) memcpy(xp.v, X, ((size_t) c->n1 + 1) * sizeof(double));
+	else {
+		memcpy(c->h_pinD, X, ((size_t) c->n1 + 1) * sizeof(double));
+		SD_CUDA(cudaMemcpyAsync(c->d_x, c->h_pinD, ((size_t) c->n1 + 1) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		xDevIn = c->d_x;
+	}
+	const int64_t n = std::max<int64_t>(std::max<int64_t>(c->basisCnt, wantAllPiCbarX ? c->sigmaCnt : 0), 1);
+	k_cut_prep<<<sd_blocks(n, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(xp, xDevIn, c->d_x, c->n1, c->d_sigmaPiCk, c->SP, c->n1c,
+			c->d_CCols, (int) c->sigmaCnt, wantAllPiCbarX ? c->d_piCbarX : nullptr, c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma,
+			c->d_sigmaPib, c->d_sigmaLam, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin);
+	sd_count_launch(c);
 	return 0;
 }
 
 static int sd_window_cutoff(int numSamples, int pi_eval) {
 	if (pi_eval) numSamples -= (int) (0.1 * numSamples + 1);          // stocUpdate.c:147-148
 	return numSamples;
-}
-
-static int sd_launch_desc(sdgpu_ctx *c, int cutoff, int split) {
-	if (c->sigmaCnt > 0) {
-		k_picbarx<<<sd_blocks(c->sigmaCnt, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(c->d_sigmaPiCk, c->SP, c->n1c, c->d_CCols, c->d_x,
-				c->n1, (int) c->sigmaCnt, c->d_piCbarX);
-		sd_count_launch(c);
-	}
-	if (c->basisCnt > 0) {
-		k_basis_desc<<<sd_blocks(c->basisCnt, 128), 128, 0, c->stream>>>(c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaLam,
-				c->d_piCbarX, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin);
-		sd_count_launch(c);
-	}
-	return 0;
 }
 
 static SweepGenArgs sd_gen_args(sdgpu_ctx *c, int chunkSize, int nChunks) {
@@ -572,24 +581,25 @@ static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks
 	*nChunks = (int) ((c->basisCnt + cs - 1) / cs);
 }
 
-extern "C" int sdgpu_sd_cut_partial(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb) {
+static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, bool fuseNormalise) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
+	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
 	if (c->Q > 64) return sdgpu_fail("sd_cut: rvCOmCnt %d exceeds the 64 random T elements this build stages in shared memory", c->Q);
 	SD_CUDA(cudaSetDevice(c->device));
 	int64_t launches0 = c->stats.total_launches;
 	SD_CUDA(cudaEventRecord(c->evA, c->stream));
-	if (sd_stage_x(c, Xvect)) return SDGPU_ERR;
 	const int N = (int) c->omegaCnt;
 	const int tiles = (int) ((N + SD_TILE_W - 1) / SD_TILE_W);
 	const int P = 4 + c->n1c + c->Q;
 	c->lastOmegaCnt = N;
+	c->cutFused = false;
 	if (N > 0 && c->basisCnt > 0) {
-		sd_launch_desc(c, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0);
+		const bool general = c->maxPhiLen > 0;
+		if (sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, general)) return SDGPU_ERR;
 		int chunkSize = 1, nChunks = 1;
 		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);
 		dim3 grid((unsigned) tiles, (unsigned) nChunks);
 		SD_CUDA(cudaEventRecord(c->evC, c->stream));
-		const bool general = c->maxPhiLen > 0;
 		if (general) {
 			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
 		}
@@ -621,29 +631,33 @@ extern "C" int sdgpu_sd_cut_partial(sdgpu_ctx *c, const double *Xvect, int numSa
 		m.bTermStart = c->d_bTermStart; m.tSigma = c->d_tSigma; m.tOmega = c->d_tOmega;
 		m.randCost = c->rvd > 0;
 		m.iStar = c->d_iStar; m.tilePart = c->d_tilePart; m.P = P;
+		m.n1 = c->n1; m.CCols = c->d_CCols; m.qCols = c->rvd > 0 ? c->d_rvCOmCols : c->d_rvCols;       // cuts.c:157 vs :167
+		m.partial = c->d_cutPartial; m.fuseNormalise = c->ncclComm == nullptr && fuseNormalise; m.numSamples = numSamples;
+		m.hostRes = c->d_cutRes; m.st = c->d_state;
+		c->cutFused = m.fuseNormalise != 0;
 		const int kp = ((c->n1c + 31) / 32) * 32;
 		const int groups = c->n1c > 0 ? std::max(1, MG_THREADS / kp) : 1;
-		k_cut_merge<<<tiles, MG_THREADS, (size_t) std::max(1, groups * c->n1c) * 8, c->stream>>>(m);
+		const size_t dyn = (size_t) std::max(std::max(1, groups * c->n1c), P + c->n1 + 4) * 8;
+		k_cut_merge<<<tiles, MG_THREADS, dyn, c->stream>>>(m);
 		sd_count_launch(c);
 	}
 	else {
+		// no observation or no basis at all: nothing to sweep; with observations every one is missing its maximiser (cuts.c:136-139)
 		SD_CUDA(cudaEventRecord(c->evC, c->stream));
 		SD_CUDA(cudaEventRecord(c->evD, c->stream));
 		c->stats.last_sweep_bytes = 0;
-	}
-	const int usedTiles = (N > 0 && c->basisCnt > 0) ? tiles : 0;
-	k_cut_finalize<<<1, 256, (size_t) P * 8, c->stream>>>(c->d_tilePart, usedTiles, P, c->n1, c->n1c, c->Q, c->d_CCols,
-			c->rvd > 0 ? c->d_rvCOmCols : c->d_rvCols, c->d_cutPartial);
-	sd_count_launch(c);
-	if (N > 0 && c->basisCnt == 0) {
-		// no basis at all: every observation is missing its maximiser (cuts.c:136-139)
-		double miss = (double) N;
-		SD_CUDA(cudaMemcpyAsync(c->d_cutPartial + c->n1 + 3, &miss, 8, cudaMemcpyHostToDevice, c->stream));
-		SD_CUDA(cudaMemsetAsync(c->d_iStar, 0xff, (size_t) N * 4, c->stream));
+		std::vector<double> zero((size_t) c->n1 + 4, 0.0);
+		zero[c->n1 + 3] = (double) N;
+		SD_CUDA(cudaMemcpyAsync(c->d_cutPartial, zero.data(), zero.size() * 8, cudaMemcpyHostToDevice, c->stream));
+		if (N > 0) SD_CUDA(cudaMemsetAsync(c->d_iStar, 0xff, (size_t) N * 4, c->stream));
 		SD_CUDA(cudaStreamSynchronize(c->stream));
 	}
 	c->stats.last_cut_launches = c->stats.total_launches - launches0;
 	return 0;
+}
+
+extern "C" int sdgpu_sd_cut_partial(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb) {
+	return sd_cut_partial_impl(c, Xvect, numSamples, pi_eval_flag, lb, false);
 }
 
 extern "C" int sdgpu_sd_cut_partial_buffer(sdgpu_ctx *c, void **devPtr, int *len) {
@@ -657,10 +671,11 @@ extern "C" int sdgpu_sd_cut_finish(sdgpu_ctx *c, int numSamples, sdgpu_cut *cut)
 	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
 	SD_CUDA(cudaSetDevice(c->device));
 	int64_t launches0 = c->stats.total_launches;
-	k_cut_normalise<<<sd_blocks(c->n1 + 4, 128), 128, 0, c->stream>>>(c->d_cutPartial, c->n1, numSamples, c->d_cutOut);
-	sd_count_launch(c);
-	double *h = c->h_pinD;
-	SD_CUDA(cudaMemcpyAsync(h, c->d_cutOut, ((size_t) c->n1 + 4) * 8, cudaMemcpyDeviceToHost, c->stream));
+	if (!c->cutFused) {          // sharded / split form: normalise after the caller's (or NCCL's) all-reduce, straight into mapped host memory
+		k_cut_normalise<<<sd_blocks(c->n1 + 4, 128), 128, 0, c->stream>>>(c->d_cutPartial, c->n1, numSamples, c->d_cutRes);
+		sd_count_launch(c);
+	}
+	double *h = c->h_cutRes;
 	if (cut->iStar && c->lastOmegaCnt > 0)
 		SD_CUDA(cudaMemcpyAsync(cut->iStar, c->d_iStar, (size_t) c->lastOmegaCnt * 4, cudaMemcpyDeviceToHost, c->stream));
 	SD_CUDA(cudaEventRecord(c->evB, c->stream));
@@ -682,7 +697,8 @@ extern "C" int sdgpu_sd_cut_finish(sdgpu_ctx *c, int numSamples, sdgpu_cut *cut)
 }
 
 extern "C" int sdgpu_sd_cut(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, sdgpu_cut *cut) {
-	int rc = sdgpu_sd_cut_partial(c, Xvect, numSamples, pi_eval_flag, lb);
+	if (!cut || !cut->beta) return sdgpu_fail("null argument");
+	int rc = sd_cut_partial_impl(c, Xvect, numSamples, pi_eval_flag, lb, true);
 	if (rc != 0) return rc;
 	if (c->ncclComm) {
 		rc = sd_nccl_allreduce(c, c->d_cutPartial, c->n1 + 4);
@@ -709,9 +725,8 @@ extern "C" int sdgpu_compute_istar(sdgpu_ctx *c, const double *Xvect, int obs, i
 	if (obs < 0 || obs >= c->omegaCnt) return sdgpu_fail("compute_istar: observation %d out of range", obs);
 	if (c->Q > 64) return sdgpu_fail("compute_istar: rvCOmCnt too large");
 	SD_CUDA(cudaSetDevice(c->device));
-	if (sd_stage_x(c, Xvect)) return SDGPU_ERR;
 	// always split at the (possibly shrunk) sample count: isNew asks for the bases above it, !isNew for those at or below
-	sd_launch_desc(c, sd_window_cutoff(numSamples, pi_eval != 0), 1);
+	if (sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval != 0), 1, true)) return SDGPU_ERR;
 	double *d_v = c->d_cutOut; int32_t *d_i = (int32_t *) (c->d_cutOut + 1);
 	if (c->basisCnt > 0) {
 		k_istar_one<<<1, 256, 0, c->stream>>>(sd_gen_args(c, 1, 1), obs, isNew != 0, d_v, d_i);

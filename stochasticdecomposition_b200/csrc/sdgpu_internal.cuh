@@ -42,6 +42,8 @@ struct SdDevState {
 	int foundSigma, sigmaIdx, newSigma;        // calcSigma result
 	int foundOmega, omegaIdx, newOmega;        // calcOmega result
 	int overflow;                              // a capacity was exceeded
+	unsigned int ticket;                       // last-block election of the fused find+commit kernels
+	unsigned int cutTicket;                    // ... of the cut merge kernel
 	double pibBar;                             // pi x bBar + mubBar of the vector being processed
 };
 
@@ -93,7 +95,11 @@ struct sdgpu_ctx {
 	double  *d_candC = nullptr;
 	double  *h_pinD = nullptr;       // pinned doubles (inputs and results)
 	int32_t *h_pinI = nullptr;       // pinned ints
-	SdDevState *h_state = nullptr;   // pinned mirror
+	SdDevState *h_state = nullptr;   // pinned + mapped mirror: commit kernels publish the state straight into it
+	SdDevState *d_hstate = nullptr;  // device alias of h_state
+	double  *d_pinD = nullptr;       // device alias of h_pinD (zero-copy reads of small host vectors)
+	double  *h_cutRes = nullptr;     // pinned + mapped [n1+4]: the finished cut, written by the last merge block
+	double  *d_cutRes = nullptr;     // device alias of h_cutRes
 	size_t   pinDcap = 0, pinIcap = 0;
 
 	// cut formation scratch
@@ -110,6 +116,7 @@ struct sdgpu_ctx {
 	int      maxChunks = 1;
 	int      sweepVariant = 0;
 	int      lastOmegaCnt = 0;
+	bool     cutFused = false;       // the last merge block already normalised the cut into h_cutRes
 
 	// host mirrors (bookkeeping only; no table arithmetic happens on the host)
 	int64_t omegaCnt = 0, lambdaCnt = 0, sigmaCnt = 0, basisCnt = 0, termCnt = 0;
@@ -136,6 +143,22 @@ __host__ __device__ static inline size_t sd_mask_off(int64_t Bcap, int64_t b, in
 	int64_t t = o / SD_TILE_W, w = o % SD_TILE_W;
 	return ((size_t) t * Bcap + b) * SD_TILE_W + w;
 }
+
+#ifdef __CUDACC__
+// The block that draws the last ticket of a launch (1-D grid) gets `true`; the ticket is reset for the next launch.
+__device__ __forceinline__ bool sd_is_last_block(unsigned int *ticket) {
+	__shared__ bool s_last;
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned int t = atomicAdd(ticket, 1u);
+		s_last = (t == gridDim.x - 1);
+		if (s_last) *ticket = 0;
+	}
+	__syncthreads();
+	return s_last;
+}
+#endif
 
 int sd_sync_state(sdgpu_ctx *c);                 // D2H of SdDevState + stream sync + mirror update
 int sd_nccl_allreduce(sdgpu_ctx *c, double *buf, int n);

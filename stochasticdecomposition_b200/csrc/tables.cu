@@ -33,60 +33,139 @@ __device__ __forceinline__ double sd_abs(double x) { return x > 0.0 ? x : -x; }
 // kernels
 // ======================================================================================================
 
-// Stage the candidate of a find-or-append: cand[i] = vec[idx[i]] (reduceVector, stocUpdate.c:269) or, with
-// idx == nullptr, cand[i] = vec[1 + i] (an observation, stocUpdate.c:331).  Also arms the result slots.
-__global__ void k_stage_candidate(const double *__restrict__ vec, const int32_t *__restrict__ idx, int n,
-		double *__restrict__ cand, SdDevState *st, int which) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) cand[i] = idx ? vec[idx[i]] : vec[1 + i];
-	if (i == 0) {
-		if (which == 0) st->foundLambda = INT_MAX;
-		else st->foundOmega = INT_MAX;
+// ---- fused find-or-append kernels (one launch per table, no host round trip) ---------------------------------
+// Every block scans its rows; the block that draws the last ticket commits the result and publishes the device
+// state into mapped pinned host memory, so the host only has to wait for the stream.
+__device__ __forceinline__ void sd_publish(const SdDevState *st, SdDevState *host) {
+	*host = *st;
+	__threadfence_system();
+}
+
+// calcLambda (stocUpdate.c:264-284) in one launch, followed in the same launch by the staging part of calcSigma
+// (stocUpdate.c:293-296) so that the sigma scan can start right after.  `pi` may be a mapped host pointer.
+__global__ void k_lambda_fused(const double *__restrict__ pi, int rows, const int32_t *__restrict__ rvRows, int R,
+		double *__restrict__ lambda, int64_t LP, int64_t cap, double tol,
+		const int32_t *__restrict__ bCol, const double *__restrict__ bVal, int bCnt, double mubBar,
+		const int32_t *__restrict__ cbStart, const int32_t *__restrict__ cbRow, const double *__restrict__ cbVal, int n1c,
+		double *__restrict__ vecDev, double *__restrict__ candC, SdDevState *st, SdDevState *hst) {
+	extern __shared__ double s_cand[];
+	for (int i = threadIdx.x; i < R; i += blockDim.x) s_cand[i] = pi[rvRows[i]];            // reduceVector :269
+	__syncthreads();
+	const int cnt = st->lambdaCnt;
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < cnt) {                                                                           // :272-277
+		bool same = true;
+		for (int i = 0; i < R; i++)
+			if (sd_abs(s_cand[i] - lambda[(size_t) i * LP + r]) > tol) { same = false; break; }
+		if (same) atomicMin(&st->foundLambda, r);
+	}
+	if (!sd_is_last_block(&st->ticket)) return;
+	const int found = *(volatile int *) &st->foundLambda;
+	int idx = found, isNew = 0;
+	if (found == INT_MAX) {
+		if (cnt >= cap) { idx = -1; if (threadIdx.x == 0) st->overflow = 1; }
+		else {
+			for (int i = threadIdx.x; i < R; i += blockDim.x) lambda[(size_t) i * LP + cnt] = s_cand[i];   // :280
+			idx = cnt; isNew = 1;
+		}
+	}
+	for (int i = threadIdx.x; i <= rows; i += blockDim.x) vecDev[i] = pi[i];                // keep pi on the device for calcSigma
+	__syncthreads();
+	for (int k = threadIdx.x; k < n1c; k += blockDim.x) {                                    // vxMSparse + reduceVector :295-296
+		double t = 0.0;
+		for (int e = cbStart[k]; e < cbStart[k + 1]; e++) t += vecDev[cbRow[e]] * cbVal[e];
+		candC[k] = t;
+	}
+	if (threadIdx.x == 0) {
+		double sum = 0.0;                                                                    // vXvSparse :293
+		for (int e = 0; e < bCnt; e++) sum += bVal[e] * vecDev[bCol[e]];
+		st->pibBar = sum + mubBar;
+		st->lambdaIdx = idx; st->newLambda = isNew; st->foundLambda = INT_MAX;
+		if (isNew) st->lambdaCnt = cnt + 1;
+		sd_publish(st, hst);
 	}
 }
 
-// calcLambda scan stocUpdate.c:272-277 / calcOmega scan :330-335: one thread per stored row, first mismatch ends
-// the row (most rows differ in their first entry, so the scan mostly touches one column of the table);
-// atomicMin keeps the FIRST matching index, which is what the sequential scan returns.
-__global__ void k_find_row(const double *__restrict__ table, int64_t pitch, int len, const double *__restrict__ cand,
-		double tol, SdDevState *st, int which) {
-	int cnt = which == 0 ? st->lambdaCnt : st->omegaCnt;
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= cnt) return;
-	for (int i = 0; i < len; i++)
-		if (sd_abs(cand[i] - table[(size_t) i * pitch + r]) > tol) return;
-	atomicMin(which == 0 ? &st->foundLambda : &st->foundOmega, r);
+// calcSigma scan + commit (stocUpdate.c:299-318) in one launch
+__global__ void k_sigma_fused(double *__restrict__ pib, double *__restrict__ piCk, double *__restrict__ piCr, int32_t *__restrict__ lam,
+		int32_t *__restrict__ ck, int64_t SP, int n1c, int n1cP, const double *__restrict__ candC, double tol, int iter, int64_t cap,
+		SdDevState *st, SdDevState *hst) {
+	const int cnt = st->sigmaCnt;
+	if (!st->newLambda) {
+		const int s = blockIdx.x * blockDim.x + threadIdx.x;
+		if (s < cnt && sd_abs(st->pibBar - pib[s]) <= tol) {
+			bool same = true;
+			for (int k = 0; k < n1c; k++)
+				if (sd_abs(candC[k] - piCk[(size_t) k * SP + s]) > tol) { same = false; break; }
+			if (same && lam[s] == st->lambdaIdx) atomicMin(&st->foundSigma, s);
+		}
+	}
+	if (!sd_is_last_block(&st->ticket)) return;
+	const int found = *(volatile int *) &st->foundSigma;
+	int idx = found, isNew = 0;
+	if (found == INT_MAX) {
+		if (cnt >= cap || st->lambdaIdx < 0) { idx = -1; if (threadIdx.x == 0) st->overflow = 1; }
+		else {
+			for (int k = threadIdx.x; k < n1c; k += blockDim.x) {
+				piCk[(size_t) k * SP + cnt] = candC[k];
+				piCr[(size_t) cnt * n1cP + k] = candC[k];
+			}
+			idx = cnt; isNew = 1;
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (isNew) { pib[cnt] = st->pibBar; lam[cnt] = st->lambdaIdx; ck[cnt] = iter; st->sigmaCnt = cnt + 1; }
+		st->sigmaIdx = idx; st->newSigma = isNew; st->foundSigma = INT_MAX;
+		sd_publish(st, hst);
+	}
 }
 
-// stocUpdate.c:274-283: report the match or append the candidate as a new lambda row.
-__global__ void k_lambda_commit(double *__restrict__ lambda, int64_t LP, int R, const double *__restrict__ cand,
-		int64_t cap, SdDevState *st) {
-	__shared__ int s_cnt, s_found;
-	if (threadIdx.x == 0) { s_cnt = st->lambdaCnt; s_found = st->foundLambda; }
+// calcOmega (stocUpdate.c:326-348) in one launch.  mode 0: find, then bump or append; 1: find only; 2: append only
+__global__ void k_omega_fused(const double *__restrict__ observ, int numRV, double *__restrict__ omega, int32_t *__restrict__ w, int64_t NP,
+		int64_t cap, double tol, int mode, int weight, SdDevState *st, SdDevState *hst) {
+	extern __shared__ double s_cand[];
+	for (int j = threadIdx.x; j < numRV; j += blockDim.x) s_cand[j] = observ[1 + j];
 	__syncthreads();
-	if (s_found != INT_MAX) {
-		if (threadIdx.x == 0) { st->lambdaIdx = s_found; st->newLambda = 0; }
+	const int cnt = st->omegaCnt;
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (mode != 2 && r < cnt) {                                                              // :330-335
+		bool same = true;
+		for (int j = 0; j < numRV; j++)
+			if (sd_abs(s_cand[j] - omega[(size_t) j * NP + r]) > tol) { same = false; break; }
+		if (same) atomicMin(&st->foundOmega, r);
+	}
+	if (!sd_is_last_block(&st->ticket)) return;
+	const int found = *(volatile int *) &st->foundOmega;
+	if (mode == 1) {
+		if (threadIdx.x == 0) { st->omegaIdx = found == INT_MAX ? -1 : found; st->newOmega = 0; sd_publish(st, hst); st->foundOmega = INT_MAX; }
 		return;
 	}
-	if (s_cnt >= cap) { if (threadIdx.x == 0) { st->overflow = 1; st->lambdaIdx = -1; st->newLambda = 0; } return; }
-	for (int i = threadIdx.x; i < R; i += blockDim.x) lambda[(size_t) i * LP + s_cnt] = cand[i];
-	if (threadIdx.x == 0) { st->lambdaIdx = s_cnt; st->newLambda = 1; st->lambdaCnt = s_cnt + 1; }
+	int idx = found, isNew = 0;
+	if (found == INT_MAX) {
+		if (cnt >= cap) { idx = -1; if (threadIdx.x == 0) st->overflow = 1; }
+		else {
+			for (int j = threadIdx.x; j < numRV; j += blockDim.x) omega[(size_t) j * NP + cnt] = s_cand[j];   // :338
+			idx = cnt; isNew = 1;
+		}
+	}
+	if (threadIdx.x == 0) {
+		if (isNew) { w[cnt] = weight; st->omegaCnt = cnt + 1; }
+		else if (idx >= 0) w[idx] += 1;                                                      // :333
+		st->omegaIdx = idx; st->newOmega = isNew; st->foundOmega = INT_MAX;
+		sd_publish(st, hst);
+	}
 }
 
-// stocUpdate.c:332-340,347: bump the weight of the match or append the observation with weight 1.
-__global__ void k_omega_commit(double *__restrict__ omega, int32_t *__restrict__ w, int64_t NP, int numRV,
-		const double *__restrict__ cand, int64_t cap, SdDevState *st, int mode, int weight) {
-	// mode 0: calcOmega (find result decides); mode 1: append unconditionally with `weight`
-	__shared__ int s_cnt, s_found;
-	if (threadIdx.x == 0) { s_cnt = st->omegaCnt; s_found = mode == 0 ? st->foundOmega : INT_MAX; }
-	__syncthreads();
-	if (s_found != INT_MAX) {
-		if (threadIdx.x == 0) { w[s_found] += 1; st->omegaIdx = s_found; st->newOmega = 0; }
-		return;
-	}
-	if (s_cnt >= cap) { if (threadIdx.x == 0) { st->overflow = 1; st->omegaIdx = -1; st->newOmega = 0; } return; }
-	for (int j = threadIdx.x; j < numRV; j += blockDim.x) omega[(size_t) j * NP + s_cnt] = cand[j];
-	if (threadIdx.x == 0) { w[s_cnt] = weight; st->omegaIdx = s_cnt; st->newOmega = 1; st->omegaCnt = s_cnt + 1; }
+struct SdBasisRec { int b, ck, feas, phiLen, termStart, nT; int sigma[16]; int omega[16]; };
+
+__global__ void k_basis_commit(SdBasisRec r, int32_t *bCk, int32_t *bFeas, int32_t *bPhiLen, int32_t *bTermStart, int32_t *tSigma, int32_t *tOmega,
+		SdDevState *st, SdDevState *hst) {
+	bCk[r.b] = r.ck; bFeas[r.b] = r.feas; bPhiLen[r.b] = r.phiLen;
+	bTermStart[r.b] = r.termStart; bTermStart[r.b + 1] = r.termStart + r.nT;
+	for (int t = 0; t < r.nT; t++) { tSigma[r.termStart + t] = r.sigma[t]; tOmega[r.termStart + t] = r.omega[t]; }
+	st->basisCnt = r.b + 1;
+	sd_publish(st, hst);
 }
 
 // calcSigma stocUpdate.c:293-296: pibBar = (sum_e bBar.val[e] * pi[bBar.col[e]]) + mubBar, and for each kept column
@@ -107,42 +186,6 @@ __global__ void k_sigma_prepare(const double *__restrict__ pi, const int32_t *__
 		st->pibBar = s + mubBar;
 		st->foundSigma = INT_MAX;
 		if (overrideNewLambda >= 0) { st->newLambda = overrideNewLambda; st->lambdaIdx = overrideLambdaIdx; }
-	}
-}
-
-// stocUpdate.c:299-310: scan only when the lambda was already known; match = |pib diff| <= tol, every piC entry
-// within tol, and the same lambda index.  First match wins.
-__global__ void k_sigma_find(const double *__restrict__ pib, const double *__restrict__ piCk, const int32_t *__restrict__ lam,
-		int64_t SP, int n1c, const double *__restrict__ candC, double tol, SdDevState *st) {
-	if (st->newLambda) return;
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= st->sigmaCnt) return;
-	if (!(sd_abs(st->pibBar - pib[s]) <= tol)) return;
-	for (int k = 0; k < n1c; k++)
-		if (sd_abs(candC[k] - piCk[(size_t) k * SP + s]) > tol) return;
-	if (lam[s] != st->lambdaIdx) return;
-	atomicMin(&st->foundSigma, s);
-}
-
-// stocUpdate.c:304-318
-__global__ void k_sigma_commit(double *__restrict__ pib, double *__restrict__ piCk, double *__restrict__ piCr, int32_t *__restrict__ lam,
-		int32_t *__restrict__ ck, int64_t SP, int n1c, int n1cP, const double *__restrict__ candC, int iter, int64_t cap,
-		SdDevState *st) {
-	__shared__ int s_cnt, s_found;
-	if (threadIdx.x == 0) { s_cnt = st->sigmaCnt; s_found = st->foundSigma; }
-	__syncthreads();
-	if (s_found != INT_MAX) {
-		if (threadIdx.x == 0) { st->sigmaIdx = s_found; st->newSigma = 0; }
-		return;
-	}
-	if (s_cnt >= cap || st->lambdaIdx < 0) { if (threadIdx.x == 0) { st->overflow = 1; st->sigmaIdx = -1; st->newSigma = 0; } return; }
-	for (int k = threadIdx.x; k < n1c; k += blockDim.x) {
-		piCk[(size_t) k * SP + s_cnt] = candC[k];
-		piCr[(size_t) s_cnt * n1cP + k] = candC[k];
-	}
-	if (threadIdx.x == 0) {
-		pib[s_cnt] = st->pibBar; lam[s_cnt] = st->lambdaIdx; ck[s_cnt] = iter;
-		st->sigmaIdx = s_cnt; st->newSigma = 1; st->sigmaCnt = s_cnt + 1;
 	}
 }
 
@@ -308,8 +351,9 @@ __global__ void k_dual_bulk(const double *__restrict__ pis, int64_t n, int rows,
 	ck[sbase + i] = iters ? iters[i] : (int32_t) (i + 1);
 }
 
-__global__ void k_bump_counts(SdDevState *st, int dOmega, int dLambda, int dSigma, int dBasis) {
+__global__ void k_bump_counts(SdDevState *st, SdDevState *hst, int dOmega, int dLambda, int dSigma, int dBasis) {
 	st->omegaCnt += dOmega; st->lambdaCnt += dLambda; st->sigmaCnt += dSigma; st->basisCnt += dBasis;
+	sd_publish(st, hst);
 }
 
 __global__ void k_record_pair(const SdDevState *st, int32_t *lamOut, int32_t *sigOut, int64_t i) {
@@ -351,12 +395,12 @@ static int sd_upload(T **p, const std::vector<T> &h) {
 }
 
 int sd_sync_state(sdgpu_ctx *c) {
-	SD_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SdDevState), cudaMemcpyDeviceToHost, c->stream));
-	SD_CUDA(cudaStreamSynchronize(c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));          // the commit kernels already published the state into h_state
 	c->omegaCnt = c->h_state->omegaCnt; c->lambdaCnt = c->h_state->lambdaCnt;
 	c->sigmaCnt = c->h_state->sigmaCnt;
 	if (c->h_state->overflow) {
 		SD_CUDA(cudaMemsetAsync(&c->d_state->overflow, 0, sizeof(int), c->stream));
+		c->h_state->overflow = 0;
 		return sdgpu_fail("table capacity exceeded (omega %lld/%lld, lambda %lld/%lld, sigma %lld/%lld)",
 				(long long) c->omegaCnt, (long long) c->caps.maxOmega, (long long) c->lambdaCnt, (long long) c->caps.maxLambda,
 				(long long) c->sigmaCnt, (long long) c->caps.maxSigma);
@@ -364,9 +408,10 @@ int sd_sync_state(sdgpu_ctx *c) {
 	return 0;
 }
 
-static int sd_stage_vec(sdgpu_ctx *c, const double *h, int n) {       // host vector -> d_vecIn through pinned memory
+// host vector -> mapped pinned staging; kernels read it through the device alias c->d_pinD (zero copy).  Safe to reuse:
+// every caller waits for the stream before returning.
+static int sd_stage_vec(sdgpu_ctx *c, const double *h, int n) {
 	memcpy(c->h_pinD, h, (size_t) n * sizeof(double));
-	SD_CUDA(cudaMemcpyAsync(c->d_vecIn, c->h_pinD, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	return 0;
 }
 
@@ -447,7 +492,8 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	SD_TRY(sd_alloc(&c->d_bCk, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bFeas, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bPhiLen, (size_t) c->BP));
 	SD_TRY(sd_alloc(&c->d_bTermStart, (size_t) c->BP + 1)); SD_TRY(sd_alloc(&c->d_tSigma, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_tOmega, (size_t) c->termCap));
 	SD_TRY(sd_alloc(&c->d_state, 1));
-	cudaMemset(c->d_state, 0, sizeof(SdDevState));
+	{ SdDevState init; memset(&init, 0, sizeof init); init.foundLambda = init.foundSigma = init.foundOmega = INT_MAX;
+	  cudaMemcpy(c->d_state, &init, sizeof init, cudaMemcpyHostToDevice); }
 	cudaMemset(c->d_omegaW, 0, (size_t) c->NP * sizeof(int32_t));
 	cudaMemset(c->d_bTermStart, 0, ((size_t) c->BP + 1) * sizeof(int32_t));
 
@@ -455,11 +501,16 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	size_t vecLen = (size_t) std::max(std::max(c->rows, c->numRV), c->n1) + 2;
 	SD_TRY(sd_alloc(&c->d_vecIn, vecLen)); SD_TRY(sd_alloc(&c->d_cand, (size_t) std::max(c->R, c->numRV) + 1)); SD_TRY(sd_alloc(&c->d_candC, (size_t) c->n1cP));
 	c->pinDcap = vecLen + (size_t) c->n1 + 16; c->pinIcap = 64;
-	if (cudaMallocHost((void **) &c->h_pinD, c->pinDcap * sizeof(double)) != cudaSuccess ||
-	    cudaMallocHost((void **) &c->h_pinI, c->pinIcap * sizeof(int32_t)) != cudaSuccess ||
-	    cudaMallocHost((void **) &c->h_state, sizeof(SdDevState)) != cudaSuccess) {
-		sdgpu_fail("cudaMallocHost failed"); sdgpu_destroy(c); return SDGPU_ERR;
+	if (cudaHostAlloc((void **) &c->h_pinD, c->pinDcap * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostAlloc((void **) &c->h_pinI, c->pinIcap * sizeof(int32_t), cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostAlloc((void **) &c->h_state, sizeof(SdDevState), cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostAlloc((void **) &c->h_cutRes, ((size_t) c->n1 + 8) * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostGetDevicePointer((void **) &c->d_pinD, c->h_pinD, 0) != cudaSuccess ||
+	    cudaHostGetDevicePointer((void **) &c->d_hstate, c->h_state, 0) != cudaSuccess ||
+	    cudaHostGetDevicePointer((void **) &c->d_cutRes, c->h_cutRes, 0) != cudaSuccess) {
+		sdgpu_fail("pinned host allocation failed"); sdgpu_destroy(c); return SDGPU_ERR;
 	}
+	memset(c->h_state, 0, sizeof(SdDevState));
 
 	// ---- cut scratch -------------------------------------------------------------------------------------
 	c->maxChunks = SD_MAX_CHUNKS;
@@ -495,6 +546,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	if (c->h_pinD) cudaFreeHost(c->h_pinD);
 	if (c->h_pinI) cudaFreeHost(c->h_pinI);
 	if (c->h_state) cudaFreeHost(c->h_state);
+	if (c->h_cutRes) cudaFreeHost(c->h_cutRes);
 	if (c->evA) cudaEventDestroy(c->evA);
 	if (c->evB) cudaEventDestroy(c->evB);
 	if (c->evC) cudaEventDestroy(c->evC);
@@ -507,8 +559,10 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 extern "C" int sdgpu_reset(sdgpu_ctx *c) {
 	if (!c) return sdgpu_fail("null context");
 	SD_CUDA(cudaSetDevice(c->device));
-	SD_CUDA(cudaMemsetAsync(c->d_state, 0, sizeof(SdDevState), c->stream));
-	SD_CUDA(cudaStreamSynchronize(c->stream));
+	{ SdDevState init; memset(&init, 0, sizeof init); init.foundLambda = init.foundSigma = init.foundOmega = INT_MAX;
+	  SD_CUDA(cudaStreamSynchronize(c->stream));
+	  SD_CUDA(cudaMemcpy(c->d_state, &init, sizeof init, cudaMemcpyHostToDevice));
+	  *c->h_state = init; }
 	c->omegaCnt = c->lambdaCnt = c->sigmaCnt = c->basisCnt = c->termCnt = 0;
 	c->maxPhiLen = 0; c->anyInfeasibleBasis = false; c->lastOmegaCnt = 0;
 	c->basis.clear(); c->hostMask.clear();
@@ -536,24 +590,19 @@ extern "C" int sdgpu_get_stats(sdgpu_ctx *c, sdgpu_stats *out) {
 }
 
 // ---- omega -------------------------------------------------------------------------------------------------
-static int sd_omega_stage(sdgpu_ctx *c, const double *observ) {
+static int sd_launch_omega(sdgpu_ctx *c, const double *observ, double tol, int mode, int weight) {
 	if (sd_stage_vec(c, observ, c->numRV + 1)) return SDGPU_ERR;
-	k_stage_candidate<<<sd_blocks(c->numRV, 128), 128, 0, c->stream>>>(c->d_vecIn, nullptr, c->numRV, c->d_cand, c->d_state, 1);
+	const int blocks = mode == 2 ? 1 : sd_blocks(c->omegaCnt, 256);
+	k_omega_fused<<<blocks, 256, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(c->d_pinD, c->numRV, c->d_omega, c->d_omegaW, c->NP,
+			c->caps.maxOmega, tol, mode, weight, c->d_state, c->d_hstate);
 	sd_count_launch(c);
-	return 0;
+	return sd_sync_state(c);
 }
 
 extern "C" int sdgpu_calc_omega(sdgpu_ctx *c, const double *observ, double tol, int *newOmegaFlag) {
 	if (!c || !observ) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
-	if (sd_omega_stage(c, observ)) return SDGPU_ERR;
-	if (c->omegaCnt > 0) {
-		k_find_row<<<sd_blocks(c->omegaCnt, 256), 256, 0, c->stream>>>(c->d_omega, c->NP, c->numRV, c->d_cand, tol, c->d_state, 1);
-		sd_count_launch(c);
-	}
-	k_omega_commit<<<1, 128, 0, c->stream>>>(c->d_omega, c->d_omegaW, c->NP, c->numRV, c->d_cand, c->caps.maxOmega, c->d_state, 0, 1);
-	sd_count_launch(c);
-	if (sd_sync_state(c)) return SDGPU_ERR;
+	if (sd_launch_omega(c, observ, tol, 0, 1)) return SDGPU_ERR;
 	if (newOmegaFlag) *newOmegaFlag = c->h_state->newOmega;
 	return c->h_state->omegaIdx;
 }
@@ -561,22 +610,14 @@ extern "C" int sdgpu_calc_omega(sdgpu_ctx *c, const double *observ, double tol, 
 extern "C" int sdgpu_omega_find(sdgpu_ctx *c, const double *observ, double tol) {
 	if (!c || !observ) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
-	if (sd_omega_stage(c, observ)) return SDGPU_ERR;
-	if (c->omegaCnt > 0) {
-		k_find_row<<<sd_blocks(c->omegaCnt, 256), 256, 0, c->stream>>>(c->d_omega, c->NP, c->numRV, c->d_cand, tol, c->d_state, 1);
-		sd_count_launch(c);
-	}
-	if (sd_sync_state(c)) return SDGPU_ERR;
-	return c->h_state->foundOmega == INT_MAX ? SDGPU_NONE : c->h_state->foundOmega;
+	if (sd_launch_omega(c, observ, tol, 1, 0)) return SDGPU_ERR;
+	return c->h_state->omegaIdx < 0 ? SDGPU_NONE : c->h_state->omegaIdx;
 }
 
 extern "C" int sdgpu_omega_append(sdgpu_ctx *c, const double *observ, int weight) {
 	if (!c || !observ) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
-	if (sd_omega_stage(c, observ)) return SDGPU_ERR;
-	k_omega_commit<<<1, 128, 0, c->stream>>>(c->d_omega, c->d_omegaW, c->NP, c->numRV, c->d_cand, c->caps.maxOmega, c->d_state, 1, weight);
-	sd_count_launch(c);
-	if (sd_sync_state(c)) return SDGPU_ERR;
+	if (sd_launch_omega(c, observ, 0.0, 2, weight)) return SDGPU_ERR;
 	return c->h_state->omegaIdx;
 }
 
@@ -610,7 +651,7 @@ extern "C" int sdgpu_omega_append_bulk(sdgpu_ctx *c, int64_t n, const double *va
 		if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = sdgpu_fail("omega_append_bulk kernel failed");
 	}
 	if (rc == 0) {
-		k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, (int) n, 0, 0, 0);
+		k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, c->d_hstate, (int) n, 0, 0, 0);
 		sd_count_launch(c);
 		rc = sd_sync_state(c);
 	}
@@ -619,23 +660,18 @@ extern "C" int sdgpu_omega_append_bulk(sdgpu_ctx *c, int64_t n, const double *va
 }
 
 // ---- lambda / sigma / delta --------------------------------------------------------------------------------
-static void sd_launch_lambda(sdgpu_ctx *c, const double *d_pi, double tol, int64_t lambdaUpper) {
-	k_stage_candidate<<<sd_blocks(c->R, 128), 128, 0, c->stream>>>(d_pi, c->d_rvRows, c->R, c->d_cand, c->d_state, 0);
-	if (lambdaUpper > 0)
-		k_find_row<<<sd_blocks(lambdaUpper, 256), 256, 0, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_cand, tol, c->d_state, 0);
-	k_lambda_commit<<<1, 256, 0, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_cand, c->caps.maxLambda, c->d_state);
-	sd_count_launch(c, lambdaUpper > 0 ? 3 : 2);
+// calcLambda in one launch; its last block also stages calcSigma's candidate (pibBar, piCBar) from the same vector
+static void sd_launch_lambda(sdgpu_ctx *c, const double *d_pi, double mubBar, double tol, int64_t lambdaUpper) {
+	k_lambda_fused<<<sd_blocks(lambdaUpper, 256), 256, (size_t) std::max(1, c->R) * 8, c->stream>>>(d_pi, c->rows, c->d_rvRows, c->R, c->d_lambda, c->LP,
+			c->caps.maxLambda, tol, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->n1c,
+			c->d_vecIn, c->d_candC, c->d_state, c->d_hstate);
+	sd_count_launch(c);
 }
 
-static void sd_launch_sigma(sdgpu_ctx *c, const double *d_pi, double mubBar, int iter, double tol, int64_t sigmaUpper,
-		int overrideNew, int overrideIdx) {
-	k_sigma_prepare<<<sd_blocks(c->n1c + 1, 128), 128, 0, c->stream>>>(d_pi, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart,
-			c->d_cbRow, c->d_cbVal, c->n1c, c->d_candC, c->d_state, overrideNew, overrideIdx);
-	if (sigmaUpper > 0)
-		k_sigma_find<<<sd_blocks(sigmaUpper, 256), 256, 0, c->stream>>>(c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaLam, c->SP, c->n1c, c->d_candC, tol, c->d_state);
-	k_sigma_commit<<<1, 128, 0, c->stream>>>(c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr, c->d_sigmaLam, c->d_sigmaCk, c->SP, c->n1c, c->n1cP,
-			c->d_candC, iter, c->caps.maxSigma, c->d_state);
-	sd_count_launch(c, sigmaUpper > 0 ? 3 : 2);
+static void sd_launch_sigma(sdgpu_ctx *c, int iter, double tol, int64_t sigmaUpper) {
+	k_sigma_fused<<<sd_blocks(sigmaUpper, 256), 256, 0, c->stream>>>(c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr, c->d_sigmaLam, c->d_sigmaCk, c->SP,
+			c->n1c, c->n1cP, c->d_candC, tol, iter, c->caps.maxSigma, c->d_state, c->d_hstate);
+	sd_count_launch(c);
 }
 
 static void sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
@@ -656,7 +692,7 @@ extern "C" int sdgpu_calc_lambda(sdgpu_ctx *c, const double *Pi, double tol, int
 	if (!c || !Pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, Pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, c->d_vecIn, tol, c->lambdaCnt);
+	sd_launch_lambda(c, c->d_pinD, 0.0, tol, c->lambdaCnt);
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
 	return c->h_state->lambdaIdx;
@@ -668,7 +704,11 @@ extern "C" int sdgpu_calc_sigma(sdgpu_ctx *c, const double *pi, double mubBar, i
 	if (idxLambda < 0 || idxLambda >= c->lambdaCnt) return sdgpu_fail("calc_sigma: lambda index %d out of range", idxLambda);
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_sigma(c, c->d_vecIn, mubBar, currentIter, tol, c->sigmaCnt, newLambdaFlag != 0, idxLambda);
+	// stand-alone form: stage (pibBar, piCBar) with the caller's lambda index / flag, then scan + commit
+	k_sigma_prepare<<<sd_blocks(c->n1c + 1, 128), 128, 0, c->stream>>>(c->d_pinD, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart,
+			c->d_cbRow, c->d_cbVal, c->n1c, c->d_candC, c->d_state, newLambdaFlag != 0, idxLambda);
+	sd_count_launch(c);
+	sd_launch_sigma(c, currentIter, tol, c->sigmaCnt);
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (newSigmaFlag) *newSigmaFlag = c->h_state->newSigma;
 	return c->h_state->sigmaIdx;
@@ -685,7 +725,7 @@ extern "C" int sdgpu_calc_delta(sdgpu_ctx *c, int newOmegaFlag, int elemIdx) {
 		if (elemIdx < 0 || elemIdx >= c->lambdaCnt) return sdgpu_fail("calc_delta: lambda %d out of range", elemIdx);
 		sd_launch_delta_row(c, elemIdx, c->omegaCnt);
 	}
-	SD_CUDA(cudaStreamSynchronize(c->stream));
+	// no host wait: later calls are ordered behind this one on the context's stream (a fault surfaces at the next sync)
 	SD_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -695,8 +735,8 @@ extern "C" int sdgpu_update_dual(sdgpu_ctx *c, const double *pi, double mubBar, 
 	if (!c || !pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, c->d_vecIn, tol, c->lambdaCnt);                    // stocUpdate.c:78
-	sd_launch_sigma(c, c->d_vecIn, mubBar, currentIter, tol, c->sigmaCnt, -1, 0);   // :81
+	sd_launch_lambda(c, c->d_pinD, mubBar, tol, c->lambdaCnt);             // stocUpdate.c:78 (+ staging of :293-296)
+	sd_launch_sigma(c, currentIter, tol, c->sigmaCnt);                     // :81
 	sd_launch_delta_row(c, -1, c->omegaCnt);                               // :84-85 (kernel no-op unless the lambda was new)
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (lambdaIdx) *lambdaIdx = c->h_state->lambdaIdx;
@@ -732,7 +772,7 @@ extern "C" int sdgpu_update_dual_bulk(sdgpu_ctx *c, int64_t n, const double *pis
 			k_dual_bulk<<<sd_blocks(m, 64), 64, 0, c->stream>>>(d_pis, m, c->rows, mubBar ? d_mub : nullptr, iters ? d_it : nullptr, c->d_rvRows, c->R,
 					c->d_bBarCol, c->d_bBarVal, c->bBarCnt, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->n1c, c->n1cP, c->d_lambda, c->LP,
 					c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr, c->d_sigmaLam, c->d_sigmaCk, c->SP, c->lambdaCnt, c->sigmaCnt);
-			k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, 0, (int) m, (int) m, 0);
+			k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, c->d_hstate, 0, (int) m, (int) m, 0);
 			sd_count_launch(c, 2);
 			for (int64_t i = 0; i < m; i++) {
 				if (lambdaIdx) lambdaIdx[i0 + i] = (int32_t) (c->lambdaCnt + i);
@@ -747,8 +787,8 @@ extern "C" int sdgpu_update_dual_bulk(sdgpu_ctx *c, int64_t n, const double *pis
 				const double *d_pi = d_pis + (size_t) i * stride;
 				double mb = mubBar ? mubBar[i0 + i] : 0.0;
 				int it = iters ? iters[i0 + i] : (int) (i0 + i + 1);
-				sd_launch_lambda(c, d_pi, tol, c->lambdaCnt + i);
-				sd_launch_sigma(c, d_pi, mb, it, tol, c->sigmaCnt + i, -1, 0);
+				sd_launch_lambda(c, d_pi, mb, tol, c->lambdaCnt + i);
+				sd_launch_sigma(c, it, tol, c->sigmaCnt + i);
 				sd_launch_delta_row(c, -1, c->omegaCnt);
 				k_record_pair<<<1, 1, 0, c->stream>>>(c->d_state, d_li, d_si, i);
 				sd_count_launch(c);
@@ -805,17 +845,29 @@ extern "C" int sdgpu_basis_append(sdgpu_ctx *c, int ck, int feasFlag, int phiLen
 	hb.sigmaIdx.assign(sigmaIdx, sigmaIdx + phiLength + 1);
 	hb.omegaIdx.assign(phiLength + 1, 0);
 	for (int t = 1; t <= phiLength; t++) hb.omegaIdx[t] = omegaIdx[t];
-	int32_t *pi = c->h_pinI;      // [ck, feas, phiLen, termStart, termEnd, sigma..., omega...]
-	int nT = phiLength + 1;
-	if ((size_t) (5 + 2 * nT) > c->pinIcap) return sdgpu_fail("basis_append: too many terms for the staging buffer");
-	pi[0] = ck; pi[1] = hb.feas; pi[2] = phiLength; pi[3] = (int32_t) c->termCnt; pi[4] = (int32_t) (c->termCnt + nT);
-	for (int t = 0; t < nT; t++) { pi[5 + t] = hb.sigmaIdx[t]; pi[5 + nT + t] = hb.omegaIdx[t]; }
-	SD_CUDA(cudaMemcpyAsync(c->d_bCk + b, pi + 0, 4, cudaMemcpyHostToDevice, c->stream));
-	SD_CUDA(cudaMemcpyAsync(c->d_bFeas + b, pi + 1, 4, cudaMemcpyHostToDevice, c->stream));
-	SD_CUDA(cudaMemcpyAsync(c->d_bPhiLen + b, pi + 2, 4, cudaMemcpyHostToDevice, c->stream));
-	SD_CUDA(cudaMemcpyAsync(c->d_bTermStart + b, pi + 3, 8, cudaMemcpyHostToDevice, c->stream));
-	SD_CUDA(cudaMemcpyAsync(c->d_tSigma + c->termCnt, pi + 5, (size_t) nT * 4, cudaMemcpyHostToDevice, c->stream));
-	SD_CUDA(cudaMemcpyAsync(c->d_tOmega + c->termCnt, pi + 5 + nT, (size_t) nT * 4, cudaMemcpyHostToDevice, c->stream));
+	const int nT = phiLength + 1;
+	if (nT <= 16) {
+		SdBasisRec r;
+		r.b = b; r.ck = ck; r.feas = hb.feas; r.phiLen = phiLength; r.termStart = (int) c->termCnt; r.nT = nT;
+		for (int t = 0; t < nT; t++) { r.sigma[t] = hb.sigmaIdx[t]; r.omega[t] = hb.omegaIdx[t]; }
+		k_basis_commit<<<1, 1, 0, c->stream>>>(r, c->d_bCk, c->d_bFeas, c->d_bPhiLen, c->d_bTermStart, c->d_tSigma, c->d_tOmega, c->d_state, c->d_hstate);
+		sd_count_launch(c);
+	}
+	else {
+		int32_t *pi = c->h_pinI;      // [ck, feas, phiLen, termStart, termEnd, sigma..., omega...]
+		if ((size_t) (5 + 2 * nT) > c->pinIcap) return sdgpu_fail("basis_append: too many terms for the staging buffer");
+		pi[0] = ck; pi[1] = hb.feas; pi[2] = phiLength; pi[3] = (int32_t) c->termCnt; pi[4] = (int32_t) (c->termCnt + nT);
+		for (int t = 0; t < nT; t++) { pi[5 + t] = hb.sigmaIdx[t]; pi[5 + nT + t] = hb.omegaIdx[t]; }
+		SD_CUDA(cudaMemcpyAsync(c->d_bCk + b, pi + 0, 4, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaMemcpyAsync(c->d_bFeas + b, pi + 1, 4, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaMemcpyAsync(c->d_bPhiLen + b, pi + 2, 4, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaMemcpyAsync(c->d_bTermStart + b, pi + 3, 8, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaMemcpyAsync(c->d_tSigma + c->termCnt, pi + 5, (size_t) nT * 4, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaMemcpyAsync(c->d_tOmega + c->termCnt, pi + 5 + nT, (size_t) nT * 4, cudaMemcpyHostToDevice, c->stream));
+		k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, c->d_hstate, 0, 0, 0, 1);
+		sd_count_launch(c);
+		SD_CUDA(cudaStreamSynchronize(c->stream));
+	}
 	if (c->rvd > 0) {
 		c->hostMask.emplace_back(hb.feas ? std::vector<uint8_t>((size_t) c->NP, 1) : std::vector<uint8_t>());
 		if (hb.feas) {
@@ -823,9 +875,6 @@ extern "C" int sdgpu_basis_append(sdgpu_ctx *c, int ck, int feasFlag, int phiLen
 			sd_count_launch(c);
 		}
 	}
-	k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, 0, 0, 0, 1);
-	sd_count_launch(c);
-	SD_CUDA(cudaStreamSynchronize(c->stream));
 	c->basis.push_back(std::move(hb));
 	c->termCnt += nT; c->basisCnt++;
 	c->maxPhiLen = std::max(c->maxPhiLen, phiLength);
@@ -849,7 +898,7 @@ extern "C" int sdgpu_basis_append_bulk(sdgpu_ctx *c, int64_t n, const int32_t *c
 	SD_CUDA(cudaMemcpyAsync(c->d_bTermStart + b0, starts.data(), ((size_t) n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
 	SD_CUDA(cudaMemcpyAsync(c->d_tSigma + c->termCnt, sigmaIdx, (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
 	SD_CUDA(cudaMemcpyAsync(c->d_tOmega + c->termCnt, zeros.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
-	k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, 0, 0, 0, (int) n);
+	k_bump_counts<<<1, 1, 0, c->stream>>>(c->d_state, c->d_hstate, 0, 0, 0, (int) n);
 	sd_count_launch(c);
 	for (int64_t i = 0; i < n; i++) {
 		SdHostBasis hb;
