@@ -275,6 +275,7 @@ def gpu_arm(args):
 
     stream = torch.cuda.Stream()
     t._check(api._fn("set_stream")(t.ctx, C.c_void_p(stream.cuda_stream)), "set_stream")
+    t.set_timing(True)
     beta = np.zeros(prob.prevCols + 1)
     istar = np.zeros(N + extra + 8, np.int32)
     cut_dev = CCut(0.0, _pf64(beta), None, 0, 0, 0.0, 0.0)           # iStar stays device-resident

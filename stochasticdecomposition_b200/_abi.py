@@ -215,7 +215,7 @@ class Api:
             "get_sigma": (i, [vp, i, c_f64p, c_f64p, c_intp, c_intp]), "get_delta": (i, [vp, i, i, c_f64p, c_f64p]),
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
             "get_stats": (i, [vp, C.POINTER(CStats)]),
-            "set_sweep_variant": (i, [vp, i]), "set_stream": (i, [vp, vp]),
+            "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]),
         }
         for name, (res, args) in table.items():
             fn = self._fn(name)
@@ -459,6 +459,9 @@ class Tables:
         s = CStats()
         self._check(self._call("get_stats", C.byref(s)), "get_stats")
         return {k: getattr(s, k) for k, _ in CStats._fields_}
+
+    def set_timing(self, on: bool = True):
+        self._check(self._call("set_timing", int(on)), "set_timing")
 
     def set_sweep_variant(self, v: int):
         self._check(self._call("set_sweep_variant", v), "set_sweep_variant")

@@ -245,7 +245,7 @@ struct MergeArgs {
 	const double *sigmaPib, *sigmaPiCr; const int32_t *sigmaLam; int sigmaCnt, n1c, n1cP;
 	const int32_t *bTermStart, *tSigma, *tOmega;
 	int randCost;                 // num->rvdOmCnt > 0: the cuts.c:142-159 branch
-	int32_t *iStar; double *tilePart; int P;
+	int32_t *iStar; int32_t *iStarHost; int iStarHostCap; double *tilePart; int P;
 	// epilogue run by the last block: tile partials -> un-normalised cut [-> normalised cut in mapped host memory]
 	int n1; const int32_t *CCols, *qCols; double *partial; int fuseNormalise, numSamples; double *hostRes; SdDevState *st;
 };
@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		else
 			istar = oldI;                                         // cuts.c:132
 		a.iStar[o] = istar;
+		if (o < a.iStarHostCap) a.iStarHost[o] = istar;           // small cuts: iStar lands in mapped host memory, no D2H copy
 		if (istar < 0) tMiss = 1.0;                               // cuts.c:136-139
 		else if (!a.randCost) {                                   // cuts.c:160-162: the BASIS index doubles as the sigma index
 			if (istar >= a.sigmaCnt) { tMiss = 1.0e9; istar = -1; }
@@ -574,7 +575,7 @@ static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks
 	int64_t target = (int64_t) smCount * 4 * 3;
 	int64_t want = std::max<int64_t>(1, (target + tiles - 1) / tiles);
 	want = std::min<int64_t>(want, c->maxChunks);
-	want = std::min<int64_t>(want, std::max<int64_t>(1, (c->basisCnt + 63) / 64));
+	want = std::min<int64_t>(want, std::max<int64_t>(1, (c->basisCnt + 15) / 16));   // at least two load batches per chunk
 	int cs = (int) ((c->basisCnt + want - 1) / want);
 	cs = std::max(cs, 1);
 	*chunkSize = cs;
@@ -587,7 +588,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 	if (c->Q > 64) return sdgpu_fail("sd_cut: rvCOmCnt %d exceeds the 64 random T elements this build stages in shared memory", c->Q);
 	SD_CUDA(cudaSetDevice(c->device));
 	int64_t launches0 = c->stats.total_launches;
-	SD_CUDA(cudaEventRecord(c->evA, c->stream));
+	if (c->timing) SD_CUDA(cudaEventRecord(c->evA, c->stream));
 	const int N = (int) c->omegaCnt;
 	const int tiles = (int) ((N + SD_TILE_W - 1) / SD_TILE_W);
 	const int P = 4 + c->n1c + c->Q;
@@ -599,7 +600,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		int chunkSize = 1, nChunks = 1;
 		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);
 		dim3 grid((unsigned) tiles, (unsigned) nChunks);
-		SD_CUDA(cudaEventRecord(c->evC, c->stream));
+		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
 		if (general) {
 			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
 		}
@@ -617,7 +618,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			else                     k_sweep_ldg<false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 		}
 		sd_count_launch(c);
-		SD_CUDA(cudaEventRecord(c->evD, c->stream));
+		if (c->timing) SD_CUDA(cudaEventRecord(c->evD, c->stream));
 		// algorithmic bytes of the sweep: delta stream + per-observation weight and iStar + per-basis descriptors
 		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * c->basisCnt * (int64_t) N + (int64_t) N * 8 + c->basisCnt * 16;
 
@@ -631,6 +632,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		m.bTermStart = c->d_bTermStart; m.tSigma = c->d_tSigma; m.tOmega = c->d_tOmega;
 		m.randCost = c->rvd > 0;
 		m.iStar = c->d_iStar; m.tilePart = c->d_tilePart; m.P = P;
+		m.iStarHost = c->d_iStarHost; m.iStarHostCap = N <= c->iStarHostCap ? N : 0;
 		m.n1 = c->n1; m.CCols = c->d_CCols; m.qCols = c->rvd > 0 ? c->d_rvCOmCols : c->d_rvCols;       // cuts.c:157 vs :167
 		m.partial = c->d_cutPartial; m.fuseNormalise = c->ncclComm == nullptr && fuseNormalise; m.numSamples = numSamples;
 		m.hostRes = c->d_cutRes; m.st = c->d_state;
@@ -643,8 +645,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 	}
 	else {
 		// no observation or no basis at all: nothing to sweep; with observations every one is missing its maximiser (cuts.c:136-139)
-		SD_CUDA(cudaEventRecord(c->evC, c->stream));
-		SD_CUDA(cudaEventRecord(c->evD, c->stream));
+		if (c->timing) { SD_CUDA(cudaEventRecord(c->evC, c->stream)); SD_CUDA(cudaEventRecord(c->evD, c->stream)); }
 		c->stats.last_sweep_bytes = 0;
 		std::vector<double> zero((size_t) c->n1 + 4, 0.0);
 		zero[c->n1 + 3] = (double) N;
@@ -676,14 +677,18 @@ extern "C" int sdgpu_sd_cut_finish(sdgpu_ctx *c, int numSamples, sdgpu_cut *cut)
 		sd_count_launch(c);
 	}
 	double *h = c->h_cutRes;
-	if (cut->iStar && c->lastOmegaCnt > 0)
+	const bool istarMapped = c->lastOmegaCnt > 0 && c->lastOmegaCnt <= c->iStarHostCap && c->basisCnt > 0;
+	if (cut->iStar && c->lastOmegaCnt > 0 && !istarMapped)
 		SD_CUDA(cudaMemcpyAsync(cut->iStar, c->d_iStar, (size_t) c->lastOmegaCnt * 4, cudaMemcpyDeviceToHost, c->stream));
-	SD_CUDA(cudaEventRecord(c->evB, c->stream));
+	if (c->timing) SD_CUDA(cudaEventRecord(c->evB, c->stream));
 	SD_CUDA(cudaStreamSynchronize(c->stream));
 	SD_CUDA(cudaGetLastError());
-	float ms = 0.f;
-	if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->stats.last_cut_ms = ms;
-	if (cudaEventElapsedTime(&ms, c->evC, c->evD) == cudaSuccess) c->stats.last_sweep_ms = ms;
+	if (cut->iStar && istarMapped) memcpy(cut->iStar, c->h_iStar, (size_t) c->lastOmegaCnt * 4);
+	if (c->timing) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->stats.last_cut_ms = ms;
+		if (cudaEventElapsedTime(&ms, c->evC, c->evD) == cudaSuccess) c->stats.last_sweep_ms = ms;
+	}
 	c->stats.last_cut_launches += c->stats.total_launches - launches0;
 	cut->omegaCnt = c->lastOmegaCnt; cut->numSamples = numSamples;
 	cut->cummOld = h[c->n1 + 1]; cut->cummAll = h[c->n1 + 2];

@@ -116,6 +116,10 @@ struct sdgpu_ctx {
 	int      maxChunks = 1;
 	int      sweepVariant = 0;
 	int      lastOmegaCnt = 0;
+	bool     timing = false;         // record CUDA events around the cut and its sweep (sdgpu_set_timing)
+	int32_t *h_iStar = nullptr;      // pinned + mapped [iStarHostCap]: the merge kernel mirrors iStar here for small N
+	int32_t *d_iStarHost = nullptr;  // device alias
+	int64_t  iStarHostCap = 0;
 	bool     cutFused = false;       // the last merge block already normalised the cut into h_cutRes
 
 	// host mirrors (bookkeeping only; no table arithmetic happens on the host)

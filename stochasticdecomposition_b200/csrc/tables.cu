@@ -505,12 +505,15 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	    cudaHostAlloc((void **) &c->h_pinI, c->pinIcap * sizeof(int32_t), cudaHostAllocMapped) != cudaSuccess ||
 	    cudaHostAlloc((void **) &c->h_state, sizeof(SdDevState), cudaHostAllocMapped) != cudaSuccess ||
 	    cudaHostAlloc((void **) &c->h_cutRes, ((size_t) c->n1 + 8) * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostAlloc((void **) &c->h_iStar, (size_t) std::min<int64_t>(c->NP, 65536) * sizeof(int32_t), cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostGetDevicePointer((void **) &c->d_iStarHost, c->h_iStar, 0) != cudaSuccess ||
 	    cudaHostGetDevicePointer((void **) &c->d_pinD, c->h_pinD, 0) != cudaSuccess ||
 	    cudaHostGetDevicePointer((void **) &c->d_hstate, c->h_state, 0) != cudaSuccess ||
 	    cudaHostGetDevicePointer((void **) &c->d_cutRes, c->h_cutRes, 0) != cudaSuccess) {
 		sdgpu_fail("pinned host allocation failed"); sdgpu_destroy(c); return SDGPU_ERR;
 	}
 	memset(c->h_state, 0, sizeof(SdDevState));
+	c->iStarHostCap = std::min<int64_t>(c->NP, 65536);
 
 	// ---- cut scratch -------------------------------------------------------------------------------------
 	c->maxChunks = SD_MAX_CHUNKS;
@@ -547,6 +550,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	if (c->h_pinI) cudaFreeHost(c->h_pinI);
 	if (c->h_state) cudaFreeHost(c->h_state);
 	if (c->h_cutRes) cudaFreeHost(c->h_cutRes);
+	if (c->h_iStar) cudaFreeHost(c->h_iStar);
 	if (c->evA) cudaEventDestroy(c->evA);
 	if (c->evB) cudaEventDestroy(c->evB);
 	if (c->evC) cudaEventDestroy(c->evC);
@@ -580,6 +584,12 @@ extern "C" int sdgpu_set_stream(sdgpu_ctx *c, void *stream) {
 	SD_CUDA(cudaStreamSynchronize(c->stream));
 	if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
 	c->stream = (cudaStream_t) stream; c->ownStream = false;
+	return 0;
+}
+
+extern "C" int sdgpu_set_timing(sdgpu_ctx *c, int on) {
+	if (!c) return sdgpu_fail("null context");
+	c->timing = on != 0;
 	return 0;
 }
 

@@ -17,6 +17,7 @@ def probe(D, N, rv, n1, reps=30):
     k = int(weights.sum())
     t = bench.load_tables(sd.load_library(), prob, pis, obsv, weights, D, N, k, reps + 8)
     out = {"D": D, "N": N, "rv": rv, "n1": n1}
+    t.set_timing(True)
     for want_istar in (True, False):
         for s in range(5):
             t.sd_cut(xs[s], k, 1, 0.0, want_istar=want_istar)
