@@ -54,6 +54,22 @@ __device__ __forceinline__ double sd_block_sum(double v, double *s_red) {
 	return t;
 }
 
+// sum_k col[k*stride] * s_x[k], left to right from 0.0 with separate multiply and add (vXv, cuts.c:106); the loads of a
+// batch of 8 are issued together so the chain of dependent adds does not also serialise the memory latency
+__device__ __forceinline__ double sd_dot_strided(const double *__restrict__ col, size_t stride, const double *s_x, int n) {
+	double acc = 0.0;
+	int k = 0;
+	for (; k + 8 <= n; k += 8) {
+		double v[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) v[u] = col[(size_t) (k + u) * stride];
+#pragma unroll
+		for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, __dmul_rn(v[u], s_x[k + u]));
+	}
+	for (; k < n; k++) acc = __dadd_rn(acc, __dmul_rn(col[(size_t) k * stride], s_x[k]));
+	return acc;
+}
+
 // Fused prologue of a cut: x arrives as a kernel parameter (no H2D copy), thread i computes piCbarX of sigma i (only
 // when the general sweep needs the whole vector) and the descriptor of basis i, whose piCbarX is recomputed from its
 // own sigma row with the same left-to-right sum, hence the same bits.
@@ -71,15 +87,10 @@ __global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, doubl
 		for (int i = threadIdx.x; i <= n1; i += blockDim.x) xDevOut[i] = xp.v[i];
 	__syncthreads();
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (piCbarXAll && i < sigmaCnt) {
-		double acc = 0.0;
-		for (int k = 0; k < n1c; k++) acc = __dadd_rn(acc, __dmul_rn(piCk[(size_t) k * SP + i], s_x[k]));
-		piCbarXAll[i] = acc;
-	}
+	if (piCbarXAll && i < sigmaCnt) piCbarXAll[i] = sd_dot_strided(piCk + i, (size_t) SP, s_x, n1c);
 	if (i < basisCnt) {
 		const int s = tSigma[bTermStart[i]];
-		double acc = 0.0;
-		for (int k = 0; k < n1c; k++) acc = __dadd_rn(acc, __dmul_rn(piCk[(size_t) k * SP + s], s_x[k]));
+		const double acc = sd_dot_strided(piCk + s, (size_t) SP, s_x, n1c);
 		const int ck = bCk[i];
 		int win = 0;
 		if (bFeas[i]) {
@@ -338,7 +349,17 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 			const int per = (SD_TILE_W + groups - 1) / groups;
 			const int w0 = g * per, w1 = min(SD_TILE_W, w0 + per);
 			double acc = 0.0;
-			for (int w = w0; w < w1; w++) {
+			int w = w0;
+			if (!a.randCost) {
+				for (; w + 8 <= w1; w += 8) {                    // gathers of a batch issued together, adds still in observation order
+					double v[8];
+#pragma unroll
+					for (int u = 0; u < 8; u++) { const int is = s_istar[w + u]; v[u] = is >= 0 ? a.sigmaPiCr[(size_t) is * a.n1cP + k] : 0.0; }
+#pragma unroll
+					for (int u = 0; u < 8; u++) if (s_istar[w + u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], (double) s_w[w + u]));
+				}
+			}
+			for (; w < w1; w++) {
 				const int is = s_istar[w];
 				if (is < 0) continue;
 				if (!a.randCost)
@@ -370,7 +391,15 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	const int nT = gridDim.x;
 	for (int p = tid; p < a.P; p += blockDim.x) {
 		double acc = 0.0;
-		for (int t = 0; t < nT; t++) acc = __dadd_rn(acc, __ldcg(a.tilePart + (size_t) t * a.P + p));
+		int t = 0;
+		for (; t + 8 <= nT; t += 8) {
+			double v[8];
+#pragma unroll
+			for (int u = 0; u < 8; u++) v[u] = __ldcg(a.tilePart + (size_t) (t + u) * a.P + p);
+#pragma unroll
+			for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
+		}
+		for (; t < nT; t++) acc = __dadd_rn(acc, __ldcg(a.tilePart + (size_t) t * a.P + p));
 		s_tot[p] = acc;
 	}
 	for (int c = tid; c <= a.n1 + 3; c += blockDim.x) s_cut[c] = 0.0;
