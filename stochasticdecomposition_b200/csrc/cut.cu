@@ -190,6 +190,123 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a) {
 	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
 }
 
+// ======================================================================================================
+// K6, variant 2: the same sweep fed by the TMA engine.  One producer warp issues 1-D bulk copies
+// (cp.async.bulk.shared::cluster.global, 4 KiB = one dual row of the observation tile each) into a ring of
+// shared-memory stages guarded by mbarriers; eight consumer warps read their 16 bytes per row with LDS.128 and
+// run the identical score / running-maximum code.  Bytes in flight are set by the ring (TMA_STAGES x TMA_ROWS x
+// 4 KiB = 128 KiB per SM), not by registers.  RHS-only bases without a feasibility mask (Q = 0, rvdOmCnt = 0).
+// ======================================================================================================
+#define TMA_ROWS 8
+#define TMA_STAGES 4
+#define TMA_CONSUMERS SD_SWEEP_THREADS
+#define TMA_THREADS (TMA_CONSUMERS + 32)
+#define TMA_ROW_BYTES (SD_TILE_W * 8)
+
+__device__ __forceinline__ uint32_t sd_smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sd_mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sd_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sd_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(sd_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_wait(uint64_t *bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+				: "=r"(done) : "r"(sd_smem_u32(bar)), "r"(parity) : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 1) k_sweep_tma(SweepArgs a) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *ring = reinterpret_cast<double *>(smem_raw);                                   // [stage][row][512]
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t) TMA_STAGES * TMA_ROWS * TMA_ROW_BYTES);
+	uint64_t *empty = full + TMA_STAGES;
+	double2 *s_ac = reinterpret_cast<double2 *>(empty + TMA_STAGES);                        // [SW_BATCH] (sigma.pib, piCbarX)
+	int *s_win = reinterpret_cast<int *>(s_ac + SW_BATCH);                                 // [SW_BATCH]
+	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	const int nRows = b1 - b0, nIter = (nRows + TMA_ROWS - 1) / TMA_ROWS;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * SD_TILE_W;                  // Q == 0: one plane per row
+	if (tid == 0) {
+		for (int s = 0; s < TMA_STAGES; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	if (tid >= TMA_CONSUMERS) {
+		// ---------------- producer warp: one lane feeds the ring -------------------------------------------------
+		if (tid == TMA_CONSUMERS) {
+			for (int it = 0; it < nIter; it++) {
+				const int s = it % TMA_STAGES;
+				sd_mbar_wait(&empty[s], ((it / TMA_STAGES) & 1) ^ 1);
+				const int r0 = it * TMA_ROWS, nr = min(TMA_ROWS, nRows - r0);
+				sd_mbar_expect_tx(&full[s], (uint32_t) nr * TMA_ROW_BYTES);
+				for (int r = 0; r < nr; r++) {
+					const int row = a.descRow[b0 + r0 + r];
+					sd_bulk_g2s(ring + ((size_t) s * TMA_ROWS + r) * SD_TILE_W, tileBase + (size_t) row * SD_TILE_W, TMA_ROW_BYTES, &full[s]);
+				}
+			}
+		}
+		return;
+	}
+
+	// ---------------- consumers --------------------------------------------------------------------------------------
+	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
+	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+	for (int it = 0; it < nIter; it++) {
+		const int r0 = it * TMA_ROWS;
+		if (r0 % SW_BATCH == 0) {                                                           // refill the descriptor batch (consumers only)
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+			const int b = b0 + r0 + tid;
+			const bool ok = b < b1;
+			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
+			s_win[tid] = ok ? a.descWin[b] : 0;
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+		}
+		const int s = it % TMA_STAGES;
+		sd_mbar_wait(&full[s], (it / TMA_STAGES) & 1);
+		const double2 *stage = reinterpret_cast<const double2 *>(ring + (size_t) s * TMA_ROWS * SD_TILE_W) + tid;
+		double2 d[TMA_ROWS];
+#pragma unroll
+		for (int r = 0; r < TMA_ROWS; r++) d[r] = stage[(size_t) r * (SD_TILE_W / 2)];
+		__syncwarp();
+		if ((tid & 31) == 0) sd_mbar_arrive(&empty[s]);                                    // this warp is done with the stage
+#pragma unroll
+		for (int r = 0; r < TMA_ROWS; r++) {
+			const int j = (r0 + r) % SW_BATCH;
+			const int win = s_win[j];
+			if (win == 0) continue;
+			const double2 ac = s_ac[j];
+			const int b = b0 + r0 + r;
+			const double s0 = __dsub_rn(__dadd_rn(ac.x, d[r].x), ac.y);                     // stocUpdate.c:174
+			const double s1 = __dsub_rn(__dadd_rn(ac.x, d[r].y), ac.y);
+			if (win == 1) {
+				if (s0 > oV0) { oV0 = s0; oI0 = b; }
+				if (s1 > oV1) { oV1 = s1; oI1 = b; }
+			}
+			else {
+				if (s0 > nV0) { nV0 = s0; nI0 = b; }
+				if (s1 > nV1) { nV1 = s1; nI1 = b; }
+			}
+		}
+	}
+	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
+	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
+	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
+	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
+	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
+	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
+}
+
 // General sweep: bases with phi columns (random cost, multi-term score) and/or the feasibility mask.
 //   arg = sum_t m_t * ((sigma.pib[s_t] + delta.pib[l_t][o]) - piCbarX[s_t]) - m_t * (delta.piC[l_t][o] . x)   stocUpdate.c:164-176
 struct SweepGenArgs {
@@ -263,6 +380,24 @@ struct MergeArgs {
 
 #define MG_THREADS SD_TILE_W
 
+// running (max, first index) over the per-chunk partial maxima of one observation, chunks in ascending basis order; the
+// loads of 8 chunks are issued together (the compare chain is sequential, the memory latency must not be)
+__device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int nChunks, int64_t NP,
+		double &bestV, int &bestI) {
+	int c = 0;
+	for (; c + 8 <= nChunks; c += 8) {
+		double v[8]; int ix[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) { v[u] = __ldcg(pv + (size_t) (c + u) * NP); ix[u] = __ldcg(pi + (size_t) (c + u) * NP); }
+#pragma unroll
+		for (int u = 0; u < 8; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
+	}
+	for (; c < nChunks; c++) {
+		double v = __ldcg(pv + (size_t) c * NP);
+		if (v > bestV) { bestV = v; bestI = __ldcg(pi + (size_t) c * NP); }
+	}
+}
+
 __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	__shared__ int s_istar[SD_TILE_W];
 	__shared__ int s_w[SD_TILE_W];
@@ -278,16 +413,10 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	int oldI = -1, newI = -1, istar = -1, wgt = 0;
 	double tAlpha = 0.0, tOld = 0.0, tAll = 0.0, tMiss = 0.0;
 	if (valid) {
-		for (int c = 0; c < a.nChunks; c++) {            // ascending chunks = ascending basis index: strict '>' keeps the first
-			double v = a.partV[((size_t) 0 * a.nChunks + c) * a.NP + o];
-			if (v > oldV) { oldV = v; oldI = a.partI[((size_t) 0 * a.nChunks + c) * a.NP + o]; }
-		}
+		sd_merge_chunks(a.partV + o, a.partI + o, a.nChunks, a.NP, oldV, oldI);
 		wgt = a.omegaW[o];
 		if (a.pi_eval) {
-			for (int c = 0; c < a.nChunks; c++) {
-				double v = a.partV[((size_t) 1 * a.nChunks + c) * a.NP + o];
-				if (v > newV) { newV = v; newI = a.partI[((size_t) 1 * a.nChunks + c) * a.NP + o]; }
-			}
+			sd_merge_chunks(a.partV + (size_t) a.nChunks * a.NP + o, a.partI + (size_t) a.nChunks * a.NP + o, a.nChunks, a.NP, newV, newI);
 			double argmax = fmax(oldV, newV);                     // cuts.c:124
 			istar = (newV > oldV) ? newI : oldI;                  // cuts.c:125 (an empty window carries index -1)
 			tOld = fmax(oldV - a.lb, 0.0) * wgt;                  // cuts.c:127
@@ -641,7 +770,14 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
 			a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
 			const bool hasMask = c->rvd > 0;
-			if (c->Q > 0 && hasMask) k_sweep_ldg<true, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
+			const bool useTma = c->sweepVariant == 2 && c->Q == 0 && !hasMask;
+			if (useTma) {
+				const size_t smem = (size_t) TMA_STAGES * TMA_ROWS * TMA_ROW_BYTES + 2 * TMA_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int));
+				static bool attrSet = false;
+				if (!attrSet) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attrSet = true; }
+				k_sweep_tma<<<grid, TMA_THREADS, smem, c->stream>>>(a);
+			}
+			else if (c->Q > 0 && hasMask) k_sweep_ldg<true, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else if (c->Q > 0)       k_sweep_ldg<true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else if (hasMask)        k_sweep_ldg<false, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else                     k_sweep_ldg<false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
