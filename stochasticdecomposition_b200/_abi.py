@@ -59,7 +59,7 @@ class CCut(C.Structure):
 
 class CStats(C.Structure):
     _fields_ = [("last_cut_ms", C.c_double), ("last_sweep_ms", C.c_double), ("last_cut_launches", C.c_int64),
-                ("total_launches", C.c_int64), ("last_sweep_bytes", C.c_int64)]
+                ("total_launches", C.c_int64), ("last_sweep_bytes", C.c_int64), ("last_sweep_variant", C.c_int64)]
 
 
 def _i32(a) -> np.ndarray:

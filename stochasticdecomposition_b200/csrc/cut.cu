@@ -20,6 +20,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 #include "sdgpu_internal.cuh"
@@ -195,10 +196,8 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a) {
 // (cp.async.bulk.shared::cluster.global, 4 KiB = one dual row of the observation tile each) into a ring of
 // shared-memory stages guarded by mbarriers; eight consumer warps read their 16 bytes per row with LDS.128 and
 // run the identical score / running-maximum code.  Bytes in flight are set by the ring (TMA_STAGES x TMA_ROWS x
-// 4 KiB = 128 KiB per SM), not by registers.  RHS-only bases without a feasibility mask (Q = 0, rvdOmCnt = 0).
+// 4 KiB per CTA), not by registers.  RHS-only bases without a feasibility mask (Q = 0, rvdOmCnt = 0).
 // ======================================================================================================
-#define TMA_ROWS 8
-#define TMA_STAGES 4
 #define TMA_CONSUMERS SD_SWEEP_THREADS
 #define TMA_THREADS (TMA_CONSUMERS + 32)
 #define TMA_ROW_BYTES (SD_TILE_W * 8)
@@ -225,7 +224,10 @@ __device__ __forceinline__ void sd_bulk_g2s(void *dst, const void *src, uint32_t
 			:: "r"(sd_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sd_smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(TMA_THREADS, 1) k_sweep_tma(SweepArgs a) {
+// <ROWS, STAGES, CTAS>: rows per stage, ring depth, resident CTAs per SM.  Default <8, 2, 3>: 64 KiB ring per CTA, three CTAs
+// per SM => 192 KiB of bulk copies in flight per SM and 24 consumer warps to hide the FP64 compare chains.
+template <int TMA_ROWS, int TMA_STAGES, int TMA_CTAS>
+__global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) k_sweep_tma(SweepArgs a) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double *ring = reinterpret_cast<double *>(smem_raw);                                   // [stage][row][512]
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t) TMA_STAGES * TMA_ROWS * TMA_ROW_BYTES);
@@ -740,6 +742,29 @@ static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks
 	*nChunks = (int) ((c->basisCnt + cs - 1) / cs);
 }
 
+template <int ROWS, int STAGES, int CTAS>
+static int sd_launch_tma_cfg(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
+	const size_t smem = (size_t) STAGES * ROWS * TMA_ROW_BYTES + 2 * STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int));
+	static bool attrSet = false;
+	if (!attrSet) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma<ROWS, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attrSet = true; }
+	k_sweep_tma<ROWS, STAGES, CTAS><<<grid, TMA_THREADS, smem, c->stream>>>(a);
+	return 0;
+}
+
+static int sd_launch_tma(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
+	static int cfg = -1;                      // SDGPU_TMA_CFG = experiment knob (tools/tma_check.py); unset = the measured best
+	if (cfg < 0) { const char *e = getenv("SDGPU_TMA_CFG"); cfg = e ? atoi(e) : 0; }
+	switch (cfg) {
+	// measured on B200, 65 536 x 131 072 (profiles/r01_tma_cfg_sweep.jsonl): <8,2,3> 6.87 TB/s, <8,3,2> 6.73, <4,4,3> 6.67,
+	// <4,3,4> 6.62, <8,4,1> 5.71; the LDG variant 6.4-6.5
+	case 1: return sd_launch_tma_cfg<8, 3, 2>(c, grid, a);
+	case 2: return sd_launch_tma_cfg<4, 4, 3>(c, grid, a);
+	case 3: return sd_launch_tma_cfg<8, 4, 1>(c, grid, a);
+	case 4: return sd_launch_tma_cfg<4, 3, 4>(c, grid, a);
+	default: return sd_launch_tma_cfg<8, 2, 3>(c, grid, a);
+	}
+}
+
 static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, bool fuseNormalise) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
 	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
@@ -761,6 +786,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
 		if (general) {
 			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
+			c->stats.last_sweep_variant = 3;
 		}
 		else {
 			SweepArgs a;
@@ -770,12 +796,12 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
 			a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
 			const bool hasMask = c->rvd > 0;
-			const bool useTma = c->sweepVariant == 2 && c->Q == 0 && !hasMask;
+			// variant 0 = automatic: the TMA ring wins from ~4M pairs up, the LDG kernel below that (tools/tma_check.py)
+			const bool tmaOk = c->Q == 0 && !hasMask;
+			const bool useTma = tmaOk && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N >= ((int64_t) 4 << 20)));
+			c->stats.last_sweep_variant = useTma ? 2 : 1;
 			if (useTma) {
-				const size_t smem = (size_t) TMA_STAGES * TMA_ROWS * TMA_ROW_BYTES + 2 * TMA_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int));
-				static bool attrSet = false;
-				if (!attrSet) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attrSet = true; }
-				k_sweep_tma<<<grid, TMA_THREADS, smem, c->stream>>>(a);
+				if (sd_launch_tma(c, grid, a)) return SDGPU_ERR;
 			}
 			else if (c->Q > 0 && hasMask) k_sweep_ldg<true, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else if (c->Q > 0)       k_sweep_ldg<true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);

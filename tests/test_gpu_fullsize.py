@@ -34,8 +34,9 @@ def _sigma_host(t, D, n1c):
     return pib, piC, lam
 
 
-def _check(D, N, rv, n1, nsample, pi_eval=1, lb=0.0):
+def _check(D, N, rv, n1, nsample, pi_eval=1, lb=0.0, variant=0):
     prob, pis, obsv, weights, xs, k, iters, t = _load(D, N, rv, n1)
+    t.set_sweep_variant(variant)
     x = xs[0]
     cut = t.sd_cut(x, k, pi_eval, lb)
     again = t.sd_cut(x, k, pi_eval, lb)
@@ -95,8 +96,9 @@ def _check(D, N, rv, n1, nsample, pi_eval=1, lb=0.0):
     t.close()
 
 
-def test_mid_size_multi_wave():
-    _check(D=8192, N=65536, rv=64, n1=40, nsample=48)
+@pytest.mark.parametrize("variant", [1, 2])
+def test_mid_size_multi_wave(variant):
+    _check(D=8192, N=65536, rv=64, n1=40, nsample=48, variant=variant)
 
 
 def test_mid_size_no_pi_eval_nonzero_lb():

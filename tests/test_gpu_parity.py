@@ -51,8 +51,9 @@ def _bulk_tables(api, prob, pis, mub, iters, obs, weights, caps, tol=-1.0):
     return t, li, si
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("D,N,Q", [(700, 1500, 0), (300, 1100, 3), (2100, 600, 0)])
-def test_bulk_multi_tile_multi_chunk(D, N, Q):
+def test_bulk_multi_tile_multi_chunk(D, N, Q, variant):
     """Several observation tiles and several basis chunks; ties forced by duplicated duals (lowest index must
     win) and all-zero observations; both pi_eval modes; weights > 1."""
     prob = make_problem(9, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=Q)
@@ -71,6 +72,7 @@ def test_bulk_multi_tile_multi_chunk(D, N, Q):
     to, lo, so = _bulk_tables(oracle_loader.oracle(), prob, pis, mub, iters, obs, weights, caps)
     tg, lg, sg = _bulk_tables(sd.load_library(), prob, pis, mub, iters, obs, weights, caps)
     assert np.array_equal(lo, lg) and np.array_equal(so, sg)
+    tg.set_sweep_variant(variant)           # 1 = LDG streaming, 2 = TMA bulk ring (falls back to LDG when Q > 0)
     for plane in range(Q + 1):
         a = to.get_delta_block(0, D, 0, N, plane); b = tg.get_delta_block(0, D, 0, N, plane)
         assert np.array_equal(a.view(np.int64), b.view(np.int64)), f"delta plane {plane} differs"

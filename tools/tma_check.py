@@ -33,5 +33,9 @@ def run(D, N, rv=64, n1=40, reps=10):
     return out
 
 if __name__ == "__main__":
-    for D, N in ((100, 700), (3000, 5000), (8192, 65536), (65536, 131072)):
-        print(json.dumps(run(D, N)), flush=True)
+    import os
+    shapes = [(int(a), int(b)) for a, b in (x.split("x") for x in sys.argv[1:])] or [(100, 700), (3000, 5000), (8192, 65536), (65536, 131072)]
+    for D, N in shapes:
+        r = run(D, N)
+        r["cfg"] = os.environ.get("SDGPU_TMA_CFG", "0")
+        print(json.dumps(r), flush=True)
