@@ -156,6 +156,27 @@ int  sdgpu_basis_set_obs_feasible(sdgpu_ctx *ctx, int basisIdx, int obsIdx, int 
 int  sdgpu_basis_set_obs_feasible_row(sdgpu_ctx *ctx, int basisIdx, const uint8_t *flags /* [omegaCnt] */);
 int  sdgpu_basis_set_obs_feasible_col(sdgpu_ctx *ctx, int obsIdx, const uint8_t *flags /* [basisCnt] */);
 
+/* ---- basis feasibility under random costs: checkBasisFeasibility randCost.c:202-258 on the device -------------
+ * The host still extracts piDet / phi / gBar / psi / cstat from the CPLEX basis (randCost.c:19-180); it hands them over
+ * once per new basis and the library evaluates the basis x observation mask itself, for a new observation against
+ * all stored bases (stocUpdate.c:28-30) and for a new basis against all stored observations (stocUpdate.c:123-126). */
+int  sdgpu_set_cost_coords(sdgpu_ctx *ctx, const int32_t *rvdOmCols /* [rvdOmCnt+1], 1-based */, const char *senx /* [rows] */);
+/* phi: phiLength vectors of rows+1 doubles back to back; psiVal: psi->val in the order calcBasis writes it
+ * (randCost.c:83-88), i.e. [cols][phiLength] row-major, 0-based; gBar [cols+1]; cstat [cols+1] (AT_UPPER == 2). */
+int  sdgpu_basis_set_feas_data(sdgpu_ctx *ctx, int basisIdx, const double *piDet, const double *phi, const double *gBar,
+                               const double *psiVal, const int32_t *cstat);
+/* flagsOut (may be NULL) receives the computed flags; the device mask and the library's host mirror are updated. */
+int  sdgpu_check_feasibility_obs(sdgpu_ctx *ctx, int obsIdx, double tol, uint8_t *flagsOut /* [basisCnt] */);
+int  sdgpu_check_feasibility_basis(sdgpu_ctx *ctx, int basisIdx, double tol, uint8_t *flagsOut /* [omegaCnt] */);
+
+/* ---- feasibility cuts: the numeric core of updtFeasCutPool cuts.c:465-517 ------------------------------------------
+ * For every observation in [obsFirst, obsLast) (outer loop) and every INFEASIBLE basis in [basisFirst, basisLast)
+ * (inner loop, feasFlag == 0) one raw cut: alpha = sigma.pib + delta.pib, beta[CCols] += sigma.piC, beta[rvCols] +=
+ * delta.piC of the basis' first sigma (cuts.c:478-486).  Returns the number of cuts written (<= maxOut) in that loop
+ * order; the pool de-duplication of addCut2Pool (cuts.c:643-655) stays with the host. */
+int  sdgpu_feas_cuts(sdgpu_ctx *ctx, int obsFirst, int obsLast, int basisFirst, int basisLast, int maxOut,
+                     double *alpha /* [maxOut] */, double *beta /* [maxOut][prevCols+1] */);
+
 /* ---- cut formation (cuts.c, stocUpdate.c:142-190) ------------------------------------------------- */
 /* computeIstar stocUpdate.c:142-190 for ONE observation (debug / STOCH_CHECK use; the cut path below
  * never calls it).  Returns the basis index or SDGPU_NONE; *argmax as the reference sets it. */
@@ -198,6 +219,12 @@ int  sdgpu_cut_heights(sdgpu_ctx *ctx, int n, const double *alpha, const double 
  * recent sdgpu_sd_cut().  lb is truncated to int as optimal.c:188 does. */
 int  sdgpu_reform_cut(sdgpu_ctx *ctx, const int32_t *iStar, int omegaCnt, const int32_t *observ, int k,
                       int lbType, int lb, double *alpha, double *beta /* [prevCols+1] */);
+
+/* The bootstrap of fullTest (optimal.c:96-103) in one call: nCuts cuts (iStar rows of istarStride ints, omegaCnt[i] valid
+ * entries each) x nReps resampled observation lists (observ = nReps rows of k).  Outputs alpha[nReps][nCuts] and
+ * beta[nReps][nCuts][prevCols+1]. */
+int  sdgpu_reform_cuts_batch(sdgpu_ctx *ctx, int nCuts, const int32_t *iStar, int istarStride, const int32_t *omegaCnt,
+                             int nReps, const int32_t *observ, int k, int lbType, int lb, double *alpha, double *beta);
 
 /* ---- readers for the host code that still walks the tables (optimal.c:203-221, cuts.c:472-513) ---- */
 int  sdgpu_get_omega(sdgpu_ctx *ctx, int idx, double *vals /* [numRV+1] */, int *weight);

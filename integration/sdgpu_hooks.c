@@ -233,6 +233,67 @@ double maxCutHeight_gpu(sdgpu_ctx *gpu, cutsType *cuts, int currIter, dVector xk
 	return Sm;
 }//END maxCutHeight_gpu()
 
+/* ---- cuts.c:465-517: feasibility-cut pool update; the gathers run on the device, the pool de-duplication
+ * (addCut2Pool, cuts.c:643-655) stays here ---------------------------------------------------------------------- */
+int addCut2Pool(cellType *cell, oneCut *cut, int lenX, double lb, typeOfCut type);     /* cuts.c:616 */
+
+static int feasCutsFromDevice(numType *num, cellType *cell, sdgpu_ctx *gpu, int obsFirst, int obsLast, int basisFirst, int basisLast) {
+	int n, cnt, c, maxOut = (obsLast - obsFirst) * (basisLast - basisFirst);
+	dVector alpha, beta;
+	oneCut *cut;
+
+	if ( maxOut <= 0 )
+		return 0;
+	alpha = (dVector) arr_alloc(maxOut, double); beta = (dVector) arr_alloc(maxOut*(num->prevCols+1), double);
+	n = sdgpu_feas_cuts(gpu, obsFirst, obsLast, basisFirst, basisLast, maxOut, alpha, beta);
+	for ( cnt = 0; cnt < n; cnt++ ) {
+		cut = newCut(num->prevCols, 0, 1);
+		cut->alpha = alpha[cnt];
+		for ( c = 0; c <= num->prevCols; c++ )
+			cut->beta[c] = beta[cnt*(num->prevCols+1)+c];
+		addCut2Pool(cell, cut, num->prevCols, 0.0, FEASIBILITY);
+	}
+	mem_free(alpha); mem_free(beta);
+	return n < 0 ? -1 : 0;
+}
+
+int updtFeasCutPool_gpu(numType *num, cellType *cell, sdgpu_ctx *gpu) {
+	int initCutsCnt = cell->fcutsPool->cnt;
+
+	feasCutsFromDevice(num, cell, gpu, cell->fUpdt[1], cell->omega->cnt, 0, cell->fUpdt[0]);        /* cuts.c:472-490 */
+	cell->fUpdt[1] = cell->omega->cnt;
+	feasCutsFromDevice(num, cell, gpu, 0, cell->omega->cnt, cell->fUpdt[0], cell->basis->cnt);      /* cuts.c:494-512 */
+	cell->fUpdt[0] = cell->basis->cnt;
+	return (cell->fcutsPool->cnt - initCutsCnt);
+}//END updtFeasCutPool_gpu()
+
+/* ---- randCost.c:202-258 on the device: hand a new basis' CPLEX-derived vectors over once (after calcBasis /
+ * decomposeDualSolution), then let the library evaluate obsFeasible for it --------------------------------------- */
+int basisFeasibility_gpu(probType *prob, sdgpu_ctx *gpu, oneBasis *B, int basisIdx, iVector cstat, double TOLERANCE) {
+	dVector phi = NULL, psiVal = NULL;
+	int n, i;
+
+	if ( prob->num->rvdOmCnt == 0 )
+		return 0;
+	if ( B->phiLength > 0 ) {
+		phi = (dVector) arr_alloc(B->phiLength*(prob->num->rows+1), double);
+		for ( n = 0; n < B->phiLength; n++ )
+			for ( i = 0; i <= prob->num->rows; i++ )
+				phi[n*(prob->num->rows+1)+i] = B->phi[n][i];
+		psiVal = (dVector) arr_alloc(B->psi->cnt+1, double);
+		for ( i = 1; i <= B->psi->cnt; i++ )
+			psiVal[i-1] = B->psi->val[i];                                 /* entry order of randCost.c:83-88 */
+	}
+	if ( sdgpu_basis_set_feas_data(gpu, basisIdx, B->piDet, phi, B->gBar, psiVal, cstat) ||
+			sdgpu_check_feasibility_basis(gpu, basisIdx, TOLERANCE, NULL) ) {
+		errMsg("algorithm", "basisFeasibility_gpu", sdgpu_last_error(), 0);
+		return 1;
+	}
+	if ( phi ) mem_free(phi);
+	if ( psiVal ) mem_free(psiVal);
+	return 0;
+}//END basisFeasibility_gpu()
+
 /* ---- setup.c:242-246 and :282-286 ---------------------------------------------------------------------------- */
 void cleanGpuTables(sdgpu_ctx *gpu) { sdgpu_reset(gpu); }
 void freeGpuTables(sdgpu_ctx *gpu)  { sdgpu_destroy(gpu); }

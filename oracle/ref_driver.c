@@ -26,6 +26,8 @@ typedef struct {
 	sparseVector bBar;
 	sparseMatrix Cbar;
 	sdgpu_caps   caps;
+	iVector      rvdOmCols; char *senx;
+	cellType    *cell;          /* only the fields updtFeasCutPool / addCut2Pool(FEASIBILITY) read */
 	lambdaType  *lambda;
 	sigmaType   *sigma;
 	deltaType   *delta;
@@ -272,6 +274,96 @@ int sdref_basis_set_obs_feasible_col(void *vc, int obsIdx, const uint8_t *flags)
 	return 0;
 }
 
+/* checkBasisFeasibility randCost.c:202-258: fill the oneBasis fields calcBasis / decomposeDualSolution would have set */
+int sdref_set_cost_coords(void *vc, const int32_t *rvdOmCols, const char *senx) {
+	refCtx *c = (refCtx *) vc;
+	c->rvdOmCols = dupInts(rvdOmCols, c->num.rvdOmCnt);
+	c->senx = (char *) malloc(c->num.rows + 1);
+	memcpy(c->senx, senx, c->num.rows);
+	return 0;
+}
+
+int sdref_basis_set_feas_data(void *vc, int b, const double *piDet, const double *phi, const double *gBar, const double *psiVal,
+		const int32_t *cstat) {
+	refCtx *c = (refCtx *) vc;
+	oneBasis *B = c->basis->vals[b];
+	int rows = c->num.rows, cols = c->num.cols, i, j, n;
+	iVector cs = dupInts(cstat, cols);
+	B->piDet = dupDbls(piDet, rows);
+	B->gBar = dupDbls(gBar, cols);
+	B->cCode = encodeIntvec(cs, cols, WORDLENGTH, 3);                      /* randCost.c:171 */
+	mem_free(cs);
+	if (B->phiLength > 0) {
+		B->phi = (dVector *) arr_alloc(B->phiLength, dVector);
+		for (n = 0; n < B->phiLength; n++) B->phi[n] = dupDbls(phi + (size_t) n * (rows + 1), rows);
+		B->psi = (sparseMatrix *) mem_malloc(sizeof(sparseMatrix));         /* randCost.c:56-61,83-88 */
+		B->psi->val = (dVector) arr_alloc(cols * B->phiLength + 1, double);
+		B->psi->col = (iVector) arr_alloc(cols * B->phiLength + 1, int);
+		B->psi->row = (iVector) arr_alloc(cols * B->phiLength + 1, int);
+		B->psi->cnt = 0;
+		for (i = 1; i <= cols; i++)
+			for (j = 1; j <= B->phiLength; j++) {
+				B->psi->row[B->psi->cnt + 1] = i;
+				B->psi->col[B->psi->cnt + 1] = B->omegaIdx[j];
+				B->psi->val[B->psi->cnt + 1] = psiVal[(size_t) (i - 1) * B->phiLength + (j - 1)];
+				B->psi->cnt++;
+			}
+	}
+	return 0;
+}
+
+static bool refPairFeasible(refCtx *c, int b, int obs, double tol) {
+	sparseVector dOmega;
+	dOmega.cnt = c->num.rvdOmCnt; dOmega.col = c->rvdOmCols;
+	dOmega.val = c->coord.rvOffset[2] + c->omega->vals[obs];                /* stocUpdate.c:28 */
+	return checkBasisFeasibility(c->basis->vals[b], dOmega, c->senx, c->num.cols, c->num.rows, tol);
+}
+
+int sdref_check_feasibility_obs(void *vc, int obsIdx, double tol, uint8_t *flagsOut) {
+	refCtx *c = (refCtx *) vc;
+	int b;
+	for (b = 0; b < c->basis->cnt; b++) {
+		if (c->basis->obsFeasible[b] && c->basis->vals[b]->piDet) c->basis->obsFeasible[b][obsIdx] = refPairFeasible(c, b, obsIdx, tol);
+		if (flagsOut) flagsOut[b] = c->basis->obsFeasible[b] ? c->basis->obsFeasible[b][obsIdx] : 0;
+	}
+	return 0;
+}
+
+int sdref_check_feasibility_basis(void *vc, int b, double tol, uint8_t *flagsOut) {
+	refCtx *c = (refCtx *) vc;
+	int o;
+	if (b < 0 || b >= c->basis->cnt || !c->basis->obsFeasible[b] || !c->basis->vals[b]->piDet) return SDGPU_ERR;
+	for (o = 0; o < c->omega->cnt; o++) {
+		c->basis->obsFeasible[b][o] = refPairFeasible(c, b, o, tol);
+		if (flagsOut) flagsOut[o] = c->basis->obsFeasible[b][o];
+	}
+	return 0;
+}
+
+int updtFeasCutPool(numType *num, coordType *coord, cellType *cell);      /* cuts.c:465 (file-local prototype in cuts.c:18) */
+
+/* The reference's own updtFeasCutPool (cuts.c:465-517) including the pool de-duplication of addCut2Pool (cuts.c:643-655).
+ * fUpdt is cell->fUpdt (in/out); the whole pool is exported after the call.  Returns the pool size. */
+int sdref_updt_feas_cut_pool(void *vc, int *fUpdt, double tol, int maxOut, double *alpha, double *beta) {
+	refCtx *c = (refCtx *) vc;
+	int i, j, n1 = c->num.prevCols;
+	if (!c->cell) {
+		c->cell = (cellType *) calloc(1, sizeof(cellType));
+		c->cell->fcutsPool = newCuts(4096);
+	}
+	c->cell->omega = c->omega; c->cell->basis = c->basis; c->cell->sigma = c->sigma; c->cell->delta = c->delta;
+	c->cell->fUpdt[0] = fUpdt[0]; c->cell->fUpdt[1] = fUpdt[1];
+	config.TOLERANCE = tol;
+	updtFeasCutPool(&c->num, &c->coord, c->cell);
+	fUpdt[0] = c->cell->fUpdt[0]; fUpdt[1] = c->cell->fUpdt[1];
+	if (c->cell->fcutsPool->cnt > maxOut) return SDGPU_ERR;
+	for (i = 0; i < c->cell->fcutsPool->cnt; i++) {
+		alpha[i] = c->cell->fcutsPool->vals[i]->alpha;
+		for (j = 0; j <= n1; j++) beta[(size_t) i * (n1 + 1) + j] = c->cell->fcutsPool->vals[i]->beta[j];
+	}
+	return c->cell->fcutsPool->cnt;
+}
+
 int sdref_compute_istar(void *vc, const double *Xvect, int obs, int numSamples, int pi_eval, int isNew, double *argmax) {
 	refCtx *c = (refCtx *) vc;
 	dVector piCbarX = arr_alloc(c->sigma->cnt + 1, double);
@@ -360,6 +452,28 @@ int sdref_reform_cut(void *vc, const int32_t *iStar, int omegaCnt, const int32_t
 	reformCuts(c->basis, c->sigma, c->delta, c->omega, &c->num, &c->coord, g, (int *) observ, k, lbType, lb, c->num.prevCols);
 	*alpha = g->vals[0]->alpha;
 	for (i = 0; i <= c->num.prevCols; i++) beta[i] = g->vals[0]->beta[i];
+	freeCutsType(g, false);
+	return 0;
+}
+
+/* the bootstrap loop of fullTest (optimal.c:96-103): reformCuts over all cuts at once, once per replication */
+int sdref_reform_cuts_batch(void *vc, int nCuts, const int32_t *iStar, int istarStride, const int32_t *omegaCnt,
+		int nReps, const int32_t *observ, int k, int lbType, int lb, double *alpha, double *beta) {
+	refCtx *c = (refCtx *) vc;
+	cutsType *g = newCuts(nCuts);
+	int i, j, r, n1 = c->num.prevCols;
+	for (i = 0; i < nCuts; i++) {
+		g->vals[i] = newCut(n1, omegaCnt[i], k);
+		for (j = 0; j < omegaCnt[i]; j++) g->vals[i]->iStar[j] = iStar[(size_t) i * istarStride + j];
+		g->cnt++;
+	}
+	for (r = 0; r < nReps; r++) {
+		reformCuts(c->basis, c->sigma, c->delta, c->omega, &c->num, &c->coord, g, (int *) (observ + (size_t) r * k), k, lbType, lb, n1);
+		for (i = 0; i < nCuts; i++) {
+			alpha[(size_t) r * nCuts + i] = g->vals[i]->alpha;
+			for (j = 0; j <= n1; j++) beta[((size_t) r * nCuts + i) * (n1 + 1) + j] = g->vals[i]->beta[j];
+		}
+	}
 	freeCutsType(g, false);
 	return 0;
 }

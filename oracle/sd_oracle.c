@@ -52,6 +52,9 @@ typedef struct {
 	int64_t  basisCnt;  int32_t *bCk, *bFeas, *bPhiLen, *bWeight;  int64_t *bTermStart;
 	int64_t  termCnt, termCap;  int32_t *tSigma, *tOmega;
 	uint8_t **obsFeasible;                                           /* [b] -> [maxOmega] or NULL */
+	/* checkBasisFeasibility inputs (randCost.c:202-258): per basis piDet, phi, gBar, psi values, cstat */
+	int32_t *rvdOmCols; char *senx;
+	double **fPiDet, **fPhi, **fGBar, **fPsi; int32_t **fCstat;
 } oracleCtx;
 
 static char g_err[512];
@@ -109,6 +112,9 @@ int sdo_create(const sdgpu_problem *p, const sdgpu_caps *caps, int device, oracl
 	c->tSigma = (int32_t *) calloc((size_t) c->termCap, sizeof(int32_t));
 	c->tOmega = (int32_t *) calloc((size_t) c->termCap, sizeof(int32_t));
 	c->obsFeasible = (uint8_t **) calloc((size_t) caps->maxBasis, sizeof(uint8_t *));
+	c->fPiDet = (double **) calloc((size_t) caps->maxBasis, sizeof(double *)); c->fPhi = (double **) calloc((size_t) caps->maxBasis, sizeof(double *));
+	c->fGBar = (double **) calloc((size_t) caps->maxBasis, sizeof(double *)); c->fPsi = (double **) calloc((size_t) caps->maxBasis, sizeof(double *));
+	c->fCstat = (int32_t **) calloc((size_t) caps->maxBasis, sizeof(int32_t *));
 	*out = c;
 	return 0;
 }
@@ -119,7 +125,11 @@ int sdo_reset(oracleCtx *c) {
 		free(c->deltaPib[l]); c->deltaPib[l] = NULL;
 		free(c->deltaPiC[l]); c->deltaPiC[l] = NULL;
 	}
-	for (int64_t b = 0; b < c->basisCnt; b++) { free(c->obsFeasible[b]); c->obsFeasible[b] = NULL; }
+	for (int64_t b = 0; b < c->basisCnt; b++) {
+		free(c->obsFeasible[b]); c->obsFeasible[b] = NULL;
+		free(c->fPiDet[b]); free(c->fPhi[b]); free(c->fGBar[b]); free(c->fPsi[b]); free(c->fCstat[b]);
+		c->fPiDet[b] = c->fPhi[b] = c->fGBar[b] = c->fPsi[b] = NULL; c->fCstat[b] = NULL;
+	}
 	c->omegaCnt = c->lambdaCnt = c->sigmaCnt = c->basisCnt = c->termCnt = 0;
 	return 0;
 }
@@ -422,6 +432,87 @@ int sdo_basis_set_obs_feasible_col(oracleCtx *c, int obsIdx, const uint8_t *flag
 	return 0;
 }
 
+/* ---- checkBasisFeasibility randCost.c:202-258 ---------------------------------------------------------------- */
+int sdo_set_cost_coords(oracleCtx *c, const int32_t *rvdOmCols, const char *senx) {
+	free(c->rvdOmCols); free(c->senx);
+	c->rvdOmCols = copyI(rvdOmCols, c->num.rvdOmCnt);
+	c->senx = (char *) malloc((size_t) c->num.rows);
+	memcpy(c->senx, senx, (size_t) c->num.rows);
+	return 0;
+}
+
+int sdo_basis_set_feas_data(oracleCtx *c, int b, const double *piDet, const double *phi, const double *gBar, const double *psiVal,
+		const int32_t *cstat) {
+	if (b < 0 || b >= c->basisCnt) return fail("basis_set_feas_data: bad basis");
+	int rows = c->num.rows, cols = c->num.cols, pl = c->bPhiLen[b];
+	free(c->fPiDet[b]); free(c->fPhi[b]); free(c->fGBar[b]); free(c->fPsi[b]); free(c->fCstat[b]);
+	c->fPiDet[b] = copyD(piDet, rows); c->fGBar[b] = copyD(gBar, cols); c->fCstat[b] = copyI(cstat, cols);
+	c->fPhi[b] = (double *) malloc(((size_t) pl * (rows + 1) + 1) * sizeof(double));
+	c->fPsi[b] = (double *) malloc(((size_t) pl * cols + 1) * sizeof(double));
+	if (pl) { memcpy(c->fPhi[b], phi, (size_t) pl * (rows + 1) * sizeof(double)); memcpy(c->fPsi[b], psiVal, (size_t) pl * cols * sizeof(double)); }
+	return 0;
+}
+
+static int pairFeasible(oracleCtx *c, int b, int64_t obs, double tol) {
+	int rows = c->num.rows, cols = c->num.cols, rvd = c->num.rvdOmCnt, pl = c->bPhiLen[b];
+	const double *val = omegaRow(c, obs) + c->rvOffset[2];               /* dOmega.val, 1-based (stocUpdate.c:28) */
+	if (rvd == 0) return 1;                                              /* randCost.c:208 */
+	if (pl > 0) {                                                        /* :213-224 */
+		for (int r = 1; r <= rows; r++) {
+			double theta = 0.0;
+			for (int n = 0; n < pl; n++) theta += c->fPhi[b][(size_t) n * (rows + 1) + r] * val[c->tOmega[c->bTermStart[b] + 1 + n]];
+			double v = c->fPiDet[b][r] + theta;
+			if ((v < -tol && c->senx[r - 1] == 'G') || (v > tol && c->senx[r - 1] == 'L')) return 0;
+		}
+	}
+	double *rc = copyD(c->fGBar[b], cols);                               /* copyVector :239 */
+	for (int j = 1; j <= rvd; j++) rc[c->rvdOmCols[j]] += val[j];        /* addVectors :240 */
+	for (int i = 1; i <= cols; i++)                                      /* MSparsexvSub :242, entry order (i, j) */
+		for (int n = 0; n < pl; n++) rc[i] -= c->fPsi[b][(size_t) (i - 1) * pl + n] * val[c->tOmega[c->bTermStart[b] + 1 + n]];
+	int ok = 1;
+	for (int i = 1; i <= cols; i++)                                      /* :246-252, AT_UPPER == 2 */
+		if (rc[i] < -tol && c->fCstat[b][i] != 2) { ok = 0; break; }
+	free(rc);
+	return ok;
+}
+
+int sdo_check_feasibility_obs(oracleCtx *c, int obsIdx, double tol, uint8_t *flagsOut) {
+	if (obsIdx < 0 || obsIdx >= c->omegaCnt) return fail("check_feasibility_obs: bad observation");
+	for (int64_t b = 0; b < c->basisCnt; b++) {
+		if (c->obsFeasible[b] && c->fPiDet[b]) c->obsFeasible[b][obsIdx] = (uint8_t) pairFeasible(c, (int) b, obsIdx, tol);   /* stocUpdate.c:29-30 */
+		if (flagsOut) flagsOut[b] = c->obsFeasible[b] ? c->obsFeasible[b][obsIdx] : 0;
+	}
+	return 0;
+}
+
+int sdo_check_feasibility_basis(oracleCtx *c, int b, double tol, uint8_t *flagsOut) {
+	if (b < 0 || b >= c->basisCnt || !c->obsFeasible[b] || !c->fPiDet[b]) return fail("check_feasibility_basis: bad basis");
+	for (int64_t o = 0; o < c->omegaCnt; o++) {                           /* stocUpdate.c:123-126 */
+		c->obsFeasible[b][o] = (uint8_t) pairFeasible(c, b, o, tol);
+		if (flagsOut) flagsOut[o] = c->obsFeasible[b][o];
+	}
+	return 0;
+}
+
+/* ---- raw feasibility cuts: the body of updtFeasCutPool cuts.c:473-490 ------------------------------------------------ */
+int sdo_feas_cuts(oracleCtx *c, int obsFirst, int obsLast, int basisFirst, int basisLast, int maxOut, double *alpha, double *beta) {
+	int n = 0, n1 = c->num.prevCols, n1c = c->num.cntCcols, Q = c->num.rvCOmCnt;
+	if (obsFirst < 0 || obsLast > c->omegaCnt || basisFirst < 0 || basisLast > c->basisCnt) return fail("feas_cuts: range out of bounds");
+	for (int o = obsFirst; o < obsLast; o++)
+		for (int b = basisFirst; b < basisLast; b++) {
+			if (c->bFeas[b]) continue;
+			if (n >= maxOut) return fail("feas_cuts: output buffer too small");
+			int s = c->tSigma[c->bTermStart[b]], l = c->sigmaLambda[s];
+			double *bt = beta + (size_t) n * (n1 + 1);
+			for (int i = 0; i <= n1; i++) bt[i] = 0.0;
+			alpha[n] = c->sigmaPib[s] + c->deltaPib[l][o];                                   /* cuts.c:481 */
+			for (int k = 1; k <= n1c; k++) bt[c->CCols[k]] += sigmaPiCRow(c, s)[k];           /* :483-484 */
+			for (int k = 1; k <= Q; k++) bt[c->rvCols[k]] += c->deltaPiC[l][(size_t) o * (Q + 1) + k];   /* :485-486 */
+			n++;
+		}
+	return n;
+}
+
 /* ---- argmax: computeIstar stocUpdate.c:142-190 ---------------------------------------------------------- */
 static void piCbarXAll(oracleCtx *c, const double *X, double *out) {                        /* cuts.c:105-106 */
 	for (int64_t s = 0; s < c->sigmaCnt; s++) out[s] = dotIdx(sigmaPiCRow(c, s), X, c->CCols, c->num.cntCcols);
@@ -668,6 +759,18 @@ int sdo_reform_cut(oracleCtx *c, const int32_t *iStar, int omegaCnt, const int32
 	alpha /= (double) k;                                                                     /* :232 */
 	if (lbType == 1) alpha += (1 - (double) count / (double) k) * lb;                       /* :234-235, NONTRIVIAL == 1 */
 	*alphaOut = alpha;
+	return 0;
+}
+
+int sdo_reform_cuts_batch(oracleCtx *c, int nCuts, const int32_t *iStar, int istarStride, const int32_t *omegaCnt,
+		int nReps, const int32_t *observ, int k, int lbType, int lb, double *alpha, double *beta) {
+	int n1 = c->num.prevCols;
+	for (int r = 0; r < nReps; r++)
+		for (int i = 0; i < nCuts; i++) {
+			int st = sdo_reform_cut(c, iStar + (size_t) i * istarStride, omegaCnt[i], observ + (size_t) r * k, k, lbType, lb,
+					alpha + (size_t) r * nCuts + i, beta + ((size_t) r * nCuts + i) * (n1 + 1));
+			if (st < 0) return st;
+		}
 	return 0;
 }
 

@@ -198,6 +198,11 @@ class Api:
             "basis_find_or_append": (i, [vp, i, i, i, i, i, c_i32p, c_i32p, c_intp]),
             "basis_set_obs_feasible": (i, [vp, i, i, i]),
             "basis_set_obs_feasible_row": (i, [vp, i, c_u8p]), "basis_set_obs_feasible_col": (i, [vp, i, c_u8p]),
+            "set_cost_coords": (i, [vp, c_i32p, C.c_char_p]),
+            "basis_set_feas_data": (i, [vp, i, c_f64p, c_f64p, c_f64p, c_f64p, c_i32p]),
+            "check_feasibility_obs": (i, [vp, i, d, c_u8p]), "check_feasibility_basis": (i, [vp, i, d, c_u8p]),
+            "feas_cuts": (i, [vp, i, i, i, i, i, c_f64p, c_f64p]),
+            "updt_feas_cut_pool": (i, [vp, c_intp, d, i, c_f64p, c_f64p]),
             "compute_istar": (i, [vp, c_f64p, i, i, i, i, c_f64p]),
             "sd_cut": (i, [vp, c_f64p, i, i, d, C.POINTER(CCut)]),
             "sd_cut_omp": (i, [vp, c_f64p, i, i, d, C.POINTER(CCut), c_intp]),
@@ -211,6 +216,7 @@ class Api:
             "attach_nccl": (i, [vp, vp]), "nccl_unique_id": (i, [vp]), "nccl_init": (i, [vp, i, i, vp]),
             "cut_heights": (i, [vp, i, c_f64p, c_f64p, c_i32p, c_f64p, i, c_f64p, d, c_f64p, c_f64p, c_f64p]),
             "reform_cut": (i, [vp, c_i32p, i, c_i32p, i, i, i, c_f64p, c_f64p]),
+            "reform_cuts_batch": (i, [vp, i, c_i32p, i, c_i32p, i, c_i32p, i, i, i, c_f64p, c_f64p]),
             "get_omega": (i, [vp, i, c_f64p, c_intp]), "get_lambda": (i, [vp, i, c_f64p]),
             "get_sigma": (i, [vp, i, c_f64p, c_f64p, c_intp, c_intp]), "get_delta": (i, [vp, i, i, c_f64p, c_f64p]),
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
@@ -366,6 +372,33 @@ class Tables:
         f = np.ascontiguousarray(flags, dtype=np.uint8)
         self._check(self._call("basis_set_obs_feasible_col", obsIdx, f.ctypes.data_as(c_u8p)), "basis_set_obs_feasible_col")
 
+    # -- checkBasisFeasibility (randCost.c:202-258) ---------------------------------------------------------
+    def set_cost_coords(self, rvdOmCols, senx: bytes):
+        r = _i32(rvdOmCols)
+        self._check(self._call("set_cost_coords", _pi32(r), senx), "set_cost_coords")
+
+    def basis_set_feas_data(self, basisIdx, piDet, phi, gBar, psiVal, cstat):
+        p, g, cs = _f64(piDet), _f64(gBar), _i32(cstat)
+        ph = None if phi is None or len(phi) == 0 else _f64(phi)
+        ps = None if psiVal is None or len(psiVal) == 0 else _f64(psiVal)
+        self._check(self._call("basis_set_feas_data", basisIdx, _pf64(p), _pf64(ph), _pf64(g), _pf64(ps), _pi32(cs)), "basis_set_feas_data")
+
+    def check_feasibility_obs(self, obsIdx, tol):
+        f = np.zeros(max(1, self.counts()["basis"]), np.uint8)
+        self._check(self._call("check_feasibility_obs", obsIdx, tol, f.ctypes.data_as(c_u8p)), "check_feasibility_obs")
+        return f[:self.counts()["basis"]]
+
+    def check_feasibility_basis(self, basisIdx, tol):
+        f = np.zeros(max(1, self.counts()["omega"]), np.uint8)
+        self._check(self._call("check_feasibility_basis", basisIdx, tol, f.ctypes.data_as(c_u8p)), "check_feasibility_basis")
+        return f[:self.counts()["omega"]]
+
+    def feas_cuts(self, obsFirst, obsLast, basisFirst, basisLast, maxOut=4096):
+        """raw feasibility cuts (cuts.c:473-490 loop body) in the reference's loop order"""
+        alpha, beta = np.zeros(maxOut), np.zeros((maxOut, self.problem.prevCols + 1))
+        n = self._check(self._call("feas_cuts", obsFirst, obsLast, basisFirst, basisLast, maxOut, _pf64(alpha), _pf64(beta)), "feas_cuts")
+        return alpha[:n], beta[:n]
+
     # -- cut formation ----------------------------------------------------------------------------------
     def compute_istar(self, X, obs, numSamples, pi_eval, isNew):
         x, am = _f64(X), C.c_double(0.0)
@@ -433,6 +466,22 @@ class Tables:
         self._check(self._call("reform_cut", _pi32(ist), n, _pi32(ob), k, lbType, int(lb), C.byref(alpha), _pf64(beta)),
                     "reform_cut")
         return alpha.value, beta
+
+    def reform_cuts_batch(self, iStars, observ, lbType, lb):
+        """iStars: list of int32 arrays (one per cut); observ: [nReps][k].  Returns alpha[nReps][nCuts], beta[nReps][nCuts][n1+1]."""
+        ob = _i32(observ)
+        nReps, k = ob.shape
+        nCuts = len(iStars)
+        oc = _i32([len(x) for x in iStars])
+        stride = int(max(1, oc.max()))
+        mat = np.zeros((nCuts, stride), np.int32)
+        for n, x in enumerate(iStars):
+            mat[n, :len(x)] = x
+        alpha = np.zeros((nReps, nCuts))
+        beta = np.zeros((nReps, nCuts, self.problem.prevCols + 1))
+        self._check(self._call("reform_cuts_batch", nCuts, _pi32(mat), stride, _pi32(oc), nReps, _pi32(ob), k, lbType, int(lb),
+                               _pf64(alpha), _pf64(beta)), "reform_cuts_batch")
+        return alpha, beta
 
     # -- readers ----------------------------------------------------------------------------------------
     def get_omega(self, idx):

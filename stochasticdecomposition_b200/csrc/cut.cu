@@ -627,62 +627,147 @@ __global__ void k_cut_heights(int n, const double *__restrict__ alpha, const dou
 }
 
 struct ReformArgs {
-	const int32_t *iStar; int omegaCnt; const int32_t *observ; int k;
+	const int32_t *iStar; int istarStride; const int32_t *omegaCnt; int nCuts;      // per cut: iStar row and its length
+	const int32_t *observ; int k;                                                    // per replication: k resampled observation indices
 	const double *omega; int64_t NP; int rvOffset2;
 	const double *delta; int64_t Dcap; int Q;
 	const double *sigmaPib, *sigmaPiCr; const int32_t *sigmaLam; int n1c, n1cP;
 	const int32_t *bTermStart, *tSigma, *tOmega;
 	int n1, lbType, lb; const int32_t *CCols, *qCols;
-	double *out;        // [0] alpha, [1..n1+1] beta[0..n1]
+	double *out;        // [rep][cut][n1+2]: alpha, beta[0..n1]
 };
 
-// optimal.c:203-226 for one cut, one CTA
+#define RF_CHUNK 4096
+
+// reformCuts optimal.c:187-236: one CTA per (cut, bootstrap replication).  The k resampled observations are staged through
+// shared memory RF_CHUNK at a time (observation index and the basis its iStar names), then thread (group, column) adds its
+// share of the samples, gathers issued eight at a time; group sums are combined in group order (deterministic).
 __global__ void __launch_bounds__(512) k_reform(ReformArgs a) {
 	__shared__ double s_red[32];
+	__shared__ int s_o[RF_CHUNK], s_b[RF_CHUNK];
+	extern __shared__ double s_part[];      // [groups][nc] partial sums, then [0] alpha, [1] count, [2..2+nc), beta[0..n1]
+	const int cut = blockIdx.x, rep = blockIdx.y, tid = threadIdx.x;
+	const int32_t *iStar = a.iStar + (size_t) cut * a.istarStride;
+	const int32_t *observ = a.observ + (size_t) rep * a.k;
+	const int oc = a.omegaCnt[cut];
 	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
-	double tAlpha = 0.0, tCount = 0.0;
-	for (int n = threadIdx.x; n < a.k; n += blockDim.x) {
-		const int o = a.observ[n];
-		if (o >= a.omegaCnt) continue;                                  // optimal.c:205
-		const int is = a.iStar[o];
-		const double *cellBase = a.delta + (size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W);
-		for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
-			int s = a.tSigma[t], l = a.sigmaLam[s];
-			double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
-			tAlpha = __dadd_rn(tAlpha, __dmul_rn(m, __dadd_rn(a.sigmaPib[s], cellBase[(size_t) l * rowStride])));   // :216
+	const int nc = a.n1c + a.Q;
+	const int kp = ((max(nc, 1) + 31) / 32) * 32;
+	const int groups = max(1, 512 / kp);
+	const int g = tid / kp, col = tid % kp;
+	double tAlpha = 0.0, tCount = 0.0, acc = 0.0;
+	for (int n0 = 0; n0 < a.k; n0 += RF_CHUNK) {
+		const int cn = min(RF_CHUNK, a.k - n0);
+		__syncthreads();
+		for (int i = tid; i < cn; i += blockDim.x) {
+			const int o = observ[n0 + i];
+			int is = -1;
+			if (o < oc) {                                                   // optimal.c:205
+				is = iStar[o];
+				const double *cellBase = a.delta + (size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W);
+				for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
+					const int sg = a.tSigma[t], l = a.sigmaLam[sg];
+					const double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+					tAlpha = __dadd_rn(tAlpha, __dmul_rn(m, __dadd_rn(a.sigmaPib[sg], cellBase[(size_t) l * rowStride])));   // :216
+				}
+				tCount += 1.0;
+			}
+			s_o[i] = o; s_b[i] = is;
 		}
-		tCount += 1.0;
-	}
-	extern __shared__ double s_part[];      // [0] alpha sum, [1] count, [2..2+n1c) sigma part, [2+n1c..) delta part, then beta[0..n1]
-	double r = sd_block_sum(tAlpha, s_red); if (threadIdx.x == 0) s_part[0] = r;
-	r = sd_block_sum(tCount, s_red);        if (threadIdx.x == 0) s_part[1] = r;
-	for (int c = threadIdx.x; c < a.n1c + a.Q; c += blockDim.x) {
-		double acc = 0.0;
-		for (int n = 0; n < a.k; n++) {
-			const int o = a.observ[n];
-			if (o >= a.omegaCnt) continue;
-			const int is = a.iStar[o];
-			const double *cellBase = a.delta + (size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W);
-			for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
-				int s = a.tSigma[t], l = a.sigmaLam[s];
-				double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
-				double v = c < a.n1c ? a.sigmaPiCr[(size_t) s * a.n1cP + c] : cellBase[(size_t) l * rowStride + (size_t) (1 + c - a.n1c) * SD_TILE_W];
-				acc = __dadd_rn(acc, __dmul_rn(m, v));                   // :218-221
+		__syncthreads();
+		if (g < groups && col < nc) {
+			const int per = (cn + groups - 1) / groups;
+			const int i0 = g * per, i1 = min(cn, i0 + per);
+			int i = i0;
+			for (; i + 8 <= i1; i += 8) {
+				double v[8]; bool single = true;
+#pragma unroll
+				for (int u = 0; u < 8; u++) {
+					const int is = s_b[i + u];
+					v[u] = 0.0;
+					if (is >= 0) {
+						const int t0 = a.bTermStart[is];
+						if (a.bTermStart[is + 1] - t0 != 1) { single = false; continue; }
+						const int sg = a.tSigma[t0];
+						const int o = s_o[i + u];
+						v[u] = col < a.n1c ? a.sigmaPiCr[(size_t) sg * a.n1cP + col]
+						                   : a.delta[(size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W) + (size_t) a.sigmaLam[sg] * rowStride + (size_t) (1 + col - a.n1c) * SD_TILE_W];
+					}
+				}
+				if (single) {
+#pragma unroll
+					for (int u = 0; u < 8; u++) if (s_b[i + u] >= 0) acc = __dadd_rn(acc, v[u]);                         // multiplier 1.0
+				}
+				else {
+					for (int u = 0; u < 8; u++) {
+						const int is = s_b[i + u], o = s_o[i + u];
+						if (is < 0) continue;
+						for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
+							const int sg = a.tSigma[t], l = a.sigmaLam[sg];
+							const double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+							const double val = col < a.n1c ? a.sigmaPiCr[(size_t) sg * a.n1cP + col]
+							    : a.delta[(size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W) + (size_t) l * rowStride + (size_t) (1 + col - a.n1c) * SD_TILE_W];
+							acc = __dadd_rn(acc, __dmul_rn(m, val));                                                    // :218-221
+						}
+					}
+				}
+			}
+			for (; i < i1; i++) {
+				const int is = s_b[i], o = s_o[i];
+				if (is < 0) continue;
+				for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
+					const int sg = a.tSigma[t], l = a.sigmaLam[sg];
+					const double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+					const double val = col < a.n1c ? a.sigmaPiCr[(size_t) sg * a.n1cP + col]
+					    : a.delta[(size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W) + (size_t) l * rowStride + (size_t) (1 + col - a.n1c) * SD_TILE_W];
+					acc = __dadd_rn(acc, __dmul_rn(m, val));
+				}
 			}
 		}
-		s_part[2 + c] = acc;
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {                 // optimal.c:197-199 (zero), :218-221 (scatter), :228-235 (average, lower-bound share)
-		double *beta = s_part + 2 + a.n1c + a.Q;
-		for (int i = 0; i <= a.n1; i++) beta[i] = 0.0;
-		for (int k = 0; k < a.n1c; k++) beta[a.CCols[k]] = __dadd_rn(beta[a.CCols[k]], s_part[2 + k]);
-		for (int q = 0; q < a.Q; q++) beta[a.qCols[q]] = __dadd_rn(beta[a.qCols[q]], s_part[2 + a.n1c + q]);
-		for (int i = 0; i <= a.n1; i++) a.out[1 + i] = beta[i] / (double) a.k;
-		double al = s_part[0] / (double) a.k;
-		if (a.lbType == 1) al = __dadd_rn(al, __dmul_rn(__dsub_rn(1.0, s_part[1] / (double) a.k), (double) a.lb));
-		a.out[0] = al;
+	if (g < groups && col < nc) s_part[g * nc + col] = acc;
+	double *s_fin = s_part + (size_t) groups * max(nc, 1);
+	double r = sd_block_sum(tAlpha, s_red); if (tid == 0) s_fin[0] = r;
+	r = sd_block_sum(tCount, s_red);        if (tid == 0) s_fin[1] = r;
+	__syncthreads();
+	if (tid < nc) {
+		double t = 0.0;
+		for (int gg = 0; gg < groups; gg++) t = __dadd_rn(t, s_part[gg * nc + tid]);
+		s_fin[2 + tid] = t;
 	}
+	__syncthreads();
+	if (tid == 0) {                 // optimal.c:197-199 (zero), :218-221 (scatter), :228-235 (average, lower-bound share)
+		double *beta = s_fin + 2 + nc;
+		double *out = a.out + ((size_t) rep * a.nCuts + cut) * (a.n1 + 2);
+		for (int i = 0; i <= a.n1; i++) beta[i] = 0.0;
+		for (int k = 0; k < a.n1c; k++) beta[a.CCols[k]] = __dadd_rn(beta[a.CCols[k]], s_fin[2 + k]);
+		for (int q = 0; q < a.Q; q++) beta[a.qCols[q]] = __dadd_rn(beta[a.qCols[q]], s_fin[2 + a.n1c + q]);
+		for (int i = 0; i <= a.n1; i++) out[1 + i] = beta[i] / (double) a.k;
+		double al = s_fin[0] / (double) a.k;
+		if (a.lbType == 1) al = __dadd_rn(al, __dmul_rn(__dsub_rn(1.0, s_fin[1] / (double) a.k), (double) a.lb));
+		out[0] = al;
+	}
+}
+
+// raw feasibility cuts (cuts.c:478-486): one thread per (observation, infeasible basis) pair, the scatter into beta done
+// in the reference's order (CCols first, then rvCols) so that coinciding columns add up identically
+__global__ void k_feas_cuts(int nPairs, const int32_t *__restrict__ pairObs, const int32_t *__restrict__ pairBasis,
+		const int32_t *__restrict__ bTermStart, const int32_t *__restrict__ tSigma, const double *__restrict__ sigmaPib,
+		const double *__restrict__ sigmaPiCr, const int32_t *__restrict__ sigmaLam, int n1c, int n1cP, const double *__restrict__ delta,
+		int64_t Dcap, int Q, const int32_t *__restrict__ CCols, const int32_t *__restrict__ rvCols, int n1,
+		double *__restrict__ alpha, double *__restrict__ beta) {
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= nPairs) return;
+	const int o = pairObs[p], b = pairBasis[p];
+	const int s = tSigma[bTermStart[b]], l = sigmaLam[s];
+	const size_t rowStride = (size_t) (1 + Q) * SD_TILE_W;
+	const double *cell = delta + (size_t) (o / SD_TILE_W) * Dcap * rowStride + (size_t) l * rowStride + (o % SD_TILE_W);
+	double *bt = beta + (size_t) p * (n1 + 1);
+	for (int i = 0; i <= n1; i++) bt[i] = 0.0;
+	alpha[p] = __dadd_rn(sigmaPib[s], cell[0]);                                                  // cuts.c:481
+	for (int k = 0; k < n1c; k++) bt[CCols[k]] = __dadd_rn(bt[CCols[k]], sigmaPiCr[(size_t) s * n1cP + k]);   // :483-484
+	for (int q = 0; q < Q; q++) bt[rvCols[q]] = __dadd_rn(bt[rvCols[q]], cell[(size_t) (1 + q) * SD_TILE_W]);   // :485-486
 }
 
 // ======================================================================================================
@@ -994,38 +1079,86 @@ extern "C" int sdgpu_cut_heights(sdgpu_ctx *c, int n, const double *alpha, const
 	return best;
 }
 
-extern "C" int sdgpu_reform_cut(sdgpu_ctx *c, const int32_t *iStar, int omegaCnt, const int32_t *observ, int k, int lbType, int lb,
-		double *alpha, double *beta) {
-	if (!c || !observ || !alpha || !beta) return sdgpu_fail("null argument");
-	if (k <= 0) return sdgpu_fail("reform_cut: k must be positive");
+extern "C" int sdgpu_reform_cuts_batch(sdgpu_ctx *c, int nCuts, const int32_t *iStar, int istarStride, const int32_t *omegaCnt,
+		int nReps, const int32_t *observ, int k, int lbType, int lb, double *alpha, double *beta) {
+	if (!c || !observ || !alpha || !beta || !omegaCnt) return sdgpu_fail("null argument");
+	if (k <= 0 || nCuts <= 0 || nReps <= 0) return sdgpu_fail("reform_cuts_batch: k, nCuts and nReps must be positive");
 	SD_CUDA(cudaSetDevice(c->device));
-	if (!iStar) omegaCnt = c->lastOmegaCnt;
-	if (omegaCnt > c->omegaCnt) return sdgpu_fail("reform_cut: omegaCnt %d exceeds stored observations", omegaCnt);
-	int32_t *d_is = nullptr, *d_ob = nullptr; double *d_out = nullptr;
+	std::vector<int32_t> oc(omegaCnt, omegaCnt + nCuts);
+	if (!iStar) { if (nCuts != 1) return sdgpu_fail("reform_cuts_batch: the device-resident iStar serves one cut"); oc[0] = c->lastOmegaCnt; istarStride = 0; }
+	for (int i = 0; i < nCuts; i++)
+		if (oc[i] < 0 || oc[i] > c->omegaCnt || (iStar && oc[i] > istarStride)) return sdgpu_fail("reform_cuts_batch: omegaCnt[%d] = %d out of range", i, oc[i]);
 	const int nOut = c->n1 + 2;
-	if (cudaMalloc((void **) &d_ob, (size_t) k * 4) != cudaSuccess || cudaMalloc((void **) &d_out, (size_t) nOut * 8) != cudaSuccess ||
-	    (iStar && cudaMalloc((void **) &d_is, (size_t) std::max(1, omegaCnt) * 4) != cudaSuccess)) {
-		if (d_ob) cudaFree(d_ob); if (d_out) cudaFree(d_out);
-		return sdgpu_fail("reform_cut: allocation failed");
+	int32_t *d_is = nullptr, *d_ob = nullptr, *d_oc = nullptr; double *d_out = nullptr;
+	auto freeAll = [&]() { if (d_is) cudaFree(d_is); if (d_ob) cudaFree(d_ob); if (d_oc) cudaFree(d_oc); if (d_out) cudaFree(d_out); };
+	if (cudaMalloc((void **) &d_ob, (size_t) nReps * k * 4) != cudaSuccess || cudaMalloc((void **) &d_oc, (size_t) nCuts * 4) != cudaSuccess ||
+	    cudaMalloc((void **) &d_out, (size_t) nReps * nCuts * nOut * 8) != cudaSuccess ||
+	    (iStar && cudaMalloc((void **) &d_is, (size_t) nCuts * std::max(1, istarStride) * 4) != cudaSuccess)) {
+		freeAll();
+		return sdgpu_fail("reform_cuts_batch: allocation failed");
 	}
-	cudaMemcpyAsync(d_ob, observ, (size_t) k * 4, cudaMemcpyHostToDevice, c->stream);
-	if (iStar) cudaMemcpyAsync(d_is, iStar, (size_t) omegaCnt * 4, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyAsync(d_ob, observ, (size_t) nReps * k * 4, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyAsync(d_oc, oc.data(), (size_t) nCuts * 4, cudaMemcpyHostToDevice, c->stream);
+	if (iStar) cudaMemcpyAsync(d_is, iStar, (size_t) nCuts * istarStride * 4, cudaMemcpyHostToDevice, c->stream);
 	ReformArgs a;
-	a.iStar = iStar ? d_is : c->d_iStar; a.omegaCnt = omegaCnt; a.observ = d_ob; a.k = k;
+	a.iStar = iStar ? d_is : c->d_iStar; a.istarStride = istarStride; a.omegaCnt = d_oc; a.nCuts = nCuts; a.observ = d_ob; a.k = k;
 	a.omega = c->d_omega; a.NP = c->NP; a.rvOffset2 = c->rvOffset[2];
 	a.delta = c->d_delta; a.Dcap = c->caps.maxLambda; a.Q = c->Q;
 	a.sigmaPib = c->d_sigmaPib; a.sigmaPiCr = c->d_sigmaPiCr; a.sigmaLam = c->d_sigmaLam; a.n1c = c->n1c; a.n1cP = c->n1cP;
 	a.bTermStart = c->d_bTermStart; a.tSigma = c->d_tSigma; a.tOmega = c->d_tOmega;
 	a.n1 = c->n1; a.lbType = lbType; a.lb = lb; a.CCols = c->d_CCols; a.qCols = c->d_rvCOmCols;      // optimal.c:220 scatters with rvCOmCols
 	a.out = d_out;
-	k_reform<<<1, 512, (size_t) (2 + c->n1c + c->Q + c->n1 + 1) * 8, c->stream>>>(a);
+	const int nc = c->n1c + c->Q, kp = ((std::max(nc, 1) + 31) / 32) * 32, groups = std::max(1, 512 / kp);
+	const size_t dyn = ((size_t) groups * std::max(nc, 1) + 2 + nc + c->n1 + 1) * 8;
+	if (nc > 512) { freeAll(); return sdgpu_fail("reform_cuts_batch: more than 512 cut columns is not supported"); }
+	k_reform<<<dim3((unsigned) nCuts, (unsigned) nReps), 512, dyn, c->stream>>>(a);
 	sd_count_launch(c);
-	std::vector<double> h(nOut);
-	cudaMemcpyAsync(h.data(), d_out, (size_t) nOut * 8, cudaMemcpyDeviceToHost, c->stream);
+	std::vector<double> h((size_t) nReps * nCuts * nOut);
+	cudaMemcpyAsync(h.data(), d_out, h.size() * 8, cudaMemcpyDeviceToHost, c->stream);
 	cudaError_t e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_ob); cudaFree(d_out); if (d_is) cudaFree(d_is);
-	if (e != cudaSuccess) return sdgpu_fail("reform_cut: %s", cudaGetErrorString(e));
-	*alpha = h[0];
-	memcpy(beta, h.data() + 1, ((size_t) c->n1 + 1) * 8);
+	freeAll();
+	if (e != cudaSuccess) return sdgpu_fail("reform_cuts_batch: %s", cudaGetErrorString(e));
+	for (size_t i = 0; i < (size_t) nReps * nCuts; i++) {
+		alpha[i] = h[i * nOut];
+		memcpy(beta + i * (c->n1 + 1), h.data() + i * nOut + 1, ((size_t) c->n1 + 1) * 8);
+	}
 	return 0;
+}
+
+extern "C" int sdgpu_reform_cut(sdgpu_ctx *c, const int32_t *iStar, int omegaCnt, const int32_t *observ, int k, int lbType, int lb,
+		double *alpha, double *beta) {
+	if (!c) return sdgpu_fail("null context");
+	int32_t oc = iStar ? omegaCnt : c->lastOmegaCnt;
+	return sdgpu_reform_cuts_batch(c, 1, iStar, omegaCnt, &oc, 1, observ, k, lbType, lb, alpha, beta);
+}
+
+extern "C" int sdgpu_feas_cuts(sdgpu_ctx *c, int obsFirst, int obsLast, int basisFirst, int basisLast, int maxOut, double *alpha, double *beta) {
+	if (!c || (maxOut > 0 && (!alpha || !beta))) return sdgpu_fail("null argument");
+	if (obsFirst < 0 || obsLast > c->omegaCnt || basisFirst < 0 || basisLast > c->basisCnt || obsFirst > obsLast || basisFirst > basisLast)
+		return sdgpu_fail("feas_cuts: range out of bounds");
+	std::vector<int32_t> po, pb;
+	for (int o = obsFirst; o < obsLast; o++)                       // cuts.c:473-475 loop order
+		for (int b = basisFirst; b < basisLast; b++)
+			if (!c->basis[b].feas) { po.push_back(o); pb.push_back(b); }
+	const int n = (int) std::min<size_t>(po.size(), (size_t) std::max(0, maxOut));
+	if (po.size() > (size_t) std::max(0, maxOut)) return sdgpu_fail("feas_cuts: %zu cuts do not fit maxOut = %d", po.size(), maxOut);
+	if (n == 0) return 0;
+	SD_CUDA(cudaSetDevice(c->device));
+	int32_t *d_p = nullptr; double *d_o = nullptr;
+	const size_t n1p = (size_t) c->n1 + 1;
+	if (cudaMalloc((void **) &d_p, (size_t) 2 * n * 4) != cudaSuccess || cudaMalloc((void **) &d_o, (size_t) n * (1 + n1p) * 8) != cudaSuccess) {
+		if (d_p) cudaFree(d_p);
+		return sdgpu_fail("feas_cuts: allocation failed");
+	}
+	cudaMemcpyAsync(d_p, po.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyAsync(d_p + n, pb.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
+	k_feas_cuts<<<sd_blocks(n, 128), 128, 0, c->stream>>>(n, d_p, d_p + n, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaPiCr, c->d_sigmaLam,
+			c->n1c, c->n1cP, c->d_delta, c->caps.maxLambda, c->Q, c->d_CCols, c->d_rvCols, c->n1, d_o, d_o + n);
+	sd_count_launch(c);
+	cudaMemcpyAsync(alpha, d_o, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
+	cudaMemcpyAsync(beta, d_o + n, (size_t) n * n1p * 8, cudaMemcpyDeviceToHost, c->stream);
+	cudaError_t e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_p); cudaFree(d_o);
+	if (e != cudaSuccess) return sdgpu_fail("feas_cuts: %s", cudaGetErrorString(e));
+	return n;
 }

@@ -89,6 +89,18 @@ struct sdgpu_ctx {
 	int32_t *d_tSigma = nullptr, *d_tOmega = nullptr;
 	SdDevState *d_state = nullptr;
 
+	// checkBasisFeasibility inputs (allocated on first use, rvdOmCnt > 0 only)
+	int      cols = 0;
+	int32_t *d_rvdOmCols = nullptr;  // [rvd] 1-based column of each random cost
+	char    *d_senx = nullptr;       // [rows]
+	double  *d_fPiDet = nullptr;     // [Bcap][rows]
+	double  *d_fPhi = nullptr;       // [termCap][rows]   (term t >= 1 of a basis = its phi column t-1)
+	double  *d_fGBar = nullptr;      // [Bcap][cols]
+	double  *d_fPsi = nullptr;       // [termCap][cols]
+	int8_t  *d_fCstat = nullptr;     // [Bcap][cols]
+	uint8_t *d_fHas = nullptr;       // [Bcap]
+	uint8_t *d_fFlags = nullptr;     // [max(Bcap, NP)] result staging
+
 	// per-call staging
 	double  *d_vecIn = nullptr;      // a host vector (Pi / observ / X) of up to max(rows, numRV, n1)+1 doubles
 	double  *d_cand = nullptr;       // reduced candidate: lambda [R] / piCBar [n1c] / observation [numRV]

@@ -375,6 +375,61 @@ __global__ void k_mask_fill_col(uint8_t *mask, int64_t Bcap, int64_t o, const ui
 	if (b < nb && feas[b]) mask[sd_mask_off(Bcap, b, o)] = flags[b] != 0;
 }
 
+// checkBasisFeasibility randCost.c:202-258 for one (basis, observation) pair, evaluated by a whole CTA: every row's
+// reconstructed dual (piDet + sum_n phi_n * dOmega) against its sense and every column's reduced cost
+// (gBar + dOmega - psi * dOmega) against its bound status; the pair is feasible iff no thread finds a violation.
+struct FeasArgs {
+	const double *omega; int64_t NP; int rvOffset2, rvd;
+	const int32_t *rvdOmCols; const char *senx; int rows, cols;
+	const int32_t *bPhiLen, *bTermStart, *bFeas, *tOmega;
+	const double *piDet, *phi, *gBar, *psi; const int8_t *cstat; const uint8_t *has;
+	double tol; uint8_t *mask; int64_t Bcap; uint8_t *flags;
+};
+
+__device__ __forceinline__ bool sd_pair_violates(const FeasArgs &a, int b, const double *s_val) {
+	const int phiLen = a.bPhiLen[b], t0 = a.bTermStart[b];
+	bool bad = false;
+	if (phiLen > 0) {                                                   // randCost.c:213-224
+		for (int c = threadIdx.x; c < a.rows; c += blockDim.x) {
+			double theta = 0.0;
+			for (int n = 0; n < phiLen; n++)
+				theta += a.phi[(size_t) (t0 + 1 + n) * a.rows + c] * s_val[a.tOmega[t0 + 1 + n] - 1];
+			const double v = a.piDet[(size_t) b * a.rows + c] + theta;
+			const char sense = a.senx[c];
+			if ((v < -a.tol && sense == 'G') || (v > a.tol && sense == 'L')) bad = true;
+		}
+	}
+	for (int c = threadIdx.x; c < a.cols; c += blockDim.x) {            // randCost.c:236-252
+		double rc = a.gBar[(size_t) b * a.cols + c];
+		for (int j = 0; j < a.rvd; j++) if (a.rvdOmCols[j] == c + 1) rc += s_val[j];          // addVectors
+		for (int n = 0; n < phiLen; n++)                                                       // MSparsexvSub, entry order
+			rc -= a.psi[(size_t) (t0 + 1 + n) * a.cols + c] * s_val[a.tOmega[t0 + 1 + n] - 1];
+		if (rc < -a.tol && a.cstat[(size_t) b * a.cols + c] != 2) bad = true;
+	}
+	return bad;
+}
+
+// a new observation against every stored basis (stocUpdate.c:28-30): one CTA per basis
+__global__ void k_feas_obs(FeasArgs a, int obs) {
+	extern __shared__ double s_val[];
+	const int b = blockIdx.x;
+	if (!a.bFeas[b] || !a.has[b]) { if (threadIdx.x == 0) a.flags[b] = 2; return; }             // 2 = untouched
+	for (int j = threadIdx.x; j < a.rvd; j += blockDim.x) s_val[j] = a.omega[(size_t) (a.rvOffset2 + j) * a.NP + obs];
+	__syncthreads();
+	const int bad = __syncthreads_or(sd_pair_violates(a, b, s_val));
+	if (threadIdx.x == 0) { a.flags[b] = !bad; a.mask[sd_mask_off(a.Bcap, b, obs)] = !bad; }
+}
+
+// a new basis against every stored observation (stocUpdate.c:123-126): one CTA per observation
+__global__ void k_feas_basis(FeasArgs a, int b) {
+	extern __shared__ double s_val[];
+	const int obs = blockIdx.x;
+	for (int j = threadIdx.x; j < a.rvd; j += blockDim.x) s_val[j] = a.omega[(size_t) (a.rvOffset2 + j) * a.NP + obs];
+	__syncthreads();
+	const int bad = __syncthreads_or(sd_pair_violates(a, b, s_val));
+	if (threadIdx.x == 0) { a.flags[obs] = !bad; a.mask[sd_mask_off(a.Bcap, b, obs)] = !bad; }
+}
+
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -435,7 +490,7 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	c->device = device; c->num = nm; c->caps = *caps;
 	if (c->caps.maxTerms < 1) c->caps.maxTerms = 1;
 	c->n1 = nm.prevCols; c->n1c = nm.cntCcols; c->n1cP = std::max(1, nm.cntCcols); c->R = nm.rvRowCnt; c->Rb = nm.rvbOmCnt;
-	c->Q = nm.rvCOmCnt; c->rvd = nm.rvdOmCnt; c->numRV = nm.numRV; c->rows = nm.rows;
+	c->Q = nm.rvCOmCnt; c->rvd = nm.rvdOmCnt; c->numRV = nm.numRV; c->rows = nm.rows; c->cols = nm.cols;
 	memcpy(c->rvOffset, p->coord.rvOffset, sizeof c->rvOffset);
 	c->NP = sd_round_up(caps->maxOmega, SD_TILE_W); c->nTiles = c->NP / SD_TILE_W;
 	c->LP = sd_round_up(caps->maxLambda, 32); c->SP = sd_round_up(caps->maxSigma, 32); c->BP = sd_round_up(caps->maxBasis, 32);
@@ -543,6 +598,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	void *dev[] = { c->d_CCols, c->d_rvRows, c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_rvCOmCols, c->d_rvCols, c->d_bBarCol,
 		c->d_bBarVal, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->d_omega, c->d_omegaW, c->d_lambda, c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr,
 		c->d_sigmaLam, c->d_sigmaCk, c->d_delta, c->d_mask, c->d_bCk, c->d_bFeas, c->d_bPhiLen, c->d_bTermStart, c->d_tSigma, c->d_tOmega, c->d_state,
+		c->d_rvdOmCols, c->d_senx, c->d_fPiDet, c->d_fPhi, c->d_fGBar, c->d_fPsi, c->d_fCstat, c->d_fHas, c->d_fFlags,
 		c->d_vecIn, c->d_cand, c->d_candC, c->d_x, c->d_piCbarX, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin, c->d_partV, c->d_partI,
 		c->d_iStar, c->d_tilePart, c->d_cutPartial, c->d_cutOut };
 	for (void *p : dev) if (p) cudaFree(p);
@@ -570,6 +626,7 @@ extern "C" int sdgpu_reset(sdgpu_ctx *c) {
 	c->omegaCnt = c->lambdaCnt = c->sigmaCnt = c->basisCnt = c->termCnt = 0;
 	c->maxPhiLen = 0; c->anyInfeasibleBasis = false; c->lastOmegaCnt = 0;
 	c->basis.clear(); c->hostMask.clear();
+	if (c->d_fHas) SD_CUDA(cudaMemset(c->d_fHas, 0, (size_t) c->caps.maxBasis));
 	return 0;
 }
 
@@ -1050,5 +1107,103 @@ extern "C" int sdgpu_get_delta_block(sdgpu_ctx *c, int64_t l0, int64_t l1, int64
 			o = tEnd;
 		}
 	}
+	return 0;
+}
+
+// ---- checkBasisFeasibility on the device (randCost.c:202-258) ----------------------------------------------------
+static int sd_feas_alloc(sdgpu_ctx *c) {
+	if (c->d_fPiDet) return 0;
+	if (sd_alloc(&c->d_fPiDet, (size_t) c->caps.maxBasis * c->rows) || sd_alloc(&c->d_fPhi, (size_t) c->termCap * c->rows) ||
+	    sd_alloc(&c->d_fGBar, (size_t) c->caps.maxBasis * c->cols) || sd_alloc(&c->d_fPsi, (size_t) c->termCap * c->cols) ||
+	    sd_alloc(&c->d_fCstat, (size_t) c->caps.maxBasis * c->cols) || sd_alloc(&c->d_fHas, (size_t) c->caps.maxBasis) ||
+	    sd_alloc(&c->d_fFlags, (size_t) std::max<int64_t>(c->caps.maxBasis, c->NP)))
+		return SDGPU_ERR;
+	SD_CUDA(cudaMemset(c->d_fHas, 0, (size_t) c->caps.maxBasis));
+	return 0;
+}
+
+extern "C" int sdgpu_set_cost_coords(sdgpu_ctx *c, const int32_t *rvdOmCols, const char *senx) {
+	if (!c || !senx || (c->rvd > 0 && !rvdOmCols)) return sdgpu_fail("null argument");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (!c->d_senx && (sd_alloc(&c->d_senx, (size_t) c->rows) || sd_alloc(&c->d_rvdOmCols, (size_t) std::max(1, c->rvd)))) return SDGPU_ERR;
+	SD_CUDA(cudaMemcpy(c->d_senx, senx, (size_t) c->rows, cudaMemcpyHostToDevice));
+	if (c->rvd > 0) SD_CUDA(cudaMemcpy(c->d_rvdOmCols, rvdOmCols + 1, (size_t) c->rvd * 4, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+extern "C" int sdgpu_basis_set_feas_data(sdgpu_ctx *c, int basisIdx, const double *piDet, const double *phi, const double *gBar,
+		const double *psiVal, const int32_t *cstat) {
+	if (!c || !piDet || !gBar || !cstat) return sdgpu_fail("null argument");
+	if (basisIdx < 0 || basisIdx >= c->basisCnt) return sdgpu_fail("basis_set_feas_data: bad basis %d", basisIdx);
+	if (c->rvd == 0) return 0;                       // constant true without random costs (randCost.c:208)
+	const SdHostBasis &hb = c->basis[basisIdx];
+	if (hb.phiLen > 0 && (!phi || !psiVal)) return sdgpu_fail("basis_set_feas_data: phi / psi required when phiLength > 0");
+	SD_CUDA(cudaSetDevice(c->device));
+	if (!c->d_senx) return sdgpu_fail("basis_set_feas_data: call sdgpu_set_cost_coords first");
+	if (sd_feas_alloc(c)) return SDGPU_ERR;
+	// term offset of this basis: recompute from the host list (terms are appended in basis order)
+	int64_t t0 = 0;
+	for (int b = 0; b < basisIdx; b++) t0 += c->basis[b].phiLen + 1;
+	SD_CUDA(cudaMemcpyAsync(c->d_fPiDet + (size_t) basisIdx * c->rows, piDet + 1, (size_t) c->rows * 8, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(c->d_fGBar + (size_t) basisIdx * c->cols, gBar + 1, (size_t) c->cols * 8, cudaMemcpyHostToDevice, c->stream));
+	std::vector<int8_t> cs((size_t) c->cols);
+	for (int i = 0; i < c->cols; i++) cs[i] = (int8_t) cstat[i + 1];
+	SD_CUDA(cudaMemcpyAsync(c->d_fCstat + (size_t) basisIdx * c->cols, cs.data(), (size_t) c->cols, cudaMemcpyHostToDevice, c->stream));
+	std::vector<double> psiT;
+	for (int n = 0; n < hb.phiLen; n++) {
+		SD_CUDA(cudaMemcpyAsync(c->d_fPhi + (size_t) (t0 + 1 + n) * c->rows, phi + (size_t) n * (c->rows + 1) + 1, (size_t) c->rows * 8, cudaMemcpyHostToDevice, c->stream));
+		psiT.resize((size_t) c->cols);
+		for (int i = 0; i < c->cols; i++) psiT[i] = psiVal[(size_t) i * hb.phiLen + n];
+		SD_CUDA(cudaMemcpyAsync(c->d_fPsi + (size_t) (t0 + 1 + n) * c->cols, psiT.data(), (size_t) c->cols * 8, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaStreamSynchronize(c->stream));           // psiT is reused
+	}
+	const uint8_t one = 1;
+	SD_CUDA(cudaMemcpyAsync(c->d_fHas + basisIdx, &one, 1, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+static FeasArgs sd_feas_args(sdgpu_ctx *c, double tol) {
+	FeasArgs a;
+	a.omega = c->d_omega; a.NP = c->NP; a.rvOffset2 = c->rvOffset[2]; a.rvd = c->rvd;
+	a.rvdOmCols = c->d_rvdOmCols; a.senx = c->d_senx; a.rows = c->rows; a.cols = c->cols;
+	a.bPhiLen = c->d_bPhiLen; a.bTermStart = c->d_bTermStart; a.bFeas = c->d_bFeas; a.tOmega = c->d_tOmega;
+	a.piDet = c->d_fPiDet; a.phi = c->d_fPhi; a.gBar = c->d_fGBar; a.psi = c->d_fPsi; a.cstat = c->d_fCstat; a.has = c->d_fHas;
+	a.tol = tol; a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.flags = c->d_fFlags;
+	return a;
+}
+
+extern "C" int sdgpu_check_feasibility_obs(sdgpu_ctx *c, int obsIdx, double tol, uint8_t *flagsOut) {
+	if (!c) return sdgpu_fail("null context");
+	if (obsIdx < 0 || obsIdx >= c->omegaCnt) return sdgpu_fail("check_feasibility_obs: bad observation %d", obsIdx);
+	if (c->rvd == 0 || c->basisCnt == 0) { if (flagsOut) memset(flagsOut, 1, (size_t) c->basisCnt); return 0; }
+	if (!c->d_fPiDet) return sdgpu_fail("check_feasibility_obs: no basis carries feasibility data yet");
+	SD_CUDA(cudaSetDevice(c->device));
+	k_feas_obs<<<(unsigned) c->basisCnt, 128, (size_t) std::max(1, c->rvd) * 8, c->stream>>>(sd_feas_args(c, tol), obsIdx);
+	sd_count_launch(c);
+	std::vector<uint8_t> f((size_t) c->basisCnt);
+	SD_CUDA(cudaMemcpyAsync(f.data(), c->d_fFlags, f.size(), cudaMemcpyDeviceToHost, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	for (int64_t b = 0; b < c->basisCnt; b++) {
+		if (f[b] == 2) { f[b] = c->basis[b].feas ? c->hostMask[b][obsIdx] : 0; continue; }   // untouched: keep what the mask holds
+		c->hostMask[b][obsIdx] = f[b];
+	}
+	if (flagsOut) memcpy(flagsOut, f.data(), f.size());
+	return 0;
+}
+
+extern "C" int sdgpu_check_feasibility_basis(sdgpu_ctx *c, int basisIdx, double tol, uint8_t *flagsOut) {
+	if (!c) return sdgpu_fail("null context");
+	if (basisIdx < 0 || basisIdx >= c->basisCnt || !c->basis[basisIdx].feas) return sdgpu_fail("check_feasibility_basis: bad basis %d", basisIdx);
+	if (c->rvd == 0 || c->omegaCnt == 0) { if (flagsOut) memset(flagsOut, 1, (size_t) c->omegaCnt); return 0; }
+	if (!c->d_fPiDet) return sdgpu_fail("check_feasibility_basis: basis %d carries no feasibility data", basisIdx);
+	SD_CUDA(cudaSetDevice(c->device));
+	k_feas_basis<<<(unsigned) c->omegaCnt, 128, (size_t) std::max(1, c->rvd) * 8, c->stream>>>(sd_feas_args(c, tol), basisIdx);
+	sd_count_launch(c);
+	std::vector<uint8_t> f((size_t) c->omegaCnt);
+	SD_CUDA(cudaMemcpyAsync(f.data(), c->d_fFlags, f.size(), cudaMemcpyDeviceToHost, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	for (int64_t o = 0; o < c->omegaCnt; o++) c->hostMask[basisIdx][o] = f[o];
+	if (flagsOut) memcpy(flagsOut, f.data(), f.size());
 	return 0;
 }

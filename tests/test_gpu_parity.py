@@ -184,3 +184,37 @@ def test_heights_reform_istar_single():
                 assert p[0] == g[0]
                 if p[0] >= 0:
                     assert np.float64(p[1]).tobytes() == np.float64(g[1]).tobytes()
+
+
+@pytest.mark.parametrize("case", ["T_random", "random_cost_T"])
+def test_bootstrap_batch_reform(case):
+    """reformCuts over cuts x bootstrap replications (optimal.c:96-103) in one launch, against the oracle"""
+    pk, K, dpool, opool, phi_len, rk = CASES[case]
+    prob = make_problem(1000 + len(case), **pk)
+    trace = make_trace(prob, K, seed=77 + K, dual_pool=dpool, obs_pool=opool, phi_len=phi_len)
+    caps = roomy_caps(K, phi_len)
+    port = replay(oracle_loader.oracle(), prob, trace, caps, **rk)
+    gpu = replay(sd.load_library(), prob, trace, caps, **rk)
+    cuts = [c for c in port.cuts if c is not None][-6:]
+    rng = np.random.default_rng(3)
+    for k in (K, 5000):                                       # 5000 > one staging chunk
+        observ = rng.integers(0, port.counts["omega"] + 2, size=(9, k)).astype(np.int32)
+        ap, bp = port.tables.reform_cuts_batch([c.iStar for c in cuts], observ, 1, -3.0)
+        ag, bg = gpu.tables.reform_cuts_batch([c.iStar for c in cuts], observ, 1, -3.0)
+        assert np.abs(ap - ag).max() <= RTOL * np.abs(ap).max()
+        assert np.abs(bp - bg).max() <= RTOL * np.abs(bp).max()
+
+
+def test_check_basis_feasibility_on_device():
+    """checkBasisFeasibility (randCost.c:202-258) evaluated by the library: flags identical to the oracle, cuts under the mask agree"""
+    import feas_scenario
+    feas_scenario.compare(feas_scenario.run(oracle_loader.oracle()), feas_scenario.run(sd.load_library()), exact=False)
+
+
+def test_feasibility_cuts_on_device():
+    """raw feasibility cuts (cuts.c:473-490) from the device: the pool built from them is bit-identical to the oracle's"""
+    import feas_pool
+    sp, ap, bp = feas_pool.run(oracle_loader.oracle())
+    sg, ag, bg = feas_pool.run(sd.load_library())
+    assert sp == sg and sp[-1] > 5
+    assert np.array_equal(ap.view(np.int64), ag.view(np.int64)) and np.array_equal(bp.view(np.int64), bg.view(np.int64))

@@ -136,6 +136,36 @@ def test_cut_heights_and_reform():
         assert np.array_equal(br.view(np.int64), bp.view(np.int64))
 
 
+def test_bootstrap_batch_reform():
+    prob = make_problem(23, rows=20, cols=30, n1=8, n1c=6, R=9, Rb=6, Q=2)
+    K = 40
+    trace = make_trace(prob, K, seed=14, dual_pool=9, obs_pool=0)
+    caps = roomy_caps(K)
+    ref = replay(oracle_loader.reference(), prob, trace, caps)
+    port = replay(oracle_loader.oracle(), prob, trace, caps)
+    cuts = [c for c in ref.cuts if c is not None][-5:]
+    rng = np.random.default_rng(3)
+    observ = rng.integers(0, ref.counts["omega"], size=(7, K)).astype(np.int32)
+    ar, br = ref.tables.reform_cuts_batch([c.iStar for c in cuts], observ, 1, -3.0)
+    ap, bp = port.tables.reform_cuts_batch([c.iStar for c in cuts], observ, 1, -3.0)
+    assert np.array_equal(ar.view(np.int64), ap.view(np.int64)) and np.array_equal(br.view(np.int64), bp.view(np.int64))
+
+
+def test_check_basis_feasibility_matches_reference():
+    """randCost.c:202-258 compiled from the reference vs the port, then cuts formed under the resulting mask"""
+    import feas_scenario
+    feas_scenario.compare(feas_scenario.run(oracle_loader.reference()), feas_scenario.run(oracle_loader.oracle()), exact=True)
+
+
+def test_feasibility_cut_pool_matches_reference():
+    """the reference's own updtFeasCutPool + addCut2Pool (cuts.c:465-517,643-655) against raw cuts from the port + the host dedup"""
+    import feas_pool
+    sr, ar, br = feas_pool.run(oracle_loader.reference(), use_reference_pool=True)
+    sp, ap, bp = feas_pool.run(oracle_loader.oracle())
+    assert sr == sp and sr[-1] > 5
+    assert np.array_equal(ar.view(np.int64), ap.view(np.int64)) and np.array_equal(br.view(np.int64), bp.view(np.int64))
+
+
 def test_omp_flavour_same_istar():
     prob = make_problem(31, rows=30, cols=40, n1=12, n1c=9, R=11, Rb=8, Q=2)
     K = 40
