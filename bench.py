@@ -233,6 +233,9 @@ def workload_name(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
 def gpu_arm(args):
+    # stdout must carry exactly one JSON line: NCCL and torchrun helpers print banners to fd 1, so route fd 1 to stderr until then
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import stochasticdecomposition_b200 as sd
     from stochasticdecomposition_b200._abi import CCut, _pf64, _pi32
@@ -374,7 +377,10 @@ def gpu_arm(args):
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline_omp_port"] = {k: cpu_omp[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     t.close()
     if dist is not None:
         dist.barrier()
