@@ -161,6 +161,8 @@ def run_cpu(kind: str, args, steps: int, warmup: int):
     iters = np.ceil((np.arange(D) + 1) * (k_total / D)).astype(np.int32)
     caps = Caps(D + 8, D + 8, D + 8, N + 8, 1)
     t0 = time.perf_counter()
+    if kind == "reference" and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsdref.so")) and not os.path.isdir("/root/reference"):
+        kind = "port_single"             # the reference build did not travel to this box: fall back to the restated oracle, one thread
     if kind == "reference":
         api = oracle_loader.reference()
         t = api.create(prob, caps)
@@ -175,7 +177,7 @@ def run_cpu(kind: str, args, steps: int, warmup: int):
         t.omega_append_bulk(obsv[:N], weights)
         li, si = t.update_dual_bulk(pis[:D], None, iters, -1.0)
         t.calc_delta_block(0, D, 0, N)
-        cores, variant = os.cpu_count() or 1, "sd_cut_omp"
+        cores, variant = (os.cpu_count() or 1, "sd_cut_omp") if kind == "port_omp" else (1, "sd_cut")
     for b in range(int(si.max()) + 1):
         t.basis_append(int(iters[b]), True, [b])          # (the reference build has no bulk form; a few thousand calls)
     nb = t.counts()["basis"]
