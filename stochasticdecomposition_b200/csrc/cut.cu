@@ -3,16 +3,16 @@
 // (SDCut, cuts.c:91-194), cut heights / aging (cuts.c:197-227, master.c:152,174) and reformCuts
 // (optimal.c:187-236).  Citations are file:line under /root/reference/twoSD_src.
 //
-// Pipeline of one cut (all on the context's stream, one host sync at the end):
-//   k_picbarx      piCbarX[s] = sigma.piC[s] . x[CCols]                      cuts.c:105-106
-//   k_basis_desc   per basis: (sigma.pib, piCbarX, lambda row, window)       stocUpdate.c:151-167
-//   k_sweep_*      2-D grid (observation tile x basis chunk): stream the delta tile, keep running
+// Pipeline of one cut (three launches on the context's stream, one host wait at the end):
+//   k_cut_prep     x as a kernel parameter; per basis (sigma.pib, piCbarX = sigma.piC . x[CCols], lambda row, window)
+//                                                                             cuts.c:105-106, stocUpdate.c:151-167
+//   k_sweep_*      2-D grid (observation tile x basis chunk): stream the delta tile (TMA bulk ring or LDG), keep running
 //                  (max, first index) per observation for the old and the new window   stocUpdate.c:161-184
 //   k_cut_merge    merge chunk maxima in index order, pick iStar (cuts.c:124-125,136-140), accumulate
-//                  w*(sigma.pib + delta.pib), w*sigma.piC, w*delta.piC, cummOld, cummAll per tile   cuts.c:127-168
-//   k_cut_finalize sum tile partials in tile order, scatter into beta          cuts.c:155-167
-//   [NCCL all-reduce of n1+4 doubles when observations are sharded]
-//   k_cut_normalise alpha/k, beta/k, beta[0] = 1                               cuts.c:184-188
+//                  w*(sigma.pib + delta.pib), w*sigma.piC, w*delta.piC, cummOld, cummAll per tile   cuts.c:127-168;
+//                  the last tile to finish sums the tile partials in tile order, scatters into beta (cuts.c:155-167),
+//                  applies alpha/k, beta/k (cuts.c:184-188) and writes the cut into mapped pinned host memory
+//   [sharded: un-normalised vector -> NCCL all-reduce of n1+4 doubles -> k_cut_normalise]
 //
 // Scores are evaluated with the reference's operation order and without FMA contraction, so they are
 // bit-identical to the CPU path; (max, index) merges keep the LOWEST index among equal maxima (strict '>'
