@@ -309,6 +309,100 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) k_sweep_tma(SweepArgs a
 	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
 }
 
+// The same ring for problems with random technology-matrix elements (Q > 0): in the tiled layout the 1+Q planes of one
+// dual row are contiguous, so one bulk copy of (1+Q) x 4 KiB brings delta.pib and all of delta.piC for 512 observations.
+// Rows per stage (rps, a power of two) keeps a stage near 32 KiB; two stages.
+__global__ void __launch_bounds__(TMA_THREADS, 2) k_sweep_tma_q(SweepArgs a, int rps) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int planes = 1 + a.Q;
+	const size_t rowDoubles = (size_t) planes * SD_TILE_W;
+	const size_t stageBytes = (size_t) rps * rowDoubles * 8;
+	double *ring = reinterpret_cast<double *>(smem_raw);
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 2 * stageBytes);
+	uint64_t *empty = full + 2;
+	double2 *s_ac = reinterpret_cast<double2 *>(empty + 2);
+	int *s_win = reinterpret_cast<int *>(s_ac + SW_BATCH);
+	double *s_xq = reinterpret_cast<double *>(s_win + SW_BATCH);                          // [64]
+	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	const int nRows = b1 - b0, nIter = (nRows + rps - 1) / rps;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowDoubles;
+	if (tid == 0) {
+		for (int s = 0; s < 2; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (int q = tid; q < a.Q; q += blockDim.x) s_xq[q] = a.x[a.rvCOmCols[q]];
+	__syncthreads();
+
+	if (tid >= TMA_CONSUMERS) {
+		if (tid == TMA_CONSUMERS) {
+			for (int it = 0; it < nIter; it++) {
+				const int s = it & 1;
+				sd_mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+				const int r0 = it * rps, nr = min(rps, nRows - r0);
+				sd_mbar_expect_tx(&full[s], (uint32_t) (nr * rowDoubles * 8));
+				for (int r = 0; r < nr; r++) {
+					const int row = a.descRow[b0 + r0 + r];
+					sd_bulk_g2s(ring + (size_t) s * rps * rowDoubles + (size_t) r * rowDoubles, tileBase + (size_t) row * rowDoubles,
+							(uint32_t) (rowDoubles * 8), &full[s]);
+				}
+			}
+		}
+		return;
+	}
+
+	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
+	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+	for (int it = 0; it < nIter; it++) {
+		const int r0 = it * rps;
+		if (r0 % SW_BATCH == 0) {
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+			const int b = b0 + r0 + tid;
+			const bool ok = b < b1;
+			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
+			s_win[tid] = ok ? a.descWin[b] : 0;
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+		}
+		const int s = it & 1;
+		sd_mbar_wait(&full[s], (it >> 1) & 1);
+		for (int r = 0; r < rps; r++) {
+			const int j = (r0 + r) % SW_BATCH;
+			const int win = s_win[j];
+			if (win == 0) continue;
+			const double2 *rowp = reinterpret_cast<const double2 *>(ring + (size_t) s * rps * rowDoubles + (size_t) r * rowDoubles) + tid;
+			const double2 d = rowp[0];
+			const double2 ac = s_ac[j];
+			const int b = b0 + r0 + r;
+			double s0 = __dsub_rn(__dadd_rn(ac.x, d.x), ac.y);                              // stocUpdate.c:174
+			double s1 = __dsub_rn(__dadd_rn(ac.x, d.y), ac.y);
+			double dx0 = 0.0, dx1 = 0.0;                                                    // stocUpdate.c:175
+			for (int q = 0; q < a.Q; q++) {
+				const double2 p = rowp[(size_t) (1 + q) * (SD_TILE_W / 2)];
+				dx0 = __dadd_rn(dx0, __dmul_rn(p.x, s_xq[q]));
+				dx1 = __dadd_rn(dx1, __dmul_rn(p.y, s_xq[q]));
+			}
+			s0 = __dsub_rn(__dadd_rn(0.0, s0), dx0);
+			s1 = __dsub_rn(__dadd_rn(0.0, s1), dx1);
+			if (win == 1) {
+				if (s0 > oV0) { oV0 = s0; oI0 = b; }
+				if (s1 > oV1) { oV1 = s1; oI1 = b; }
+			}
+			else {
+				if (s0 > nV0) { nV0 = s0; nI0 = b; }
+				if (s1 > nV1) { nV1 = s1; nI1 = b; }
+			}
+		}
+		__syncwarp();
+		if ((tid & 31) == 0) sd_mbar_arrive(&empty[s]);
+	}
+	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
+	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
+	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
+	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
+	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
+	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
+}
+
 // General sweep: bases with phi columns (random cost, multi-term score) and/or the feasibility mask.
 //   arg = sum_t m_t * ((sigma.pib[s_t] + delta.pib[l_t][o]) - piCbarX[s_t]) - m_t * (delta.piC[l_t][o] . x)   stocUpdate.c:164-176
 struct SweepGenArgs {
@@ -850,6 +944,17 @@ static int sd_launch_tma(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 	}
 }
 
+static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
+	const int planes = 1 + c->Q;
+	int rps = 8;
+	while (rps > 1 && rps * planes > 8) rps >>= 1;                    // stage near 32 KiB
+	const size_t smem = (size_t) 2 * rps * planes * TMA_ROW_BYTES + 4 * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int)) + 64 * sizeof(double);
+	static size_t attrMax = 0;
+	if (smem > attrMax) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attrMax = smem; }
+	k_sweep_tma_q<<<grid, TMA_THREADS, smem, c->stream>>>(a, rps);
+	return 0;
+}
+
 static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, bool fuseNormalise) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
 	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
@@ -882,11 +987,11 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
 			const bool hasMask = c->rvd > 0;
 			// variant 0 = automatic: the TMA ring wins from ~4M pairs up, the LDG kernel below that (tools/tma_check.py)
-			const bool tmaOk = c->Q == 0 && !hasMask;
-			const bool useTma = tmaOk && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N >= ((int64_t) 4 << 20)));
+			const bool tmaOk = !hasMask && (1 + c->Q) * TMA_ROW_BYTES <= 48 * 1024;      // one dual row (all planes) must fit a ring stage
+			const bool useTma = tmaOk && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N * (1 + c->Q) >= ((int64_t) 4 << 20)));
 			c->stats.last_sweep_variant = useTma ? 2 : 1;
 			if (useTma) {
-				if (sd_launch_tma(c, grid, a)) return SDGPU_ERR;
+				if (c->Q == 0 ? sd_launch_tma(c, grid, a) : sd_launch_tma_q(c, grid, a)) return SDGPU_ERR;
 			}
 			else if (c->Q > 0 && hasMask) k_sweep_ldg<true, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else if (c->Q > 0)       k_sweep_ldg<true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);

@@ -32,6 +32,23 @@ def probe(D, N, rv, n1, reps=30):
         out[f"cut_wall_us_{tag}"] = round(float(np.median(w)) * 1e6, 1)
         out[f"cut_dev_us_{tag}"] = round(float(np.median(dev)) * 1e3, 1)
         out[f"sweep_us_{tag}"] = round(float(np.median(swp)) * 1e3, 1)
+    # the same call with pre-built ctypes arguments: what a C host sees (no numpy / wrapper overhead), event timing off
+    import ctypes as C
+    from stochasticdecomposition_b200._abi import CCut, _pf64, _pi32
+    t.set_timing(False)
+    beta = np.zeros(prob.prevCols + 1); istar = np.zeros(N + reps + 16, np.int32)
+    cut = CCut(0.0, _pf64(beta), _pi32(istar), 0, 0, 0.0, 0.0)
+    fn, ctx = t.api._fn("sd_cut"), t.ctx
+    xs_c = [np.ascontiguousarray(xs[i]) for i in range(8)]
+    xp = [_pf64(a) for a in xs_c]
+    ref = C.byref(cut)
+    for s in range(5):
+        fn(ctx, xp[s % 8], k, 1, 0.0, ref)
+    w = []
+    for s in range(reps * 3):
+        t0 = time.perf_counter(); fn(ctx, xp[s % 8], k, 1, 0.0, ref); w.append(time.perf_counter() - t0)
+    out["cut_wall_us_raw_c_call"] = round(float(np.median(w)) * 1e6, 1)
+    t.set_timing(True)
     out["launches_per_cut"] = t.stats()["last_cut_launches"]
     out["sweep_GBps"] = round(8 * D * N / (out["sweep_us_istar"] * 1e-6) / 1e9, 1)
     its = []
