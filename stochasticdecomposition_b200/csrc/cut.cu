@@ -629,9 +629,13 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	}
 	for (int c = tid; c <= a.n1 + 3; c += blockDim.x) s_cut[c] = 0.0;
 	__syncthreads();
+	// CCols are distinct columns, so the sigma.piC scatter is conflict free and runs one thread per column (a serial loop here
+	// costs one uncached index load per column: 45 us at n1c = 89); the few delta.piC columns may coincide with them and
+	// with each other, so they follow in q order, exactly the order of cuts.c:155-157 / :165-167 for every position
+	for (int k = tid; k < a.n1c; k += blockDim.x) s_cut[a.CCols[k]] = __dadd_rn(0.0, s_tot[4 + k]);
+	__syncthreads();
 	if (tid == 0) {
 		s_cut[0] = s_tot[0];
-		for (int k = 0; k < a.n1c; k++) s_cut[a.CCols[k]] = __dadd_rn(s_cut[a.CCols[k]], s_tot[4 + k]);
 		for (int q = 0; q < a.Q; q++) s_cut[a.qCols[q]] = __dadd_rn(s_cut[a.qCols[q]], s_tot[4 + a.n1c + q]);
 		s_cut[a.n1 + 1] = s_tot[1]; s_cut[a.n1 + 2] = s_tot[2]; s_cut[a.n1 + 3] = s_tot[3];
 	}
@@ -831,17 +835,21 @@ __global__ void __launch_bounds__(512) k_reform(ReformArgs a) {
 		s_fin[2 + tid] = t;
 	}
 	__syncthreads();
-	if (tid == 0) {                 // optimal.c:197-199 (zero), :218-221 (scatter), :228-235 (average, lower-bound share)
-		double *beta = s_fin + 2 + nc;
-		double *out = a.out + ((size_t) rep * a.nCuts + cut) * (a.n1 + 2);
-		for (int i = 0; i <= a.n1; i++) beta[i] = 0.0;
-		for (int k = 0; k < a.n1c; k++) beta[a.CCols[k]] = __dadd_rn(beta[a.CCols[k]], s_fin[2 + k]);
+	// optimal.c:197-199 (zero), :218-221 (scatter: distinct CCols in parallel, then the delta.piC columns in order), :228-235
+	double *beta = s_fin + 2 + nc;
+	double *out = a.out + ((size_t) rep * a.nCuts + cut) * (a.n1 + 2);
+	for (int i = tid; i <= a.n1; i += blockDim.x) beta[i] = 0.0;
+	__syncthreads();
+	for (int k = tid; k < a.n1c; k += blockDim.x) beta[a.CCols[k]] = __dadd_rn(0.0, s_fin[2 + k]);
+	__syncthreads();
+	if (tid == 0) {
 		for (int q = 0; q < a.Q; q++) beta[a.qCols[q]] = __dadd_rn(beta[a.qCols[q]], s_fin[2 + a.n1c + q]);
-		for (int i = 0; i <= a.n1; i++) out[1 + i] = beta[i] / (double) a.k;
 		double al = s_fin[0] / (double) a.k;
 		if (a.lbType == 1) al = __dadd_rn(al, __dmul_rn(__dsub_rn(1.0, s_fin[1] / (double) a.k), (double) a.lb));
 		out[0] = al;
 	}
+	__syncthreads();
+	for (int i = tid; i <= a.n1; i += blockDim.x) out[1 + i] = beta[i] / (double) a.k;
 }
 
 // raw feasibility cuts (cuts.c:478-486): one thread per (observation, infeasible basis) pair, the scatter into beta done

@@ -199,9 +199,17 @@ __device__ __forceinline__ void sd_delta_cell(int Rb, int Q, const int32_t *__re
 		const int32_t *__restrict__ cListStart, const int32_t *__restrict__ cList, LamAt lamAt, OmAt omAt,
 		double *__restrict__ out, size_t planeStride) {
 	double s = 0.0;
-	for (int j = 0; j < Rb; j++) {
-		int p = bLamPos[j];
-		s += omAt(j) * (p >= 0 ? lamAt(p) : 0.0);
+	int j = 0;
+	for (; j + 8 <= Rb; j += 8) {            // operands of eight terms fetched together, the sum still strictly in index order
+		double ov[8], lv[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) { const int p = bLamPos[j + u]; ov[u] = omAt(j + u); lv[u] = p >= 0 ? lamAt(p) : 0.0; }
+#pragma unroll
+		for (int u = 0; u < 8; u++) s = __dadd_rn(s, __dmul_rn(ov[u], lv[u]));
+	}
+	for (; j < Rb; j++) {
+		const int p = bLamPos[j];
+		s = __dadd_rn(s, __dmul_rn(omAt(j), p >= 0 ? lamAt(p) : 0.0));
 	}
 	out[0] = s;
 	for (int c = 0; c < Q; c++) {
