@@ -476,6 +476,38 @@ struct MergeArgs {
 
 #define MG_THREADS SD_TILE_W
 
+#ifdef SD_PHASE_CLOCKS
+__device__ long long g_sd_phase[16];
+#define SD_PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sd_phase[i] = clock64(); } while (0)
+extern "C" int sdgpu_debug_phase_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_sd_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -2; }
+#else
+#define SD_PHASE(i)
+#endif
+
+// running (max, first index) over the per-chunk partial maxima of one observation, chunks in ascending basis order; the
+// loads of 8 chunks are issued together (the compare chain is sequential, the memory latency must not be)
+__device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int nChunks, int64_t NP,
+		double &bestV, int &bestI) {
+	for (int c = 0; c < nChunks; c += 16) {
+		double v[16]; int ix[16];
+#pragma unroll
+		for (int u = 0; u < 16; u++) {                       // past the end: re-read the last chunk, it cannot beat itself under strict '>'
+			const int cc = min(c + u, nChunks - 1);
+			v[u] = __ldcg(pv + (size_t) cc * NP); ix[u] = __ldcg(pi + (size_t) cc * NP);
+		}
+#pragma unroll
+		for (int u = 0; u < 16; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
+	}
+}
+
+#ifdef SD_PHASE_CLOCKS
+__device__ long long g_sd_phase[16];
+#define SD_PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sd_phase[i] = clock64(); } while (0)
+extern "C" int sdgpu_debug_phase_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_sd_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -2; }
+#else
+#define SD_PHASE(i)
+#endif
+
 // running (max, first index) over the per-chunk partial maxima of one observation, chunks in ascending basis order; the
 // loads of 8 chunks are issued together (the compare chain is sequential, the memory latency must not be)
 __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int nChunks, int64_t NP,
@@ -508,6 +540,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	double oldV = -DBL_MAX, newV = -DBL_MAX;
 	int oldI = -1, newI = -1, istar = -1, wgt = 0;
 	double tAlpha = 0.0, tOld = 0.0, tAll = 0.0, tMiss = 0.0;
+	SD_PHASE(0);
 	if (valid) {
 		sd_merge_chunks(a.partV + o, a.partI + o, a.nChunks, a.NP, oldV, oldI);
 		wgt = a.omegaW[o];
@@ -538,6 +571,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 			}
 		}
 	}
+	SD_PHASE(1);
 	s_istar[tid] = valid ? istar : -1;
 	s_w[tid] = wgt;
 	double *out = a.tilePart + (size_t) tile * a.P;
@@ -546,6 +580,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	r = sd_block_sum(tOld, s_red);   if (tid == 0) out[1] = r;
 	r = sd_block_sum(tAll, s_red);   if (tid == 0) out[2] = r;
 	r = sd_block_sum(tMiss, s_red);  if (tid == 0) out[3] = r;
+	SD_PHASE(2);
 
 	// delta.piC part of beta: one block sum per random T element   cuts.c:156-157 / :166-167
 	for (int q = 0; q < a.Q; q++) {
@@ -566,6 +601,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 
 	// sigma.piC part of beta: thread (group g, column k) walks the observations of its group in order   cuts.c:154-155 / :164-165
 	__syncthreads();
+	SD_PHASE(3);
 	if (a.n1c > 0) {
 		const int kp = ((a.n1c + 31) / 32) * 32;
 		const int groups = max(1, MG_THREADS / kp);
@@ -610,7 +646,9 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 
 	// ---- epilogue: the last tile to finish sums the tile partials in tile order (cuts.c:155-167) and, on a single GPU,
 	// applies cuts.c:184-188 and hands the cut to the host through mapped pinned memory
+	SD_PHASE(4);
 	if (!sd_is_last_block(&a.st->cutTicket)) return;
+	SD_PHASE(5);
 	double *s_tot = s_dyn;                                   // [P], then the cut vector [n1+4]
 	double *s_cut = s_dyn + a.P;
 	const int nT = gridDim.x;
@@ -645,6 +683,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		if (a.fuseNormalise) a.hostRes[c] = (c <= a.n1) ? s_cut[c] / a.numSamples : s_cut[c];
 	}
 	if (a.fuseNormalise) __threadfence_system();
+	SD_PHASE(6);
 }
 
 // cuts.c:184-188
@@ -922,7 +961,8 @@ static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks
 	int64_t target = (int64_t) smCount * 4 * 3;
 	int64_t want = std::max<int64_t>(1, (target + tiles - 1) / tiles);
 	want = std::min<int64_t>(want, c->maxChunks);
-	want = std::min<int64_t>(want, std::max<int64_t>(1, (c->basisCnt + 15) / 16));   // at least two load batches per chunk
+	want = std::min<int64_t>(want, std::max<int64_t>(1, (c->basisCnt + 31) / 32));   // at least four load batches per chunk: the merge
+	                                                                                 // kernel pays ~0.3 us of latency per 16 chunks and window
 	int cs = (int) ((c->basisCnt + want - 1) / want);
 	cs = std::max(cs, 1);
 	*chunkSize = cs;
