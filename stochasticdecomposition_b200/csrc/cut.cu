@@ -485,7 +485,7 @@ extern "C" int sdgpu_debug_phase_clocks(long long *out) { return cudaMemcpyFromS
 #endif
 
 // running (max, first index) over the per-chunk partial maxima of one observation, chunks in ascending basis order; the
-// loads of 8 chunks are issued together (the compare chain is sequential, the memory latency must not be)
+// loads of 16 chunks are issued together (the compare chain is sequential, the memory latency must not be)
 __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int nChunks, int64_t NP,
 		double &bestV, int &bestI) {
 	for (int c = 0; c < nChunks; c += 16) {
@@ -497,32 +497,6 @@ __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, c
 		}
 #pragma unroll
 		for (int u = 0; u < 16; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
-	}
-}
-
-#ifdef SD_PHASE_CLOCKS
-__device__ long long g_sd_phase[16];
-#define SD_PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sd_phase[i] = clock64(); } while (0)
-extern "C" int sdgpu_debug_phase_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_sd_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -2; }
-#else
-#define SD_PHASE(i)
-#endif
-
-// running (max, first index) over the per-chunk partial maxima of one observation, chunks in ascending basis order; the
-// loads of 8 chunks are issued together (the compare chain is sequential, the memory latency must not be)
-__device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int nChunks, int64_t NP,
-		double &bestV, int &bestI) {
-	int c = 0;
-	for (; c + 8 <= nChunks; c += 8) {
-		double v[8]; int ix[8];
-#pragma unroll
-		for (int u = 0; u < 8; u++) { v[u] = __ldcg(pv + (size_t) (c + u) * NP); ix[u] = __ldcg(pi + (size_t) (c + u) * NP); }
-#pragma unroll
-		for (int u = 0; u < 8; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
-	}
-	for (; c < nChunks; c++) {
-		double v = __ldcg(pv + (size_t) c * NP);
-		if (v > bestV) { bestV = v; bestI = __ldcg(pi + (size_t) c * NP); }
 	}
 }
 
