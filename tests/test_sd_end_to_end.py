@@ -28,7 +28,7 @@ def _lockstep(apis, shape, K, rtol, seed=3):
 
 
 @pytest.mark.skipif(not oracle_loader.have_reference(), reason="reference build unavailable")
-@pytest.mark.parametrize("shape,K", [("pgp2", 150), ("20term", 40)])
+@pytest.mark.parametrize("shape,K", [("pgp2", 150), ("20term", 40), ("20term_T", 40)])
 def test_reference_and_port_agree_over_a_whole_run(shape, K):
     _lockstep([oracle_loader.reference(), oracle_loader.oracle()], shape, K, rtol=0.0)
 
@@ -43,14 +43,14 @@ def test_sd_converges_on_pgp2_shape():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,K", [("pgp2", 300), ("20term", 120), ("ssn", 120)])
+@pytest.mark.parametrize("shape,K", [("pgp2", 300), ("20term", 120), ("20term_T", 120), ("ssn", 120)])
 def test_cuda_and_port_agree_over_a_whole_run(shape, K):
     import stochasticdecomposition_b200 as sd
     _lockstep([sd.load_library(), oracle_loader.oracle()], shape, K, rtol=1e-9)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,K", [("pgp2", 300), ("ssn", 100)])
+@pytest.mark.parametrize("shape,K", [("pgp2", 300), ("20term_T", 100), ("ssn", 100)])
 def test_independent_runs_reach_the_same_incumbent(shape, K):
     import stochasticdecomposition_b200 as sd
     out = []

@@ -62,9 +62,9 @@ class SyntheticSLP:
     W = [W0 | I | -I] (penalised slack / surplus columns => every subproblem is feasible and bounded below by 0; the
     penalties dominate c, so the problem is bounded)."""
 
-    def __init__(self, seed: int, n1: int, rows: int, core_cols: int, R: int, levels: int = 0, density: float = 0.08):
+    def __init__(self, seed: int, n1: int, rows: int, core_cols: int, R: int, levels: int = 0, density: float = 0.08, Q: int = 0):
         rng = np.random.default_rng(seed)
-        self.n1, self.rows, self.R, self.levels = n1, rows, R, levels
+        self.n1, self.rows, self.R, self.levels, self.Q = n1, rows, R, levels, Q
         self.c = rng.uniform(0.5, 1.5, n1)
         self.xu = np.full(n1, 10.0)
         self.budget = 2.5 * n1
@@ -83,6 +83,12 @@ class SyntheticSLP:
         self.rbar = rng.uniform(2.0, 6.0, rows)
         self.rv_rows = np.sort(rng.choice(rows, size=R, replace=False))      # 0-based rows with a random right-hand side
         self.scale = rng.uniform(0.5, 2.0, R)
+        # Q random technology-matrix elements T[r_e][c_e] + dT_e(w), on rows that already carry a random right-hand side
+        tr = rng.choice(self.rv_rows, size=Q, replace=True) if Q else np.zeros(0, np.int64)
+        tc = rng.choice(n1, size=Q, replace=False) if Q else np.zeros(0, np.int64)
+        order = np.lexsort((tr, tc))
+        self.t_rows, self.t_cols = tr[order], tc[order]
+        self.t_scale = rng.uniform(0.05, 0.3, Q)
         if levels:
             self.level_vals = np.sort(rng.uniform(-1.0, 1.0, (R, levels)), axis=1)
             self.level_vals -= self.level_vals.mean(axis=1, keepdims=True)   # zero mean: observations are deviations (algo.c:148-149)
@@ -92,9 +98,11 @@ class SyntheticSLP:
         """one observation of the random right-hand side, as a deviation from its mean, 1-based"""
         if self.levels:
             w = self.level_vals[np.arange(self.R), rng.integers(0, self.levels, self.R)] * self.scale
+            wt = (rng.integers(0, self.levels, self.Q) - (self.levels - 1) / 2.0) / max(1, self.levels - 1) * 2.0 * self.t_scale
         else:
             w = rng.uniform(-1.0, 1.0, self.R) * self.scale
-        return np.concatenate([[0.0], w])
+            wt = rng.uniform(-1.0, 1.0, self.Q) * self.t_scale
+        return np.concatenate([[0.0], w, wt])
 
     def problem(self) -> Problem:
         """numType / coordType / bBar / Cbar as the tables want them (1-based)"""
@@ -105,15 +113,17 @@ class SyntheticSLP:
         tr, tc = tr[order], tc[order]
         rvrows = self.rv_rows + 1
         return Problem(rows=self.rows, cols=self.cols, prevCols=self.n1, CCols=one(cc, np.int32), rvRows=one(rvrows, np.int32),
-                       rvbOmRows=one(rvrows, np.int32), rvCOmCols=one([], np.int32), rvCOmRows=one([], np.int32), rvCols=one([], np.int32),
+                       rvbOmRows=one(rvrows, np.int32), rvCOmCols=one(self.t_cols + 1, np.int32), rvCOmRows=one(self.t_rows + 1, np.int32),
+                       rvCols=one(self.t_cols + 1, np.int32),
                        bBar_col=one(np.arange(1, self.rows + 1), np.int32), bBar_val=one(self.rbar, np.float64),
                        Cbar_col=one(tc + 1, np.int32), Cbar_row=one(tr + 1, np.int32), Cbar_val=one(self.T[tr, tc], np.float64),
-                       rvdOmCnt=0, rvOffset=(0, self.R, self.R))
+                       rvdOmCnt=0, rvOffset=(0, self.R, self.R + self.Q))
 
 
 SHAPES = {
     "pgp2": dict(n1=4, rows=7, core_cols=9, R=3, levels=4, density=0.5),
     "20term": dict(n1=63, rows=124, core_cols=516, R=40, levels=2, density=0.06),
+    "20term_T": dict(n1=63, rows=124, core_cols=516, R=40, levels=3, density=0.06, Q=8),     # RHS + technology-matrix randomness
     "ssn": dict(n1=89, rows=175, core_cols=356, R=86, levels=5, density=0.05),
     "storm": dict(n1=121, rows=528, core_cols=203, R=118, levels=5, density=0.02),
 }
@@ -160,10 +170,12 @@ class Subproblem:
         self.solves = 0
 
     def solve(self, x: np.ndarray, w: np.ndarray):
-        """x: first-stage point [n1]; w: observation deviations [R].  Returns (objective, row duals pi 1-based [rows+1])."""
+        """x: first-stage point [n1]; w: observation deviations [R + Q].  Returns (objective, row duals pi 1-based [rows+1])."""
         slp = self.slp
-        rhs = slp.rbar - slp.T @ x
-        rhs[slp.rv_rows] += w
+        rhs = slp.rbar - slp.T @ x                                  # computeRHS subprob.c:96-128
+        rhs[slp.rv_rows] += w[:slp.R]
+        for e in range(slp.Q):
+            rhs[slp.t_rows[e]] -= w[slp.R + e] * x[slp.t_cols[e]]
         for i in range(slp.rows):
             self.h.changeRowBounds(i, rhs[i], rhs[i])
         self.h.run()
