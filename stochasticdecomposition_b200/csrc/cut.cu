@@ -944,10 +944,12 @@ static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks
 }
 
 template <int ROWS, int STAGES, int CTAS>
-static int sd_launch_tma_cfg(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
+static int sd_launch_tma_cfg(sdgpu_ctx *c, dim3 grid, const SweepArgs &a, int slot) {
 	const size_t smem = (size_t) STAGES * ROWS * TMA_ROW_BYTES + 2 * STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int));
-	static bool attrSet = false;
-	if (!attrSet) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma<ROWS, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attrSet = true; }
+	if (!c->tmaAttrSet[slot]) {             // the attribute is per device: remember it per context, not per process
+		SD_CUDA(cudaFuncSetAttribute(k_sweep_tma<ROWS, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		c->tmaAttrSet[slot] = true;
+	}
 	k_sweep_tma<ROWS, STAGES, CTAS><<<grid, TMA_THREADS, smem, c->stream>>>(a);
 	return 0;
 }
@@ -958,11 +960,11 @@ static int sd_launch_tma(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 	switch (cfg) {
 	// measured on B200, 65 536 x 131 072 (profiles/r01_tma_cfg_sweep.jsonl): <8,2,3> 6.87 TB/s, <8,3,2> 6.73, <4,4,3> 6.67,
 	// <4,3,4> 6.62, <8,4,1> 5.71; the LDG variant 6.4-6.5
-	case 1: return sd_launch_tma_cfg<8, 3, 2>(c, grid, a);
-	case 2: return sd_launch_tma_cfg<4, 4, 3>(c, grid, a);
-	case 3: return sd_launch_tma_cfg<8, 4, 1>(c, grid, a);
-	case 4: return sd_launch_tma_cfg<4, 3, 4>(c, grid, a);
-	default: return sd_launch_tma_cfg<8, 2, 3>(c, grid, a);
+	case 1: return sd_launch_tma_cfg<8, 3, 2>(c, grid, a, 1);
+	case 2: return sd_launch_tma_cfg<4, 4, 3>(c, grid, a, 2);
+	case 3: return sd_launch_tma_cfg<8, 4, 1>(c, grid, a, 3);
+	case 4: return sd_launch_tma_cfg<4, 3, 4>(c, grid, a, 4);
+	default: return sd_launch_tma_cfg<8, 2, 3>(c, grid, a, 0);
 	}
 }
 
@@ -971,8 +973,7 @@ static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 	int rps = 8;
 	while (rps > 1 && rps * planes > 8) rps >>= 1;                    // stage near 32 KiB
 	const size_t smem = (size_t) 2 * rps * planes * TMA_ROW_BYTES + 4 * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int)) + 64 * sizeof(double);
-	static size_t attrMax = 0;
-	if (smem > attrMax) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attrMax = smem; }
+	if (smem > c->tmaQAttr) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaQAttr = smem; }
 	k_sweep_tma_q<<<grid, TMA_THREADS, smem, c->stream>>>(a, rps);
 	return 0;
 }

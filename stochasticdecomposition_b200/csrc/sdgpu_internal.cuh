@@ -132,6 +132,8 @@ struct sdgpu_ctx {
 	int32_t *h_iStar = nullptr;      // pinned + mapped [iStarHostCap]: the merge kernel mirrors iStar here for small N
 	int32_t *d_iStarHost = nullptr;  // device alias
 	int64_t  iStarHostCap = 0;
+	bool     tmaAttrSet[8] = {false, false, false, false, false, false, false, false};   // per context (= per device): opt-in shared memory sizes
+	size_t   tmaQAttr = 0;
 	bool     cutFused = false;       // the last merge block already normalised the cut into h_cutRes
 
 	// host mirrors (bookkeeping only; no table arithmetic happens on the host)

@@ -62,3 +62,36 @@ def test_independent_runs_reach_the_same_incumbent(shape, K):
     assert abs(a.incumb_est - b.incumb_est) <= 1e-9 * max(abs(b.incumb_est), 1e-300), (a.incumb_est, b.incumb_est)
     assert np.abs(a.incumbX - b.incumbX).max() <= 1e-9 * max(np.abs(b.incumbX).max(), 1e-300)
     assert a.lp_solves == b.lp_solves and a.incumbent_changes == b.incumbent_changes
+
+
+@pytest.mark.parametrize("shape", ["pgp2", "20term_T"])
+def test_stoch_check_invariants_against_the_lp(shape):
+    """The reference's STOCH_CHECK blocks (cuts.c:64-76, subprob.c:75-80), as assertions: with the tables an SD run has
+    built, the argmax value of ANY stored observation at x is a lower bound on the true recourse value h(x, w) (LP solved
+    here), it is attained (equality) for the observation / x pair whose dual vertex was just stored, and the cut height at x
+    is the weighted mean of those argmax values.  This checks the path against the LP itself, not against another
+    implementation of the path."""
+    K = 80
+    slp = make_slp(shape)
+    t = oracle_loader.oracle().create(slp.problem(), caps_for(K))
+    host = SDHost(slp, t, seed=11)
+    host.run(K)
+    x1 = host.candidX
+    # a fresh solve at (x, last observation), stored through the normal update path -> its estimate must equal the LP objective
+    last = len(host.obs_store) - 1
+    obj, pi = host.sub.solve(x1[1:], host.obs_store[last][1:])
+    t.stochastic_updates(last, False, pi, 0.0, host.k, 1e-3)
+    istar, val = t.compute_istar(x1, last, host.k, 0, 0)
+    assert istar >= 0 and abs(val - obj) <= 1e-7 * max(1.0, abs(obj)), (val, obj)
+    # every stored observation: argmax value <= true recourse value
+    vals, ws = [], []
+    for o in range(len(host.obs_store)):
+        true_obj, _ = host.sub.solve(x1[1:], host.obs_store[o][1:])
+        _, v = t.compute_istar(x1, o, host.k, 0, 0)
+        assert v <= true_obj + 1e-6 * max(1.0, abs(true_obj)), (o, v, true_obj)
+        vals.append(v); ws.append(t.get_omega(o)[1])
+    # the cut at x, evaluated at x, is the weight-averaged argmax value (cuts.c:142-168,184-188)
+    cut = t.sd_cut(x1, host.k, 0, 0.0)
+    height = cut.alpha - float(np.dot(cut.beta[1:], x1[1:]))
+    mean = float(np.dot(vals, ws)) / host.k
+    assert abs(height - mean) <= 1e-9 * max(1.0, abs(mean)), (height, mean)
