@@ -17,10 +17,18 @@ import oracle_loader  # noqa: E402
 from sd_highs_host import Lockstep, SDHost, caps_for, make_slp  # noqa: E402
 
 
+def _caps(slp, K):
+    from stochasticdecomposition_b200._abi import Caps
+    if not slp.rvd:
+        return caps_for(K)
+    n = (1 + slp.rvd) * 2 * K + 8                         # every solve may add 1 + phiLength lambda / sigma rows
+    return Caps(n, n, 2 * K + 2, K + 1, 1 + slp.rvd)
+
+
 def _lockstep(apis, shape, K, rtol, seed=3):
     slp = make_slp(shape)
     prob = slp.problem()
-    tabs = Lockstep([a.create(prob, caps_for(K)) for a in apis], rtol=rtol)
+    tabs = Lockstep([a.create(prob, _caps(slp, K)) for a in apis], rtol=rtol)
     host = SDHost(slp, tabs, seed=seed)
     st = host.run(K)
     assert tabs.checked >= K
@@ -28,7 +36,7 @@ def _lockstep(apis, shape, K, rtol, seed=3):
 
 
 @pytest.mark.skipif(not oracle_loader.have_reference(), reason="reference build unavailable")
-@pytest.mark.parametrize("shape,K", [("pgp2", 150), ("20term", 40), ("20term_T", 40)])
+@pytest.mark.parametrize("shape,K", [("pgp2", 150), ("20term", 40), ("20term_T", 40), ("randcost_small", 70)])
 def test_reference_and_port_agree_over_a_whole_run(shape, K):
     _lockstep([oracle_loader.reference(), oracle_loader.oracle()], shape, K, rtol=0.0)
 
@@ -43,7 +51,7 @@ def test_sd_converges_on_pgp2_shape():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,K", [("pgp2", 300), ("20term", 120), ("20term_T", 120), ("ssn", 120)])
+@pytest.mark.parametrize("shape,K", [("pgp2", 300), ("20term", 120), ("20term_T", 120), ("ssn", 120), ("randcost_small", 150)])
 def test_cuda_and_port_agree_over_a_whole_run(shape, K):
     import stochasticdecomposition_b200 as sd
     _lockstep([sd.load_library(), oracle_loader.oracle()], shape, K, rtol=1e-9)
@@ -64,7 +72,7 @@ def test_independent_runs_reach_the_same_incumbent(shape, K):
     assert a.lp_solves == b.lp_solves and a.incumbent_changes == b.incumbent_changes
 
 
-@pytest.mark.parametrize("shape", ["pgp2", "20term_T"])
+@pytest.mark.parametrize("shape", ["pgp2", "20term_T", "randcost_small"])
 def test_stoch_check_invariants_against_the_lp(shape):
     """The reference's STOCH_CHECK blocks (cuts.c:64-76, subprob.c:75-80), as assertions: with the tables an SD run has
     built, the argmax value of ANY stored observation at x is a lower bound on the true recourse value h(x, w) (LP solved
@@ -73,14 +81,18 @@ def test_stoch_check_invariants_against_the_lp(shape):
     implementation of the path."""
     K = 80
     slp = make_slp(shape)
-    t = oracle_loader.oracle().create(slp.problem(), caps_for(K))
+    t = oracle_loader.oracle().create(slp.problem(), _caps(slp, K + 1))
     host = SDHost(slp, t, seed=11)
     host.run(K)
     x1 = host.candidX
     # a fresh solve at (x, last observation), stored through the normal update path -> its estimate must equal the LP objective
     last = len(host.obs_store) - 1
     obj, pi = host.sub.solve(x1[1:], host.obs_store[last][1:])
-    t.stochastic_updates(last, False, pi, 0.0, host.k, 1e-3)
+    if slp.rvd:
+        host.random_cost_updates(last, False, pi)
+        assert any(len(b) for b in [host.basis_keys]) and t.counts()["sigma"] > t.counts()["basis"]      # phi columns were stored
+    else:
+        t.stochastic_updates(last, False, pi, 0.0, host.k, 1e-3)
     istar, val = t.compute_istar(x1, last, host.k, 0, 0)
     assert istar >= 0 and abs(val - obj) <= 1e-7 * max(1.0, abs(obj)), (val, obj)
     # every stored observation: argmax value <= true recourse value

@@ -62,9 +62,10 @@ class SyntheticSLP:
     W = [W0 | I | -I] (penalised slack / surplus columns => every subproblem is feasible and bounded below by 0; the
     penalties dominate c, so the problem is bounded)."""
 
-    def __init__(self, seed: int, n1: int, rows: int, core_cols: int, R: int, levels: int = 0, density: float = 0.08, Q: int = 0):
+    def __init__(self, seed: int, n1: int, rows: int, core_cols: int, R: int, levels: int = 0, density: float = 0.08, Q: int = 0,
+                 rvd: int = 0):
         rng = np.random.default_rng(seed)
-        self.n1, self.rows, self.R, self.levels, self.Q = n1, rows, R, levels, Q
+        self.n1, self.rows, self.R, self.levels, self.Q, self.rvd = n1, rows, R, levels, Q, rvd
         self.c = rng.uniform(0.5, 1.5, n1)
         self.xu = np.full(n1, 10.0)
         self.budget = 2.5 * n1
@@ -89,6 +90,9 @@ class SyntheticSLP:
         order = np.lexsort((tr, tc))
         self.t_rows, self.t_cols = tr[order], tc[order]
         self.t_scale = rng.uniform(0.05, 0.3, Q)
+        # rvd random cost coefficients d_j + dd_j(w) on core columns (the v2.0 "randCost" path, randCost.c); |dd| < min d
+        self.d_cols = np.sort(rng.choice(core_cols, size=rvd, replace=False)) if rvd else np.zeros(0, np.int64)
+        self.d_scale = rng.uniform(0.2, 0.6, rvd)
         if levels:
             self.level_vals = np.sort(rng.uniform(-1.0, 1.0, (R, levels)), axis=1)
             self.level_vals -= self.level_vals.mean(axis=1, keepdims=True)   # zero mean: observations are deviations (algo.c:148-149)
@@ -99,10 +103,12 @@ class SyntheticSLP:
         if self.levels:
             w = self.level_vals[np.arange(self.R), rng.integers(0, self.levels, self.R)] * self.scale
             wt = (rng.integers(0, self.levels, self.Q) - (self.levels - 1) / 2.0) / max(1, self.levels - 1) * 2.0 * self.t_scale
+            wd = (rng.integers(0, self.levels, self.rvd) - (self.levels - 1) / 2.0) / max(1, self.levels - 1) * 2.0 * self.d_scale
         else:
             w = rng.uniform(-1.0, 1.0, self.R) * self.scale
             wt = rng.uniform(-1.0, 1.0, self.Q) * self.t_scale
-        return np.concatenate([[0.0], w, wt])
+            wd = rng.uniform(-1.0, 1.0, self.rvd) * self.d_scale
+        return np.concatenate([[0.0], w, wt, wd])
 
     def problem(self) -> Problem:
         """numType / coordType / bBar / Cbar as the tables want them (1-based)"""
@@ -117,7 +123,11 @@ class SyntheticSLP:
                        rvCols=one(self.t_cols + 1, np.int32),
                        bBar_col=one(np.arange(1, self.rows + 1), np.int32), bBar_val=one(self.rbar, np.float64),
                        Cbar_col=one(tc + 1, np.int32), Cbar_row=one(tr + 1, np.int32), Cbar_val=one(self.T[tr, tc], np.float64),
-                       rvdOmCnt=0, rvOffset=(0, self.R, self.R + self.Q))
+                       rvdOmCnt=self.rvd, rvOffset=(0, self.R, self.R + self.Q))
+
+    def cost_coords(self):
+        """coord->rvdOmCols (1-based) and the row senses prob->sp->senx, for checkBasisFeasibility (randCost.c:202)"""
+        return np.concatenate([[0], self.d_cols + 1]).astype(np.int32), b"E" * self.rows
 
 
 SHAPES = {
@@ -126,6 +136,7 @@ SHAPES = {
     "20term_T": dict(n1=63, rows=124, core_cols=516, R=40, levels=3, density=0.06, Q=8),     # RHS + technology-matrix randomness
     "ssn": dict(n1=89, rows=175, core_cols=356, R=86, levels=5, density=0.05),
     "storm": dict(n1=121, rows=528, core_cols=203, R=118, levels=5, density=0.02),
+    "randcost_small": dict(n1=8, rows=14, core_cols=24, R=8, levels=3, density=0.3, Q=2, rvd=3),   # storm-style random cost, small enough for tests
 }
 
 
@@ -176,6 +187,8 @@ class Subproblem:
         rhs[slp.rv_rows] += w[:slp.R]
         for e in range(slp.Q):
             rhs[slp.t_rows[e]] -= w[slp.R + e] * x[slp.t_cols[e]]
+        for j in range(slp.rvd):                                    # computeCostCoeff subprob.c:131-168
+            self.h.changeColCost(int(slp.d_cols[j]), float(slp.d[slp.d_cols[j]] + w[slp.R + slp.Q + j]))
         for i in range(slp.rows):
             self.h.changeRowBounds(i, rhs[i], rhs[i])
         self.h.run()
@@ -185,6 +198,37 @@ class Subproblem:
         sol = self.h.getSolution()
         pi = np.concatenate([[0.0], np.asarray(sol.row_dual)])
         return self.h.getInfo().objective_function_value, pi
+
+
+def basis_info(sub: "Subproblem", wd: np.ndarray, pi: np.ndarray):
+    """What newBasis / calcBasis / decomposeDualSolution (randCost.c:19-200) extract from the solver after a solve with random
+    costs: the basis code, for every BASIC column with a random cost its row of the basis inverse (phi) and its position in
+    the cost block (omegaIdx), the deterministic part of the dual (piDet = pi - sum phi * dd), the deterministic reduced costs
+    (gBar), the tableau entries of the phi rows (psi) and the column statuses.  wd = this observation's cost deltas [rvd]."""
+    slp, h = sub.slp, sub.h
+    rows, cols = slp.rows, slp.cols
+    b = h.getBasis()
+    cstat = np.array([int(v) for v in b.col_status], np.int32)
+    rstat = np.array([int(v) for v in b.row_status], np.int32)
+    key = (cstat.tobytes(), rstat.tobytes())                        # encodeIntvec of cstat / rstat (randCost.c:171-172)
+    head = h.getBasicVariables()[1]
+    phis, om, heads = [], [], []
+    for i, col in enumerate(slp.d_cols):                            # randCost.c:36-49
+        pos = np.nonzero(head == col)[0]
+        if len(pos):
+            phis.append(np.concatenate([[0.0], h.getBasisInverseRow(int(pos[0]))[1]]))
+            om.append(i + 1); heads.append(int(pos[0]))
+    piDet = pi.copy()                                               # decomposeDualSolution randCost.c:182-200
+    for n, ph in enumerate(phis):
+        piDet[1:] -= ph[1:] * wd[om[n] - 1]
+    basic_cost = np.array([slp.d[c] if c >= 0 else 0.0 for c in head])
+    gBar = np.zeros(cols + 1); psi = np.zeros((cols, len(phis)))
+    for i in range(cols):                                           # randCost.c:78-89
+        colv = h.getReducedColumn(i)[1]
+        gBar[i + 1] = slp.d[i] - float(np.dot(colv, basic_cost))
+        for n, p in enumerate(heads):
+            psi[i, n] = colv[p]
+    return dict(key=key, phi=phis, omegaIdx=om, piDet=piDet, gBar=gBar, psi=psi, cstat=np.concatenate([[0], cstat]).astype(np.int32))
 
 
 @dataclass
@@ -323,6 +367,25 @@ class Lockstep:
     def counts(self):
         return self._same([t.counts() for t in self.b], "counts")
 
+    def _all(self, name, *a, **kw):
+        outs = [getattr(t, name)(*a, **kw) for t in self.b]
+        for o in outs[1:]:
+            if isinstance(outs[0], np.ndarray):
+                assert np.array_equal(o, outs[0]), f"{name}: backends disagree"
+            elif isinstance(outs[0], tuple) and len(outs[0]) == 2 and isinstance(outs[0][1], float):
+                assert o[0] == outs[0][0] and (o[0] < 0 or abs(o[1] - outs[0][1]) <= max(self.rtol, 1e-15) * max(abs(outs[0][1]), 1e-300)), (name, o, outs[0])
+            else:
+                assert o == outs[0], f"{name}: backends disagree: {outs}"
+        return outs[0]
+
+    def calc_delta(self, *a): return self._all("calc_delta", *a)
+    def set_cost_coords(self, *a): return self._all("set_cost_coords", *a)
+    def basis_set_feas_data(self, *a): return self._all("basis_set_feas_data", *a)
+    def check_feasibility_obs(self, *a): return self._all("check_feasibility_obs", *a)
+    def check_feasibility_basis(self, *a): return self._all("check_feasibility_basis", *a)
+    def compute_istar(self, *a): return self._all("compute_istar", *a)
+    def get_omega(self, *a): return self.b[0].get_omega(*a)
+
     def sd_cut(self, X, numSamples, pi_eval_flag, lb):
         cuts = [t.sd_cut(X, numSamples, pi_eval_flag, lb) for t in self.b]
         ref = cuts[0]
@@ -382,6 +445,9 @@ class SDHost:
         self.pi_ratio = np.zeros(self.cfg.SCAN_LEN)
         self.dualStable = False
         self.obs_store: list[np.ndarray] = []                                   # host copy of omega->vals (subprob.c:24 reads it)
+        self.basis_keys: dict = {}                                              # basis code -> basis index (stocUpdate.c:39-53)
+        if slp.rvd:
+            self.t.set_cost_coords(*slp.cost_coords())
         self.stats = RunStats()
 
     # ---- cuts.c:22-89 ------------------------------------------------------------------------------------------
@@ -392,7 +458,10 @@ class SDHost:
         st.subprob_seconds += time.perf_counter() - t0
         st.lp_solves += 1
         t0 = time.perf_counter()
-        bi, bnew = self.t.stochastic_updates(omegaIdx, newOmegaFlag, pi, 0.0, self.k, cfg.TOLERANCE)      # subprob.c:70
+        if slp.rvd:
+            self.random_cost_updates(omegaIdx, newOmegaFlag, pi)
+        else:
+            self.t.stochastic_updates(omegaIdx, newOmegaFlag, pi, 0.0, self.k, cfg.TOLERANCE)             # subprob.c:70
         pi_eval = bool(cfg.DUAL_STABILITY and self.k > cfg.PI_EVAL_START and self.k % cfg.PI_CYCLE == 0)   # cuts.c:112
         cut = self.t.sd_cut(x1, self.k, pi_eval, slp.lb)                                                   # cuts.c:56
         st.argmax_seconds += time.perf_counter() - t0
@@ -407,6 +476,26 @@ class SDHost:
             self.dualStable = bool(_dual_stability(cut.cummOld, cut.cummAll, self.k, cfg.PI_EVAL_START, cfg.SCAN_LEN, self.pi_ratio))
         oc = OneCut(cut.alpha, cut.beta.copy(), self.k, cut.omegaCnt, cut.iStar, ctype)
         return self.add_cut_to_pool(oc, ctype), obj
+
+    # ---- stocUpdate.c:14-133 with random costs: the solver-side extraction stays on the host, everything else is library calls ---
+    def random_cost_updates(self, omegaIdx, newOmegaFlag, pi):
+        cfg, slp, t = self.cfg, self.slp, self.t
+        if newOmegaFlag:                                                         # stocUpdate.c:24-31
+            t.calc_delta(True, omegaIdx)
+            if t.counts()["basis"]:
+                t.check_feasibility_obs(omegaIdx, cfg.TOLERANCE)
+        wd = self.obs_store[omegaIdx][1 + slp.R + slp.Q:]
+        info = basis_info(self.sub, wd, pi)
+        if info["key"] in self.basis_keys:                                       # stocUpdate.c:39-53: basis met before
+            return self.basis_keys[info["key"]], False
+        bi, bnew = t.stochastic_updates(omegaIdx, False, info["piDet"], 0.0, self.k, cfg.TOLERANCE, True, info["phi"], info["omegaIdx"])
+        if bnew:                                                                 # stocUpdate.c:119-127
+            t.basis_set_feas_data(bi, info["piDet"], np.array(info["phi"]) if info["phi"] else None, info["gBar"],
+                                  info["psi"].ravel() if info["phi"] else None, info["cstat"])
+            flags = t.check_feasibility_basis(bi, cfg.TOLERANCE)
+            assert flags[omegaIdx], "a basis must be dual feasible at the observation it is optimal for"
+            self.basis_keys[info["key"]] = bi
+        return bi, bnew
 
     # ---- cuts.c:616-661, 277-360 ----------------------------------------------------------------------------------
     def add_cut_to_pool(self, cut: OneCut, ctype):
