@@ -735,6 +735,7 @@ __global__ void k_cut_heights(int n, const double *__restrict__ alpha, const dou
 		for (int i = 0; i < n; i++) if (Sm < s_h[i]) { Sm = s_h[i]; bi = i; }            // :203-205
 		*best = bi;
 	}
+	__threadfence_system();
 }
 
 struct ReformArgs {
@@ -1179,32 +1180,30 @@ extern "C" int sdgpu_cut_heights(sdgpu_ctx *c, int n, const double *alpha, const
 	if (!c) return sdgpu_fail("null context");
 	if (n <= 0) return SDGPU_NONE;
 	if (!alpha || !beta || !numSamples || !xk) return sdgpu_fail("null argument");
+	if (currIter == 0) return sdgpu_fail("cut_heights: currIter is zero");
 	SD_CUDA(cudaSetDevice(c->device));
+	// inputs and outputs live in one block of mapped pinned memory: the kernel reads and writes it directly (<= ~120 KiB for the
+	// CUT_MULT * n1 + 3 cuts of setup.c:126), so the call is one launch and one wait, no allocation and no copy
 	const size_t n1p = (size_t) c->n1 + 1;
-	size_t nd = (size_t) n * (n1p + 5) + n1p, ni = (size_t) n + 1;
-	double *d_d = nullptr; int32_t *d_i = nullptr;
-	if (cudaMalloc((void **) &d_d, nd * 8) != cudaSuccess || cudaMalloc((void **) &d_i, ni * 4) != cudaSuccess) { if (d_d) cudaFree(d_d); return sdgpu_fail("cut_heights: allocation failed"); }
-	double *d_alpha = d_d, *d_beta = d_alpha + n, *d_ai = d_beta + (size_t) n * n1p, *d_xk = d_ai + n, *d_h = d_xk + n1p, *d_e = d_h + n, *d_r = d_e + n;
-	cudaMemcpyAsync(d_alpha, alpha, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream);
-	cudaMemcpyAsync(d_beta, beta, (size_t) n * n1p * 8, cudaMemcpyHostToDevice, c->stream);
-	if (alphaIncumb) cudaMemcpyAsync(d_ai, alphaIncumb, (size_t) n * 8, cudaMemcpyHostToDevice, c->stream);
-	cudaMemcpyAsync(d_xk, xk, n1p * 8, cudaMemcpyHostToDevice, c->stream);
-	cudaMemcpyAsync(d_i, numSamples, (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
-	k_cut_heights<<<1, 128, (size_t) n * 8, c->stream>>>(n, d_alpha, d_beta, d_i, alphaIncumb ? d_ai : nullptr, currIter, d_xk, c->n1, lb, d_h, d_e, d_r, d_i + n);
+	const size_t nd = (size_t) n * (n1p + 5) + n1p;
+	if (sd_aux_reserve(c, nd * 8 + ((size_t) n + 2) * 4)) return SDGPU_ERR;
+	double *h = reinterpret_cast<double *>(c->h_aux), *d = reinterpret_cast<double *>(c->d_aux);
+	const size_t oAlpha = 0, oBeta = n, oAi = oBeta + (size_t) n * n1p, oXk = oAi + n, oH = oXk + n1p, oE = oH + n, oR = oE + n;
+	int32_t *hi = reinterpret_cast<int32_t *>(h + nd), *di = reinterpret_cast<int32_t *>(d + nd);
+	memcpy(h + oAlpha, alpha, (size_t) n * 8);
+	memcpy(h + oBeta, beta, (size_t) n * n1p * 8);
+	if (alphaIncumb) memcpy(h + oAi, alphaIncumb, (size_t) n * 8);
+	memcpy(h + oXk, xk, n1p * 8);
+	memcpy(hi, numSamples, (size_t) n * 4);
+	k_cut_heights<<<1, 128, (size_t) n * 8, c->stream>>>(n, d + oAlpha, d + oBeta, di, alphaIncumb ? d + oAi : nullptr, currIter, d + oXk, c->n1, lb,
+			d + oH, d + oE, d + oR, di + n);
 	sd_count_launch(c);
-	std::vector<double> hh(n), he(n), hr(n);
-	int32_t best = -1;
-	cudaMemcpyAsync(hh.data(), d_h, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
-	cudaMemcpyAsync(he.data(), d_e, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
-	cudaMemcpyAsync(hr.data(), d_r, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
-	cudaMemcpyAsync(&best, d_i + n, 4, cudaMemcpyDeviceToHost, c->stream);
-	cudaError_t e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_d); cudaFree(d_i);
-	if (e != cudaSuccess) return sdgpu_fail("cut_heights: %s", cudaGetErrorString(e));
-	if (height) memcpy(height, hh.data(), (size_t) n * 8);
-	if (etaCoef) memcpy(etaCoef, he.data(), (size_t) n * 8);
-	if (rhs) memcpy(rhs, hr.data(), (size_t) n * 8);
-	return best;
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	SD_CUDA(cudaGetLastError());
+	if (height) memcpy(height, h + oH, (size_t) n * 8);
+	if (etaCoef) memcpy(etaCoef, h + oE, (size_t) n * 8);
+	if (rhs) memcpy(rhs, h + oR, (size_t) n * 8);
+	return hi[n];
 }
 
 extern "C" int sdgpu_reform_cuts_batch(sdgpu_ctx *c, int nCuts, const int32_t *iStar, int istarStride, const int32_t *omegaCnt,

@@ -457,6 +457,19 @@ static int sd_upload(T **p, const std::vector<T> &h) {
 	return 0;
 }
 
+int sd_aux_reserve(sdgpu_ctx *c, size_t bytes) {
+	if (bytes <= c->auxCap) return 0;
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	if (c->h_aux) cudaFreeHost(c->h_aux);
+	c->h_aux = nullptr; c->d_aux = nullptr; c->auxCap = 0;
+	size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
+	if (cudaHostAlloc((void **) &c->h_aux, cap, cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostGetDevicePointer((void **) &c->d_aux, c->h_aux, 0) != cudaSuccess)
+		return sdgpu_fail("pinned scratch of %zu bytes failed", cap);
+	c->auxCap = cap;
+	return 0;
+}
+
 int sd_sync_state(sdgpu_ctx *c) {
 	SD_CUDA(cudaStreamSynchronize(c->stream));          // the commit kernels already published the state into h_state
 	c->omegaCnt = c->h_state->omegaCnt; c->lambdaCnt = c->h_state->lambdaCnt;
@@ -615,6 +628,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	if (c->h_state) cudaFreeHost(c->h_state);
 	if (c->h_cutRes) cudaFreeHost(c->h_cutRes);
 	if (c->h_iStar) cudaFreeHost(c->h_iStar);
+	if (c->h_aux) cudaFreeHost(c->h_aux);
 	if (c->evA) cudaEventDestroy(c->evA);
 	if (c->evB) cudaEventDestroy(c->evB);
 	if (c->evC) cudaEventDestroy(c->evC);
@@ -1015,14 +1029,11 @@ extern "C" int sdgpu_basis_set_obs_feasible_row(sdgpu_ctx *c, int basisIdx, cons
 	if (basisIdx < 0 || basisIdx >= c->basisCnt || !c->basis[basisIdx].feas) return sdgpu_fail("set_obs_feasible_row: bad basis %d", basisIdx);
 	if (c->rvd == 0) return 0;          // checkBasisFeasibility is constant true without random costs (randCost.c:208)
 	SD_CUDA(cudaSetDevice(c->device));
-	uint8_t *d_f = nullptr;
-	if (sd_alloc(&d_f, (size_t) std::max<int64_t>(1, c->omegaCnt))) return SDGPU_ERR;
-	cudaMemcpyAsync(d_f, flags, (size_t) c->omegaCnt, cudaMemcpyHostToDevice, c->stream);
-	k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, basisIdx, c->NP, d_f, c->omegaCnt, 0);
+	if (sd_aux_reserve(c, (size_t) std::max<int64_t>(1, c->omegaCnt))) return SDGPU_ERR;
+	memcpy(c->h_aux, flags, (size_t) c->omegaCnt);                       // the kernel reads the flags through the mapped alias
+	k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, basisIdx, c->NP, c->d_aux, c->omegaCnt, 0);
 	sd_count_launch(c);
-	cudaError_t e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_f);
-	if (e != cudaSuccess) return sdgpu_fail("set_obs_feasible_row: %s", cudaGetErrorString(e));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
 	for (int64_t o = 0; o < c->omegaCnt; o++) c->hostMask[basisIdx][o] = flags[o] != 0;
 	return 0;
 }
@@ -1032,14 +1043,11 @@ extern "C" int sdgpu_basis_set_obs_feasible_col(sdgpu_ctx *c, int obsIdx, const 
 	if (obsIdx < 0 || obsIdx >= c->caps.maxOmega) return sdgpu_fail("set_obs_feasible_col: bad observation %d", obsIdx);
 	if (c->rvd == 0 || c->basisCnt == 0) return 0;
 	SD_CUDA(cudaSetDevice(c->device));
-	uint8_t *d_f = nullptr;
-	if (sd_alloc(&d_f, (size_t) c->basisCnt)) return SDGPU_ERR;
-	cudaMemcpyAsync(d_f, flags, (size_t) c->basisCnt, cudaMemcpyHostToDevice, c->stream);
-	k_mask_fill_col<<<sd_blocks(c->basisCnt, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, obsIdx, d_f, c->d_bFeas, c->basisCnt);
+	if (sd_aux_reserve(c, (size_t) c->basisCnt)) return SDGPU_ERR;
+	memcpy(c->h_aux, flags, (size_t) c->basisCnt);
+	k_mask_fill_col<<<sd_blocks(c->basisCnt, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, obsIdx, c->d_aux, c->d_bFeas, c->basisCnt);
 	sd_count_launch(c);
-	cudaError_t e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_f);
-	if (e != cudaSuccess) return sdgpu_fail("set_obs_feasible_col: %s", cudaGetErrorString(e));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
 	for (int64_t b = 0; b < c->basisCnt; b++) if (c->basis[b].feas) c->hostMask[b][obsIdx] = flags[b] != 0;
 	return 0;
 }
