@@ -267,7 +267,10 @@ def gpu_arm(args):
     t_setup = time.perf_counter()
     t = load_tables(api, prob, pis, obsv, weights, D, N, k_total, extra, local)
     setup_s = time.perf_counter() - t_setup
-    if world > 1:                                                   # hand the library its own NCCL communicator
+    if world > 1 and args.collective == "peer":                    # NVLink peer-memory all-reduce fused into the cut kernel
+        from stochasticdecomposition_b200.sharding import ShardedTables
+        ShardedTables(t, rank, world).attach_peer_exchange()
+    elif world > 1:                                                 # hand the library its own NCCL communicator
         idbuf = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             raw = (C.c_char * 128)()
@@ -368,7 +371,8 @@ def gpu_arm(args):
                        "l2_policy": "inputs (64 GiB delta stream per step) far exceed the 126 MB L2; no flush needed",
                        "timing": "value: CUDA events on the library stream around K SDCut calls; e2e: wall clock around K full SD iterations "
                                  "(calcOmega, calcLambda/calcSigma/calcDelta, SDCut) with host buffers",
-                       "sharding": "observations split across ranks, lambda/sigma/basis replicated, one NCCL all-reduce of n1+4 doubles per cut" if world > 1 else "single GPU",
+                       "sharding": ("observations split across ranks, lambda/sigma/basis replicated, one all-reduce of n1+4 doubles per cut ("
+                                    + ("NVLink peer-memory exchange fused into the cut kernel" if args.collective == "peer" else "NCCL") + ")") if world > 1 else "single GPU",
                        "setup_s": round(setup_s, 2)},
             "roofline": {"bound": "hbm", "kernel": {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general"}.get(st["last_sweep_variant"], "?"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": ncu_traffic(nb, N), "bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_avg_ms,
@@ -402,6 +406,7 @@ def main():
     ap.add_argument("--cpu-duals", type=int, default=4096)
     ap.add_argument("--cpu-obs", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

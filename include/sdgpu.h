@@ -205,6 +205,14 @@ int  sdgpu_attach_nccl(sdgpu_ctx *ctx, void *ncclComm);
 int  sdgpu_nccl_unique_id(void *id128);                                  /* ncclGetUniqueId            */
 int  sdgpu_nccl_init(sdgpu_ctx *ctx, int nranks, int rank, const void *id128); /* ncclCommInitRank + attach */
 
+/* NVLink peer-memory all-reduce fused into the cut kernel (the latency-optimal form of the one exchange step): every rank
+ * exports a small exchange buffer (CUDA IPC), attaches everyone else's, and from then on the last block of the cut's merge
+ * kernel writes its n1+4 partial sums straight into every peer's buffer over NVLink, waits for the peers' flags, adds the
+ * rank slots in rank order (so all ranks get bit-identical cuts, run to run) and normalises -- no NCCL call, no extra launch.
+ * sdgpu_peer_export fills handle64 (64 bytes, cudaIpcMemHandle_t); handles = nranks x 64 bytes in rank order. */
+int  sdgpu_peer_export(sdgpu_ctx *ctx, int nranks, void *handle64);
+int  sdgpu_peer_attach(sdgpu_ctx *ctx, int nranks, int rank, const void *handles);
+
 /* cutHeight cuts.c:213-227 / maxCutHeight cuts.c:197-209 and the aging coefficients of
  * changeEtaCol master.c:152 and updateRHS master.c:174 for a batch of cuts held by the host:
  * alpha[n], beta = n rows of prevCols+1, numSamples[n]; outputs (each may be NULL) height[n],

@@ -213,6 +213,7 @@ class Api:
             "sd_cut_partial": (i, [vp, c_f64p, i, i, d]),
             "sd_cut_partial_buffer": (i, [vp, C.POINTER(vp), c_intp]),
             "sd_cut_finish": (i, [vp, i, C.POINTER(CCut)]),
+            "peer_export": (i, [vp, i, vp]), "peer_attach": (i, [vp, i, i, vp]),
             "attach_nccl": (i, [vp, vp]), "nccl_unique_id": (i, [vp]), "nccl_init": (i, [vp, i, i, vp]),
             "cut_heights": (i, [vp, i, c_f64p, c_f64p, c_i32p, c_f64p, i, c_f64p, d, c_f64p, c_f64p, c_f64p]),
             "reform_cut": (i, [vp, c_i32p, i, c_i32p, i, i, i, c_f64p, c_f64p]),

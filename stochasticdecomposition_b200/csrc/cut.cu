@@ -472,7 +472,17 @@ struct MergeArgs {
 	int32_t *iStar; int32_t *iStarHost; int iStarHostCap; double *tilePart; int P;
 	// epilogue run by the last block: tile partials -> un-normalised cut [-> normalised cut in mapped host memory]
 	int n1; const int32_t *CCols, *qCols; double *partial; int fuseNormalise, numSamples; double *hostRes; SdDevState *st;
+	// NVLink peer exchange (peerRanks > 1): every rank's buffer, this rank's index, the sequence number of this cut
+	int peerRanks, peerRank; unsigned peerSeq; unsigned char *peerBufs[16];
 };
+
+// exchange buffer layout: slots[parity][rank][n1+4] doubles, then flags[parity][rank] uint32
+__device__ __forceinline__ double *sd_peer_slot(unsigned char *buf, int G, int n1, int parity, int rank) {
+	return reinterpret_cast<double *>(buf) + ((size_t) parity * G + rank) * (n1 + 4);
+}
+__device__ __forceinline__ unsigned *sd_peer_flag(unsigned char *buf, int G, int n1, int parity, int rank) {
+	return reinterpret_cast<unsigned *>(reinterpret_cast<double *>(buf) + (size_t) 2 * G * (n1 + 4)) + parity * G + rank;
+}
 
 #define MG_THREADS SD_TILE_W
 
@@ -498,6 +508,58 @@ __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, c
 #pragma unroll
 		for (int u = 0; u < 16; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
 	}
+}
+
+// Tail of a cut, run by one block with the un-normalised vector [alpha, beta[1..n1], cummOld, cummAll, missing] in shared memory:
+// optional all-reduce over NVLink peer memory, then cuts.c:184-188 and the hand-over to the host.
+//   peer exchange: push this rank's sums into every rank's slot, raise the flags, wait for everyone's flag, add the slots in
+//   rank order (bit-identical on every rank).  Two slot sets alternate by cut parity: a rank can be at most one cut ahead.
+__device__ __forceinline__ void sd_cut_exchange_and_store(double *s_cut, int peerRanks, int peerRank, unsigned peerSeq, unsigned char *const *peerBufs,
+		int n1, double *partial, int fuseNormalise, int numSamples, double *hostRes) {
+	const int tid = threadIdx.x;
+	if (peerRanks > 1) {
+		const int G = peerRanks, par = peerSeq & 1;
+		__shared__ int s_timeout;
+		if (tid == 0) s_timeout = 0;
+		for (int p = 0; p < G; p++) {
+			double *slot = sd_peer_slot(peerBufs[p], G, n1, par, peerRank);
+			for (int c = tid; c <= n1 + 3; c += blockDim.x) slot[c] = s_cut[c];
+		}
+		__threadfence_system();
+		__syncthreads();
+		if (tid < G) {
+			*((volatile unsigned *) sd_peer_flag(peerBufs[tid], G, n1, par, peerRank)) = peerSeq;
+			volatile unsigned *mine = sd_peer_flag(peerBufs[peerRank], G, n1, par, tid);
+			const long long t0 = clock64();
+			while (*mine != peerSeq) {
+				if (clock64() - t0 > 20000000000LL) { s_timeout = 1; break; }          // ~10 s: a peer never arrived
+				__nanosleep(100);
+			}
+		}
+		__threadfence_system();
+		__syncthreads();
+		for (int c = tid; c <= n1 + 3; c += blockDim.x) {
+			double acc = 0.0;
+			for (int r = 0; r < G; r++) acc = __dadd_rn(acc, __ldcv(sd_peer_slot(peerBufs[peerRank], G, n1, par, r) + c));
+			s_cut[c] = acc;
+		}
+		__syncthreads();
+		if (tid == 0 && s_timeout) s_cut[n1 + 3] = 2.0e9;                              // reported by sdgpu_sd_cut_finish
+		__syncthreads();
+	}
+	for (int c = tid; c <= n1 + 3; c += blockDim.x) {
+		partial[c] = s_cut[c];
+		if (fuseNormalise) hostRes[c] = (c <= n1) ? s_cut[c] / numSamples : s_cut[c];
+	}
+	if (fuseNormalise) __threadfence_system();
+}
+
+// a rank with nothing to sweep (no local observation yet) still has to take part in the exchange
+__global__ void k_cut_exchange(MergeArgs a) {
+	extern __shared__ double s_cut[];
+	for (int c = threadIdx.x; c <= a.n1 + 3; c += blockDim.x) s_cut[c] = a.partial[c];
+	__syncthreads();
+	sd_cut_exchange_and_store(s_cut, a.peerRanks, a.peerRank, a.peerSeq, a.peerBufs, a.n1, a.partial, a.fuseNormalise, a.numSamples, a.hostRes);
 }
 
 __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
@@ -652,11 +714,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		s_cut[a.n1 + 1] = s_tot[1]; s_cut[a.n1 + 2] = s_tot[2]; s_cut[a.n1 + 3] = s_tot[3];
 	}
 	__syncthreads();
-	for (int c = tid; c <= a.n1 + 3; c += blockDim.x) {
-		a.partial[c] = s_cut[c];
-		if (a.fuseNormalise) a.hostRes[c] = (c <= a.n1) ? s_cut[c] / a.numSamples : s_cut[c];
-	}
-	if (a.fuseNormalise) __threadfence_system();
+	sd_cut_exchange_and_store(s_cut, a.peerRanks, a.peerRank, a.peerSeq, a.peerBufs, a.n1, a.partial, a.fuseNormalise, a.numSamples, a.hostRes);
 	SD_PHASE(6);
 }
 
@@ -1039,7 +1097,10 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		m.iStar = c->d_iStar; m.tilePart = c->d_tilePart; m.P = P;
 		m.iStarHost = c->d_iStarHost; m.iStarHostCap = N <= c->iStarHostCap ? N : 0;
 		m.n1 = c->n1; m.CCols = c->d_CCols; m.qCols = c->rvd > 0 ? c->d_rvCOmCols : c->d_rvCols;       // cuts.c:157 vs :167
-		m.partial = c->d_cutPartial; m.fuseNormalise = c->ncclComm == nullptr && fuseNormalise; m.numSamples = numSamples;
+		const bool peer = c->peerRanks > 1;
+		m.partial = c->d_cutPartial; m.fuseNormalise = (peer || c->ncclComm == nullptr) && fuseNormalise; m.numSamples = numSamples;
+		m.peerRanks = peer ? c->peerRanks : 0; m.peerRank = c->peerRank; m.peerSeq = peer ? ++c->peerSeq : 0;
+		for (int r = 0; r < 16; r++) m.peerBufs[r] = peer && r < c->peerRanks ? c->d_peerBufs[r] : nullptr;
 		m.hostRes = c->d_cutRes; m.st = c->d_state;
 		c->cutFused = m.fuseNormalise != 0;
 		const int kp = ((c->n1c + 31) / 32) * 32;
@@ -1057,6 +1118,16 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		SD_CUDA(cudaMemcpyAsync(c->d_cutPartial, zero.data(), zero.size() * 8, cudaMemcpyHostToDevice, c->stream));
 		if (N > 0) SD_CUDA(cudaMemsetAsync(c->d_iStar, 0xff, (size_t) N * 4, c->stream));
 		SD_CUDA(cudaStreamSynchronize(c->stream));
+		if (c->peerRanks > 1 && fuseNormalise) {
+			MergeArgs m;
+			memset(&m, 0, sizeof m);
+			m.n1 = c->n1; m.partial = c->d_cutPartial; m.fuseNormalise = 1; m.numSamples = numSamples; m.hostRes = c->d_cutRes;
+			m.peerRanks = c->peerRanks; m.peerRank = c->peerRank; m.peerSeq = ++c->peerSeq;
+			for (int r = 0; r < c->peerRanks; r++) m.peerBufs[r] = c->d_peerBufs[r];
+			k_cut_exchange<<<1, 128, ((size_t) c->n1 + 4) * 8, c->stream>>>(m);
+			sd_count_launch(c);
+			c->cutFused = true;
+		}
 	}
 	c->stats.last_cut_launches = c->stats.total_launches - launches0;
 	return 0;
@@ -1098,6 +1169,7 @@ extern "C" int sdgpu_sd_cut_finish(sdgpu_ctx *c, int numSamples, sdgpu_cut *cut)
 	cut->omegaCnt = c->lastOmegaCnt; cut->numSamples = numSamples;
 	cut->cummOld = h[c->n1 + 1]; cut->cummAll = h[c->n1 + 2];
 	const double missing = h[c->n1 + 3];
+	if (missing >= 2.0e9 && c->peerRanks > 1) return sdgpu_fail("sd_cut: peer exchange timed out (a rank did not reach this cut)");
 	if (missing >= 1.0e9) return sdgpu_fail("sd_cut: iStar used as a sigma index is out of range (cuts.c:161)");
 	if (missing > 0.0) { sdgpu_fail("sd_cut: failed to identify maximal Pi for %g observation(s)", missing); return SDGPU_NONE; }
 	cut->alpha = h[0];
@@ -1110,7 +1182,7 @@ extern "C" int sdgpu_sd_cut(sdgpu_ctx *c, const double *Xvect, int numSamples, i
 	if (!cut || !cut->beta) return sdgpu_fail("null argument");
 	int rc = sd_cut_partial_impl(c, Xvect, numSamples, pi_eval_flag, lb, true);
 	if (rc != 0) return rc;
-	if (c->ncclComm) {
+	if (c->ncclComm && !c->cutFused) {              // (with a peer exchange attached the merge kernel has already reduced)
 		rc = sd_nccl_allreduce(c, c->d_cutPartial, c->n1 + 4);
 		if (rc != 0) return rc;
 	}

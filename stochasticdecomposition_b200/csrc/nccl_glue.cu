@@ -60,9 +60,13 @@ int sd_nccl_allreduce(sdgpu_ctx *c, double *buf, int n) {
 	return 0;
 }
 
+static void sd_peer_release(sdgpu_ctx *c);
+
 void sd_nccl_release(sdgpu_ctx *c) {
 	if (c->ncclComm && c->ownComm && g_nccl.commDestroy) g_nccl.commDestroy(c->ncclComm);
 	c->ncclComm = nullptr; c->ownComm = false;
+	sd_peer_release(c);                       // destroy path: also drop the peer mappings and the exported buffer
+	if (c->d_peerLocal) { cudaFree(c->d_peerLocal); c->d_peerLocal = nullptr; }
 }
 
 extern "C" int sdgpu_attach_nccl(sdgpu_ctx *c, void *ncclComm) {
@@ -94,5 +98,52 @@ extern "C" int sdgpu_nccl_init(sdgpu_ctx *c, int nranks, int rank, const void *i
 	if (rc != 0) return sdgpu_fail("ncclCommInitRank failed: %s", ncclErr(rc));
 	sd_nccl_release(c);
 	c->ncclComm = comm; c->ownComm = true;
+	return 0;
+}
+
+// ---- NVLink peer-memory exchange buffers (CUDA IPC between the one-process-per-GPU ranks) -----------------------------
+static size_t sd_peer_bytes(const sdgpu_ctx *c, int nranks) {
+	return (size_t) 2 * nranks * (c->n1 + 4) * sizeof(double) + (size_t) 2 * nranks * sizeof(unsigned) + 64;
+}
+
+static void sd_peer_release(sdgpu_ctx *c) {
+	for (int r = 0; r < c->peerRanks; r++)
+		if (c->d_peerBufs[r] && r != c->peerRank) cudaIpcCloseMemHandle(c->d_peerBufs[r]);
+	for (int r = 0; r < sdgpu_ctx::kMaxPeers; r++) c->d_peerBufs[r] = nullptr;
+	c->peerRanks = 0; c->peerRank = -1;
+}
+
+extern "C" int sdgpu_peer_export(sdgpu_ctx *c, int nranks, void *handle64) {
+	if (!c || !handle64) return sdgpu_fail("null argument");
+	if (nranks < 2 || nranks > sdgpu_ctx::kMaxPeers) return sdgpu_fail("peer_export: nranks %d outside 2..%d", nranks, sdgpu_ctx::kMaxPeers);
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	SD_CUDA(cudaSetDevice(c->device));
+	sd_peer_release(c);
+	if (c->d_peerLocal) { cudaFree(c->d_peerLocal); c->d_peerLocal = nullptr; }
+	c->peerBytes = sd_peer_bytes(c, nranks);
+	SD_CUDA(cudaMalloc((void **) &c->d_peerLocal, c->peerBytes));
+	SD_CUDA(cudaMemset(c->d_peerLocal, 0, c->peerBytes));
+	cudaIpcMemHandle_t h;
+	SD_CUDA(cudaIpcGetMemHandle(&h, c->d_peerLocal));
+	memcpy(handle64, &h, sizeof h);
+	return 0;
+}
+
+extern "C" int sdgpu_peer_attach(sdgpu_ctx *c, int nranks, int rank, const void *handles) {
+	if (!c || !handles) return sdgpu_fail("null argument");
+	if (!c->d_peerLocal || c->peerBytes != sd_peer_bytes(c, nranks)) return sdgpu_fail("peer_attach: call sdgpu_peer_export(ctx, %d, ...) first", nranks);
+	if (rank < 0 || rank >= nranks) return sdgpu_fail("peer_attach: rank %d out of range", rank);
+	SD_CUDA(cudaSetDevice(c->device));
+	sd_peer_release(c);
+	for (int r = 0; r < nranks; r++) {
+		if (r == rank) { c->d_peerBufs[r] = c->d_peerLocal; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const unsigned char *) handles + (size_t) r * 64, sizeof h);
+		void *p = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { sd_peer_release(c); return sdgpu_fail("peer_attach: cannot open rank %d's buffer: %s", r, cudaGetErrorString(e)); }
+		c->d_peerBufs[r] = (unsigned char *) p;
+	}
+	c->peerRanks = nranks; c->peerRank = rank; c->peerSeq = 0;
 	return 0;
 }

@@ -145,6 +145,14 @@ struct sdgpu_ctx {
 	std::vector<SdHostBasis> basis;
 	std::vector<std::vector<uint8_t>> hostMask;   // [b][NP] only when rvd > 0
 
+	// NVLink peer-memory exchange (sdgpu_peer_export / _attach): slots[2][G][n1+4] doubles then flags[2][G] uint32
+	static const int kMaxPeers = 16;
+	unsigned char *d_peerLocal = nullptr;          // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
+	unsigned char *d_peerBufs[kMaxPeers] = {};     // every rank's buffer as seen from this device (own entry = d_peerLocal)
+	int      peerRanks = 0, peerRank = -1;
+	unsigned peerSeq = 0;
+	size_t   peerBytes = 0;
+
 	// NCCL (resolved with dlopen so that the library loads on a box without NCCL)
 	void *ncclComm = nullptr;
 	bool  ownComm = false;

@@ -75,6 +75,25 @@ class ShardedTables:
             raise SdError("nccl_init: " + api.error())
         self.library_nccl = True
 
+    def attach_peer_exchange(self):
+        """NVLink peer-memory all-reduce fused into the cut kernel: exchange CUDA IPC handles of the per-rank buffers."""
+        import torch
+        dist = self._dist()
+        api = self.t.api
+        raw = (C.c_char * 64)()
+        if api._fn("peer_export")(self.t.ctx, self.world, raw) != 0:
+            raise SdError("peer_export: " + api.error())
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone().to(dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        blob = b"".join(h.cpu().numpy().tobytes() for h in allh)
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        if api._fn("peer_attach")(self.t.ctx, self.world, self.rank, buf) != 0:
+            raise SdError("peer_attach: " + api.error())
+        dist.barrier(group=self.group)
+        self.library_nccl = True                      # sd_cut reduces inside the library from now on
+
     # ---- tables -----------------------------------------------------------------------------------------
     def calc_omega(self, observ, tol):
         """calcOmega stocUpdate.c:326-348 over the sharded observation set: the FIRST match in global order wins."""

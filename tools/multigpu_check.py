@@ -29,10 +29,12 @@ def main():
     K = 60
     trace = make_trace(prob, K, seed=11, dual_pool=20, obs_pool=0)
     n = 2 * K + 2
-    for mode in ("library_nccl", "torch"):
+    for mode in ("library_nccl", "torch", "peer"):
         sh = ShardedTables(sd.load_library().create(prob, Caps(n, n, n, K + 1, 1), local), rank, world)
         if mode == "library_nccl":
             sh.attach_library_nccl()
+        if mode == "peer":
+            sh.attach_peer_exchange()
         cuts = []
         for it in range(K):
             k = it + 1
