@@ -1118,15 +1118,15 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		SD_CUDA(cudaMemcpyAsync(c->d_cutPartial, zero.data(), zero.size() * 8, cudaMemcpyHostToDevice, c->stream));
 		if (N > 0) SD_CUDA(cudaMemsetAsync(c->d_iStar, 0xff, (size_t) N * 4, c->stream));
 		SD_CUDA(cudaStreamSynchronize(c->stream));
-		if (c->peerRanks > 1 && fuseNormalise) {
+		if (c->peerRanks > 1) {                      // the other ranks exchange inside their merge kernel: take part, with zero sums
 			MergeArgs m;
 			memset(&m, 0, sizeof m);
-			m.n1 = c->n1; m.partial = c->d_cutPartial; m.fuseNormalise = 1; m.numSamples = numSamples; m.hostRes = c->d_cutRes;
+			m.n1 = c->n1; m.partial = c->d_cutPartial; m.fuseNormalise = fuseNormalise; m.numSamples = numSamples; m.hostRes = c->d_cutRes;
 			m.peerRanks = c->peerRanks; m.peerRank = c->peerRank; m.peerSeq = ++c->peerSeq;
 			for (int r = 0; r < c->peerRanks; r++) m.peerBufs[r] = c->d_peerBufs[r];
 			k_cut_exchange<<<1, 128, ((size_t) c->n1 + 4) * 8, c->stream>>>(m);
 			sd_count_launch(c);
-			c->cutFused = true;
+			c->cutFused = fuseNormalise;
 		}
 	}
 	c->stats.last_cut_launches = c->stats.total_launches - launches0;
