@@ -491,6 +491,14 @@ static int sd_stage_vec(sdgpu_ctx *c, const double *h, int n) {
 	return 0;
 }
 
+// Where the scan kernels should read the staged vector from: zero-copy over PCIe is the lowest latency for a handful of
+// blocks, but every block re-reads the vector, so large tables (many blocks) get one DMA copy into device memory instead.
+static const double *sd_staged_source(sdgpu_ctx *c, int n, int64_t rowsToScan) {
+	if (rowsToScan <= 32 * 256) return c->d_pinD;
+	if (cudaMemcpyAsync(c->d_vecIn, c->h_pinD, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return c->d_pinD;
+	return c->d_vecIn;
+}
+
 static inline int sd_blocks(int64_t n, int t) { return (int) std::max<int64_t>(1, (n + t - 1) / t); }
 
 extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int device, sdgpu_ctx **out) {
@@ -682,7 +690,7 @@ extern "C" int sdgpu_get_stats(sdgpu_ctx *c, sdgpu_stats *out) {
 static int sd_launch_omega(sdgpu_ctx *c, const double *observ, double tol, int mode, int weight) {
 	if (sd_stage_vec(c, observ, c->numRV + 1)) return SDGPU_ERR;
 	const int blocks = mode == 2 ? 1 : sd_blocks(c->omegaCnt, 256);
-	k_omega_fused<<<blocks, 256, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(c->d_pinD, c->numRV, c->d_omega, c->d_omegaW, c->NP,
+	k_omega_fused<<<blocks, 256, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(sd_staged_source(c, c->numRV + 1, mode == 2 ? 0 : c->omegaCnt), c->numRV, c->d_omega, c->d_omegaW, c->NP,
 			c->caps.maxOmega, tol, mode, weight, c->d_state, c->d_hstate);
 	sd_count_launch(c);
 	return sd_sync_state(c);
@@ -781,7 +789,7 @@ extern "C" int sdgpu_calc_lambda(sdgpu_ctx *c, const double *Pi, double tol, int
 	if (!c || !Pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, Pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, c->d_pinD, 0.0, tol, c->lambdaCnt);
+	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), 0.0, tol, c->lambdaCnt);
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
 	return c->h_state->lambdaIdx;
@@ -824,7 +832,7 @@ extern "C" int sdgpu_update_dual(sdgpu_ctx *c, const double *pi, double mubBar, 
 	if (!c || !pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, c->d_pinD, mubBar, tol, c->lambdaCnt);             // stocUpdate.c:78 (+ staging of :293-296)
+	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), mubBar, tol, c->lambdaCnt);   // stocUpdate.c:78 (+ staging of :293-296)
 	sd_launch_sigma(c, currentIter, tol, c->sigmaCnt);                     // :81
 	sd_launch_delta_row(c, -1, c->omegaCnt);                               // :84-85 (kernel no-op unless the lambda was new)
 	if (sd_sync_state(c)) return SDGPU_ERR;
