@@ -416,104 +416,7 @@ struct SweepGenArgs {
 	double *partV; int32_t *partI;
 };
 
-// Term-linear form of the general sweep.  The terms of a batch of bases (<= SG_TERMS terms) are staged in shared memory as
-// descriptors (sigma.pib, piCbarX, lambda row, multiplier column, "last term of basis b" marker, window); the kernel then walks
-// the terms eight at a time -- delta pair, multiplier pair and (at a basis' last term) mask pair of all eight fetched together
-// -- and adds them into the running score of the current basis in term order, comparing when a basis ends.  One memory round
-// per eight terms instead of three dependent ones per term.
-#define SG_TERMS 256
-#define SG_BASES 128
-
 __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general(SweepGenArgs a) {
-	__shared__ double s_xq[64];
-	__shared__ double2 s_tAC[SG_TERMS];
-	__shared__ int s_tRow[SG_TERMS], s_tOm[SG_TERMS], s_tLast[SG_TERMS], s_tWin[SG_TERMS];
-	__shared__ int s_nb;
-	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
-	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
-	for (int j = tid; j < a.Q; j += blockDim.x) s_xq[j] = a.x[a.rvCOmCols[j]];
-	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
-	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
-	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
-	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride + 2 * tid;
-	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
-	for (int base = b0; base < b1; ) {
-		__syncthreads();
-		if (tid == 0) {                                     // how many bases fit the descriptor batch
-			const int T0 = a.bTermStart[base];
-			int nb = 1;
-			while (base + nb < b1 && nb < SG_BASES && a.bTermStart[base + nb + 1] - T0 <= SG_TERMS) nb++;
-			s_nb = nb;
-		}
-		__syncthreads();
-		const int nb = s_nb, T0 = a.bTermStart[base], nT = a.bTermStart[base + nb] - T0;
-		for (int j = tid; j < nb; j += blockDim.x) {        // per basis: fill its terms
-			const int b = base + j, ts = a.bTermStart[b], te = a.bTermStart[b + 1], win = a.descWin[b];
-			for (int t = ts; t < te; t++) {
-				const int sg = a.tSigma[t], i = t - T0;
-				s_tAC[i] = make_double2(a.sigmaPib[sg], a.piCbarX[sg]);
-				s_tRow[i] = a.sigmaLam[sg];
-				s_tOm[i] = (t == ts) ? -1 : a.rvOffset2 + a.tOmega[t] - 1;
-				s_tLast[i] = (t == te - 1) ? b : -1;
-				s_tWin[i] = win;
-			}
-		}
-		__syncthreads();
-		double arg0 = 0.0, arg1 = 0.0;
-		for (int g = 0; g < nT; g += 8) {
-			double2 d[8], mm[8]; uchar2 mk[8];
-#pragma unroll
-			for (int u = 0; u < 8; u++) {
-				const int i = min(g + u, nT - 1);
-				d[u] = ld_stream_f64x2(tileBase + (size_t) s_tRow[i] * rowStride);
-				const int om = s_tOm[i];
-				mm[u] = om < 0 ? make_double2(1.0, 1.0) : *reinterpret_cast<const double2 *>(a.omega + (size_t) om * a.NP + o);
-				mk[u] = make_uchar2(1, 1);
-				if (a.mask && s_tLast[i] >= 0) mk[u] = *reinterpret_cast<const uchar2 *>(a.mask + ((size_t) tile * a.Bcap + s_tLast[i]) * SD_TILE_W + 2 * tid);
-			}
-#pragma unroll
-			for (int u = 0; u < 8; u++) {
-				const int i = g + u;
-				if (i >= nT) break;
-				const double2 ac = s_tAC[i];
-				// arg += m * ((sigma.pib + delta.pib) - piCbarX);  arg -= m * (delta.piC . x)      stocUpdate.c:174-175
-				arg0 = __dadd_rn(arg0, __dmul_rn(mm[u].x, __dsub_rn(__dadd_rn(ac.x, d[u].x), ac.y)));
-				arg1 = __dadd_rn(arg1, __dmul_rn(mm[u].y, __dsub_rn(__dadd_rn(ac.x, d[u].y), ac.y)));
-				double dx0 = 0.0, dx1 = 0.0;
-				for (int q = 0; q < a.Q; q++) {
-					const double2 pq = ld_stream_f64x2(tileBase + (size_t) s_tRow[i] * rowStride + (size_t) (1 + q) * SD_TILE_W);
-					dx0 = __dadd_rn(dx0, __dmul_rn(pq.x, s_xq[q]));
-					dx1 = __dadd_rn(dx1, __dmul_rn(pq.y, s_xq[q]));
-				}
-				arg0 = __dsub_rn(arg0, __dmul_rn(mm[u].x, dx0));
-				arg1 = __dsub_rn(arg1, __dmul_rn(mm[u].y, dx1));
-				const int b = s_tLast[i];
-				if (b >= 0) {                                   // the basis is complete: compare (stocUpdate.c:178-181) and start the next one
-					const int win = s_tWin[i];
-					if (win == 1) {
-						if (mk[u].x && arg0 > oV0) { oV0 = arg0; oI0 = b; }
-						if (mk[u].y && arg1 > oV1) { oV1 = arg1; oI1 = b; }
-					}
-					else if (win == 2) {
-						if (mk[u].x && arg0 > nV0) { nV0 = arg0; nI0 = b; }
-						if (mk[u].y && arg1 > nV1) { nV1 = arg1; nI1 = b; }
-					}
-					arg0 = 0.0; arg1 = 0.0;
-				}
-			}
-		}
-		base += nb;
-	}
-	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
-	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
-	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
-	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
-	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
-}
-
-// the plain form: one basis after the other, every operand fetched where it is needed; used when a single basis has more terms
-// than the descriptor batch holds
-__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general_simple(SweepGenArgs a) {
 	__shared__ double s_xq[64];
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
@@ -1154,8 +1057,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		dim3 grid((unsigned) tiles, (unsigned) nChunks);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
 		if (general) {
-			if (c->maxPhiLen + 1 <= SG_TERMS) k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
-			else k_sweep_general_simple<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
+			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
 			c->stats.last_sweep_variant = 3;
 		}
 		else {
