@@ -213,6 +213,25 @@ int  sdgpu_nccl_init(sdgpu_ctx *ctx, int nranks, int rank, const void *id128); /
 int  sdgpu_peer_export(sdgpu_ctx *ctx, int nranks, void *handle64);
 int  sdgpu_peer_attach(sdgpu_ctx *ctx, int nranks, int rank, const void *handles);
 
+/* ---- one host thread, several GPUs (the reference's host is a single process) -------------------------------------------
+ * A group owns one context per device of this process.  Observations are dealt round-robin (global observation o lives on
+ * member o % G at local slot o / G); lambda / sigma / basis records are replicated.  The group calls below have the
+ * single-context meaning over the union of the shards; the cut's all-reduce is the NVLink peer-memory exchange inside the cut
+ * kernel (direct peer pointers, no IPC needed in one process).  rvdOmCnt must be 0. */
+typedef struct sdgpu_group sdgpu_group;
+int  sdgpu_group_create(const sdgpu_problem *prob, const sdgpu_caps *capsPerDevice, int nDevices, const int *devices, sdgpu_group **out);
+void sdgpu_group_destroy(sdgpu_group *grp);
+int  sdgpu_group_reset(sdgpu_group *grp);
+int  sdgpu_group_size(sdgpu_group *grp);
+sdgpu_ctx *sdgpu_group_member(sdgpu_group *grp, int i);
+int  sdgpu_group_get_counts(sdgpu_group *grp, sdgpu_counts *out);                      /* omega = total over the shards */
+int  sdgpu_group_calc_omega(sdgpu_group *grp, const double *observ, double tol, int *newOmegaFlag);   /* global index; fills the delta column when new */
+int  sdgpu_group_update_dual(sdgpu_group *grp, const double *pi, double mubBar, int currentIter, double tol,
+                             int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag);
+int  sdgpu_group_basis_find_or_append(sdgpu_group *grp, int retainBasis, int ck, int feasFlag, int sigmaIdx, int *newBasisFlag);
+/* SDCut over all shards; cut->iStar (if not NULL) receives the maximisers in GLOBAL observation order */
+int  sdgpu_group_sd_cut(sdgpu_group *grp, const double *Xvect, int numSamples, int pi_eval_flag, double lb, sdgpu_cut *cut);
+
 /* cutHeight cuts.c:213-227 / maxCutHeight cuts.c:197-209 and the aging coefficients of
  * changeEtaCol master.c:152 and updateRHS master.c:174 for a batch of cuts held by the host:
  * alpha[n], beta = n rows of prevCols+1, numSamples[n]; outputs (each may be NULL) height[n],

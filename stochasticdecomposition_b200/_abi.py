@@ -220,6 +220,13 @@ class Api:
             "reform_cuts_batch": (i, [vp, i, c_i32p, i, c_i32p, i, c_i32p, i, i, i, c_f64p, c_f64p]),
             "get_omega": (i, [vp, i, c_f64p, c_intp]), "get_lambda": (i, [vp, i, c_f64p]),
             "get_sigma": (i, [vp, i, c_f64p, c_f64p, c_intp, c_intp]), "get_delta": (i, [vp, i, i, c_f64p, c_f64p]),
+            "group_create": (i, [C.POINTER(CProblem), C.POINTER(CCaps), i, c_intp, C.POINTER(vp)]),
+            "group_destroy": (None, [vp]), "group_reset": (i, [vp]), "group_size": (i, [vp]), "group_member": (vp, [vp, i]),
+            "group_get_counts": (i, [vp, C.POINTER(CCounts)]),
+            "group_calc_omega": (i, [vp, c_f64p, d, c_intp]),
+            "group_update_dual": (i, [vp, c_f64p, d, i, d, c_intp, c_intp, c_intp, c_intp]),
+            "group_basis_find_or_append": (i, [vp, i, i, i, i, c_intp]),
+            "group_sd_cut": (i, [vp, c_f64p, i, i, d, C.POINTER(CCut)]),
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
             "get_stats": (i, [vp, C.POINTER(CStats)]),
             "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]),
@@ -241,6 +248,61 @@ class Api:
         if st != 0 or not ctx:
             raise SdError(f"{self.prefix}create failed ({st}): {self.error()}")
         return Tables(self, ctx, problem, caps)
+
+
+class Group:
+    """Several GPUs of this process behind one handle (include/sdgpu.h, sdgpu_group_*): observations dealt round-robin, dual-side
+    tables replicated, the cut all-reduced through NVLink peer memory inside the cut kernel.  One host thread drives it."""
+
+    def __init__(self, api: "Api", problem: Problem, capsPerDevice: Caps, devices):
+        self.api, self.problem = api, problem
+        h = C.c_void_p()
+        cp, cc = problem.to_c(), capsPerDevice.to_c()
+        devs = (C.c_int * len(devices))(*devices)
+        st = api._fn("group_create")(C.byref(cp), C.byref(cc), len(devices), devs, C.byref(h))
+        if st != 0 or not h:
+            raise SdError(f"group_create failed ({st}): {api.error()}")
+        self.h = h
+
+    def _ok(self, st, what, allow_none=False):
+        if st <= SDGPU_ERR or (st == SDGPU_NONE and not allow_none):
+            raise SdError(f"group {what} failed ({st}): {self.api.error()}")
+        return st
+
+    def close(self):
+        if self.h:
+            self.api._fn("group_destroy")(self.h)
+            self.h = None
+
+    def counts(self):
+        c = CCounts()
+        self._ok(self.api._fn("group_get_counts")(self.h, C.byref(c)), "get_counts")
+        return {"omega": c.omega, "lambda": c.lambda_, "sigma": c.sigma, "basis": c.basis}
+
+    def calc_omega(self, observ, tol):
+        o, flag = _f64(observ), C.c_int(0)
+        idx = self._ok(self.api._fn("group_calc_omega")(self.h, _pf64(o), tol, C.byref(flag)), "calc_omega")
+        return idx, bool(flag.value)
+
+    def stochastic_updates(self, omegaIdx, newOmegaFlag, piDet, mubBar, currentIter, tol, feasFlag=True):
+        p = _f64(piDet)
+        li, nl, si, ns, nb = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ok(self.api._fn("group_update_dual")(self.h, _pf64(p), mubBar, currentIter, tol, C.byref(li), C.byref(nl), C.byref(si),
+                                                     C.byref(ns)), "update_dual")
+        b = self._ok(self.api._fn("group_basis_find_or_append")(self.h, ns.value, currentIter, int(feasFlag), si.value, C.byref(nb)),
+                     "basis_find_or_append")
+        return b, bool(nb.value)
+
+    def sd_cut(self, X, numSamples, pi_eval_flag, lb):
+        x = _f64(X)
+        n = self.counts()["omega"]
+        beta, istar = np.zeros(self.problem.prevCols + 1), np.full(max(n, 1), -7, np.int32)
+        cut = CCut(0.0, _pf64(beta), _pi32(istar), 0, 0, 0.0, 0.0)
+        st = self.api._fn("group_sd_cut")(self.h, _pf64(x), numSamples, int(pi_eval_flag), lb, C.byref(cut))
+        if st == SDGPU_NONE:
+            return None
+        self._ok(st, "sd_cut")
+        return Cut(cut.alpha, beta, istar[:n], cut.omegaCnt, cut.numSamples, cut.cummOld, cut.cummAll)
 
 
 class Tables:

@@ -108,7 +108,8 @@ static size_t sd_peer_bytes(const sdgpu_ctx *c, int nranks) {
 
 static void sd_peer_release(sdgpu_ctx *c) {
 	for (int r = 0; r < c->peerRanks; r++)
-		if (c->d_peerBufs[r] && r != c->peerRank) cudaIpcCloseMemHandle(c->d_peerBufs[r]);
+		if (c->d_peerBufs[r] && r != c->peerRank && !c->peerLocalGroup) cudaIpcCloseMemHandle(c->d_peerBufs[r]);
+	c->peerLocalGroup = false;
 	for (int r = 0; r < sdgpu_ctx::kMaxPeers; r++) c->d_peerBufs[r] = nullptr;
 	c->peerRanks = 0; c->peerRank = -1;
 }
@@ -145,5 +146,34 @@ extern "C" int sdgpu_peer_attach(sdgpu_ctx *c, int nranks, int rank, const void 
 		c->d_peerBufs[r] = (unsigned char *) p;
 	}
 	c->peerRanks = nranks; c->peerRank = rank; c->peerSeq = 0;
+	return 0;
+}
+
+// same-process form: the members of a group see each other's exchange buffers through plain peer pointers
+int sd_peer_attach_local(sdgpu_ctx **ctxs, int n) {
+	for (int i = 0; i < n; i++) {
+		sdgpu_ctx *c = ctxs[i];
+		SD_CUDA(cudaSetDevice(c->device));
+		sd_peer_release(c);
+		if (c->d_peerLocal) { cudaFree(c->d_peerLocal); c->d_peerLocal = nullptr; }
+		c->peerBytes = sd_peer_bytes(c, n);
+		SD_CUDA(cudaMalloc((void **) &c->d_peerLocal, c->peerBytes));
+		SD_CUDA(cudaMemset(c->d_peerLocal, 0, c->peerBytes));
+		for (int j = 0; j < n; j++) {
+			if (j == i || ctxs[j]->device == c->device) continue;
+			int can = 0;
+			SD_CUDA(cudaDeviceCanAccessPeer(&can, c->device, ctxs[j]->device));
+			if (!can) return sdgpu_fail("devices %d and %d cannot access each other's memory", c->device, ctxs[j]->device);
+			cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return sdgpu_fail("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+			cudaGetLastError();
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		sdgpu_ctx *c = ctxs[i];
+		for (int j = 0; j < n; j++) c->d_peerBufs[j] = ctxs[j]->d_peerLocal;
+		c->peerRanks = n; c->peerRank = i; c->peerSeq = 0;
+		c->peerLocalGroup = true;
+	}
 	return 0;
 }

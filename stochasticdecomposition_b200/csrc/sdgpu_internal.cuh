@@ -150,6 +150,7 @@ struct sdgpu_ctx {
 	unsigned char *d_peerLocal = nullptr;          // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
 	unsigned char *d_peerBufs[kMaxPeers] = {};     // every rank's buffer as seen from this device (own entry = d_peerLocal)
 	int      peerRanks = 0, peerRank = -1;
+	bool     peerLocalGroup = false;               // peers are contexts of this process (plain peer pointers, nothing to close)
 	unsigned peerSeq = 0;
 	size_t   peerBytes = 0;
 

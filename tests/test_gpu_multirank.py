@@ -18,3 +18,11 @@ def test_two_ranks_library_nccl_and_torch_allreduce():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTIGPU_OK world=2" in out.stdout
+
+
+def test_single_process_group_over_all_gpus():
+    """sdgpu_group_*: one host thread drives every visible GPU (also meaningful with one GPU: the group degenerates to a context)"""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "group_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "GROUP_OK" in out.stdout
