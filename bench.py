@@ -374,7 +374,7 @@ def gpu_arm(args):
                        "sharding": ("observations split across ranks, lambda/sigma/basis replicated, one all-reduce of n1+4 doubles per cut ("
                                     + ("NVLink peer-memory exchange fused into the cut kernel" if args.collective == "peer" else "NCCL") + ")") if world > 1 else "single GPU",
                        "setup_s": round(setup_s, 2)},
-            "roofline": {"bound": "hbm", "kernel": {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general"}.get(st["last_sweep_variant"], "?"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general", 4: "k_sweep_tma_gen"}.get(st["last_sweep_variant"], "?"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": ncu_traffic(nb, N), "bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_avg_ms,
                          "sweep_share_of_step": sweep_avg_ms / ms_step},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},

@@ -81,7 +81,9 @@ __global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, doubl
 		const int32_t *__restrict__ bCk, const int32_t *__restrict__ bFeas, const int32_t *__restrict__ bTermStart,
 		const int32_t *__restrict__ tSigma, const double *__restrict__ sigmaPib, const int32_t *__restrict__ sigmaLam,
 		int basisCnt, int split, int cutoff,
-		double *__restrict__ descA, double *__restrict__ descC, int32_t *__restrict__ descRow, int32_t *__restrict__ descWin) {
+		double *__restrict__ descA, double *__restrict__ descC, int32_t *__restrict__ descRow, int32_t *__restrict__ descWin,
+		const int32_t *__restrict__ tOmega, double *__restrict__ termA, double *__restrict__ termC, int32_t *__restrict__ termRow,
+		int32_t *__restrict__ termMeta, int32_t *__restrict__ termBasis) {
 	extern __shared__ double s_x[];
 	for (int k = threadIdx.x; k < n1c; k += blockDim.x) s_x[k] = xDevIn ? xDevIn[CCols[k]] : xp.v[CCols[k]];
 	if (blockIdx.x == 0 && !xDevIn)
@@ -99,6 +101,17 @@ __global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, doubl
 			else win = split ? 2 : 0;
 		}
 		descA[i] = sigmaPib[s]; descC[i] = acc; descRow[i] = sigmaLam[s]; descWin[i] = win;
+		if (termA) {                                      // term-linear form for the random-cost sweep: one descriptor per (basis, term)
+			const int ts = bTermStart[i], te = bTermStart[i + 1];
+			for (int t = ts; t < te; t++) {
+				const int st = tSigma[t];
+				termA[t] = sigmaPib[st];
+				termC[t] = (t == ts) ? acc : sd_dot_strided(piCk + st, (size_t) SP, s_x, n1c);
+				termRow[t] = sigmaLam[st];
+				termMeta[t] = win | (t == te - 1 ? 4 : 0) | ((t == ts ? 0 : tOmega[t]) << 8);
+				termBasis[t] = i;
+			}
+		}
 	}
 }
 
@@ -456,6 +469,157 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general(SweepGenArgs
 		*reinterpret_cast<double2 *>(a.partV + at) = make_double2(bestV[wdw][0], bestV[wdw][1]);
 		*reinterpret_cast<int2 *>(a.partI + at) = make_int2(bestI[wdw][0], bestI[wdw][1]);
 	}
+}
+
+// Term-linear TMA sweep for random-cost problems (rvdOmCnt > 0): multi-term bases (stocUpdate.c:165-176) and the obsFeasible
+// mask (:163).  k_cut_prep has flattened the bases of the chunk into a list of terms (sigma.pib, piCbarX, lambda row, multiplier
+// column, window, "last term of its basis").  The producer warp feeds a two-stage ring with one bulk copy per term -- the 1+Q
+// planes of that term's delta row for this tile -- plus, at a basis' last term, the 512 mask bytes of that basis; lane r of the
+// warp looks after term r of the stage, so the descriptor reads and the copies of a stage go out together.  The cost columns of
+// omega for this tile (the multipliers m_c) are copied once per CTA and stay resident in shared memory.  Consumers therefore
+// touch only shared memory: LDS.128 of the delta pair, LDS.128 of the multiplier pair, LDS.U16 of the mask pair, and the score
+// accumulates in term order with the reference's operation order.  Terms of skipped bases (window 0) are not copied at all.
+struct SweepTGArgs {
+	const double *delta; int64_t Dcap; int Q;
+	const double *termA, *termC; const int32_t *termRow, *termMeta, *termBasis, *bTermStart;
+	const double *omegaCost; int64_t NP; int nCost;       // omega rows rvOffset[2].. (cost coefficients), nCost of them
+	int basisCnt, chunkSize, nChunks;
+	const uint8_t *mask; int64_t Bcap;
+	const double *x; const int32_t *rvCOmCols;
+	double *partV; int32_t *partI;
+	int rps, stages;                                      // terms per ring stage (1, 2, 4 or 8) and ring depth (2..4)
+};
+
+__global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_gen(SweepTGArgs a) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int planes = 1 + a.Q, rps = a.rps, stages = a.stages;
+	const size_t rowDoubles = (size_t) planes * SD_TILE_W;
+	const uint32_t rowBytes = (uint32_t) (rowDoubles * 8);
+	const size_t slotBytes = (size_t) rowBytes + SD_TILE_W;                                // delta planes, then the mask bytes of the basis
+	const size_t stageBytes = (size_t) rps * slotBytes;
+	unsigned char *cost = smem_raw;                                                      // [nCost][512] doubles
+	unsigned char *ring = smem_raw + (size_t) a.nCost * TMA_ROW_BYTES;
+	uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t) stages * stageBytes);
+	uint64_t *empty = full + 4;
+	uint64_t *costBar = empty + 4;
+	double2 *s_ac = reinterpret_cast<double2 *>(costBar + 2);
+	int *s_meta = reinterpret_cast<int *>(s_ac + SW_BATCH);
+	int *s_basis = s_meta + SW_BATCH;
+	double *s_xq = reinterpret_cast<double *>(s_basis + SW_BATCH);                        // [64]
+	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	const int T0 = a.bTermStart[b0], T1 = a.bTermStart[b1];
+	const int nTerms = T1 - T0, nIter = (nTerms + rps - 1) / rps;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowDoubles;
+	if (tid == 0) {
+		for (int s = 0; s < stages; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+		sd_mbar_init(costBar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (int q = tid; q < a.Q; q += blockDim.x) s_xq[q] = a.x[a.rvCOmCols[q]];
+	__syncthreads();
+
+	if (tid >= TMA_CONSUMERS) {
+		// ---------------- producer warp ---------------------------------------------------------------------------------
+		const int lane = tid - TMA_CONSUMERS;
+		if (lane == 0) {
+			sd_mbar_expect_tx(costBar, (uint32_t) a.nCost * TMA_ROW_BYTES);
+			for (int r = 0; r < a.nCost; r++)
+				sd_bulk_g2s(cost + (size_t) r * TMA_ROW_BYTES, a.omegaCost + (size_t) r * a.NP + (size_t) tile * SD_TILE_W, TMA_ROW_BYTES, costBar);
+		}
+		int s = 0, ph = 0;
+		for (int it = 0; it < nIter; it++) {
+			const int t = T0 + it * rps + lane;
+			int meta = 0, row = 0, basis = 0;
+			if (lane < rps && t < T1) { meta = a.termMeta[t]; row = a.termRow[t]; basis = a.termBasis[t]; }
+			const bool live = (meta & 3) != 0;
+			const bool wantMask = live && (meta & 4) && a.mask != nullptr;
+			uint32_t bytes = live ? rowBytes + (wantMask ? SD_TILE_W : 0) : 0;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+			sd_mbar_wait(&empty[s], ph ^ 1);
+			if (lane == 0) sd_mbar_expect_tx(&full[s], bytes);
+			__syncwarp();
+			if (live) {
+				unsigned char *slot = ring + (size_t) s * stageBytes + (size_t) lane * slotBytes;
+				sd_bulk_g2s(slot, tileBase + (size_t) row * rowDoubles, rowBytes, &full[s]);
+				if (wantMask) sd_bulk_g2s(slot + rowBytes, a.mask + ((size_t) tile * a.Bcap + basis) * SD_TILE_W, SD_TILE_W, &full[s]);
+			}
+			if (++s == stages) { s = 0; ph ^= 1; }
+		}
+		return;
+	}
+
+	// ---------------- consumers ------------------------------------------------------------------------------------------
+	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
+	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+	double arg0 = 0.0, arg1 = 0.0;                                                         // stocUpdate.c:164
+	sd_mbar_wait(costBar, 0);
+	int s = 0, ph = 0;
+	for (int it = 0; it < nIter; it++) {
+		const int r0 = it * rps;
+		if (r0 % SW_BATCH == 0) {
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+			const int t = T0 + r0 + tid;
+			const bool ok = t < T1;
+			s_ac[tid] = ok ? make_double2(a.termA[t], a.termC[t]) : make_double2(0.0, 0.0);
+			s_meta[tid] = ok ? a.termMeta[t] : 0;
+			s_basis[tid] = ok ? a.termBasis[t] : 0;
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+		}
+		sd_mbar_wait(&full[s], ph);
+		for (int r = 0; r < rps; r++) {
+			const int j = (r0 + r) % SW_BATCH;
+			const int meta = s_meta[j];
+			if ((meta & 3) == 0) continue;                                                 // infeasible basis / outside both windows (or past the end)
+			const unsigned char *slot = ring + (size_t) s * stageBytes + (size_t) r * slotBytes;
+			const double2 *rowp = reinterpret_cast<const double2 *>(slot) + tid;
+			const double2 d = rowp[0];
+			const double2 ac = s_ac[j];
+			double m0 = 1.0, m1 = 1.0;                                                     // stocUpdate.c:167-170
+			const int om = meta >> 8;
+			if (om > 0) {
+				const double2 mm = reinterpret_cast<const double2 *>(cost + (size_t) (om - 1) * TMA_ROW_BYTES)[tid];
+				m0 = mm.x; m1 = mm.y;
+			}
+			arg0 = __dadd_rn(arg0, __dmul_rn(m0, __dsub_rn(__dadd_rn(ac.x, d.x), ac.y)));    // stocUpdate.c:174
+			arg1 = __dadd_rn(arg1, __dmul_rn(m1, __dsub_rn(__dadd_rn(ac.x, d.y), ac.y)));
+			double dx0 = 0.0, dx1 = 0.0;                                                   // stocUpdate.c:175
+			for (int q = 0; q < a.Q; q++) {
+				const double2 p = rowp[(size_t) (1 + q) * (SD_TILE_W / 2)];
+				dx0 = __dadd_rn(dx0, __dmul_rn(p.x, s_xq[q]));
+				dx1 = __dadd_rn(dx1, __dmul_rn(p.y, s_xq[q]));
+			}
+			arg0 = __dsub_rn(arg0, __dmul_rn(m0, dx0));
+			arg1 = __dsub_rn(arg1, __dmul_rn(m1, dx1));
+			if (meta & 4) {                                                                // the basis is complete: stocUpdate.c:163,178-181
+				bool f0 = true, f1 = true;
+				if (a.mask) {
+					const uchar2 mk = reinterpret_cast<const uchar2 *>(slot + rowBytes)[tid];
+					f0 = mk.x != 0; f1 = mk.y != 0;
+				}
+				const int b = s_basis[j];
+				if ((meta & 3) == 1) {
+					if (f0 && arg0 > oV0) { oV0 = arg0; oI0 = b; }
+					if (f1 && arg1 > oV1) { oV1 = arg1; oI1 = b; }
+				}
+				else {
+					if (f0 && arg0 > nV0) { nV0 = arg0; nI0 = b; }
+					if (f1 && arg1 > nV1) { nV1 = arg1; nI1 = b; }
+				}
+				arg0 = 0.0; arg1 = 0.0;
+			}
+		}
+		__syncwarp();
+		if ((tid & 31) == 0) sd_mbar_arrive(&empty[s]);
+		if (++s == stages) { s = 0; ph ^= 1; }
+	}
+	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
+	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
+	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
+	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
+	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
+	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
 }
 
 // ======================================================================================================
@@ -951,7 +1115,7 @@ static inline int sd_blocks(int64_t n, int t) { return (int) std::max<int64_t>(1
 
 // piCbarX + basis descriptors (+ x onto the device) in one launch.  x travels as a kernel parameter when it fits
 // (n1 < 256, every reference problem), otherwise through one H2D copy.
-static int sd_launch_prep(sdgpu_ctx *c, const double *X, int cutoff, int split, bool wantAllPiCbarX) {
+static int sd_launch_prep(sdgpu_ctx *c, const double *X, int cutoff, int split, bool wantAllPiCbarX, bool wantTerms = false) {
 	SdXParam xp;
 	const double *xDevIn = nullptr;
 	if (c->n1 + 1 <= 256) memcpy(xp.v, X, ((size_t) c->n1 + 1) * sizeof(double));
@@ -963,7 +1127,8 @@ static int sd_launch_prep(sdgpu_ctx *c, const double *X, int cutoff, int split, 
 	const int64_t n = std::max<int64_t>(std::max<int64_t>(c->basisCnt, wantAllPiCbarX ? c->sigmaCnt : 0), 1);
 	k_cut_prep<<<sd_blocks(n, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(xp, xDevIn, c->d_x, c->n1, c->d_sigmaPiCk, c->SP, c->n1c,
 			c->d_CCols, (int) c->sigmaCnt, wantAllPiCbarX ? c->d_piCbarX : nullptr, c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma,
-			c->d_sigmaPib, c->d_sigmaLam, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin);
+			c->d_sigmaPib, c->d_sigmaLam, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin,
+			c->d_tOmega, wantTerms ? c->d_termA : nullptr, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis);
 	sd_count_launch(c);
 	return 0;
 }
@@ -1037,6 +1202,37 @@ static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 	return 0;
 }
 
+// shared memory of k_sweep_tma_gen for a ring of `stages` x `rps` term slots
+static size_t sd_tma_gen_smem(const sdgpu_ctx *c, int rps, int stages) {
+	const int nCost = c->numRV - c->rvOffset[2];
+	return (size_t) nCost * TMA_ROW_BYTES + (size_t) stages * rps * ((size_t) (1 + c->Q) * TMA_ROW_BYTES + SD_TILE_W) + 10 * sizeof(uint64_t) +
+	       SW_BATCH * (sizeof(double2) + 2 * sizeof(int)) + 64 * sizeof(double);
+}
+
+// ring shape <terms per stage, stages>: the one that keeps the most bytes in flight per SM, a lone CTA per SM discounted (8 consumer
+// warps alone do not hide the FP64 compare chains).  Measured on B200 (profiles/r01_variant_gen.jsonl): Q = 0 with 4 cost columns
+// <8,2> x 2 CTAs 6.25 TB/s, <4,2> x 3 6.09, <8,3> x 1 4.25; Q = 2 with 8 cost columns <4,3> x 1 6.45, <1,2> x 3 6.15.
+// SDGPU_GEN_RPS / SDGPU_GEN_STAGES override (experiment knobs).  false = even the smallest ring does not fit.
+static bool sd_tma_gen_shape(const sdgpu_ctx *c, int *rps, int *stages) {
+	static int envRps = -1, envStages = -1;
+	if (envRps < 0) { const char *e = getenv("SDGPU_GEN_RPS"); envRps = e ? atoi(e) : 0; e = getenv("SDGPU_GEN_STAGES"); envStages = e ? atoi(e) : 0; }
+	const size_t smemPerSM = (size_t) 227 << 10, slot = (size_t) (1 + c->Q) * TMA_ROW_BYTES + SD_TILE_W;
+	if (envRps > 0 || envStages > 0) {
+		int r = envRps > 0 ? envRps : 4, st = envStages > 0 ? envStages : 2;
+		if ((r == 1 || r == 2 || r == 4 || r == 8) && st >= 2 && st <= 4 && sd_tma_gen_smem(c, r, st) + 1024 <= smemPerSM) { *rps = r; *stages = st; return true; }
+	}
+	double best = 0.0;
+	for (int st = 2; st <= 3; st++)
+		for (int r = 8; r >= 1; r >>= 1) {
+			const size_t smem = sd_tma_gen_smem(c, r, st) + 1024;              // + the per-CTA reservation
+			if (smem > smemPerSM) continue;
+			const int ctas = (int) std::min<size_t>(3, smemPerSM / smem);       // 70 registers x 288 threads: three CTAs at most
+			const double score = (double) ctas * st * r * slot * (ctas == 1 ? 0.7 : 1.0) + ctas;
+			if (score > best) { best = score; *rps = r; *stages = st; }
+		}
+	return best > 0.0;
+}
+
 static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, bool fuseNormalise) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
 	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
@@ -1050,13 +1246,31 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 	c->lastOmegaCnt = N;
 	c->cutFused = false;
 	if (N > 0 && c->basisCnt > 0) {
-		const bool general = c->maxPhiLen > 0;
-		if (sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, general)) return SDGPU_ERR;
+		const bool multiTerm = c->maxPhiLen > 0;
+		// random-cost problems (mask and/or multi-term bases): the term-linear TMA ring from ~4M (term, observation) pairs up
+		int genRps = 0, genStages = 0;
+		const bool genFits = c->rvd > 0 && sd_tma_gen_shape(c, &genRps, &genStages);
+		const bool useGenTma = genFits && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->termCnt * N * (1 + c->Q) >= ((int64_t) 4 << 20)));
+		if (sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, multiTerm && !useGenTma, useGenTma)) return SDGPU_ERR;
 		int chunkSize = 1, nChunks = 1;
 		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);
 		dim3 grid((unsigned) tiles, (unsigned) nChunks);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
-		if (general) {
+		if (useGenTma) {
+			SweepTGArgs g;
+			g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
+			g.termA = c->d_termA; g.termC = c->d_termC; g.termRow = c->d_termRow; g.termMeta = c->d_termMeta; g.termBasis = c->d_termBasis;
+			g.bTermStart = c->d_bTermStart;
+			g.omegaCost = c->d_omega + (size_t) c->rvOffset[2] * c->NP; g.NP = c->NP; g.nCost = c->numRV - c->rvOffset[2];
+			g.basisCnt = (int) c->basisCnt; g.chunkSize = chunkSize; g.nChunks = nChunks;
+			g.mask = c->d_mask; g.Bcap = c->caps.maxBasis; g.x = c->d_x; g.rvCOmCols = c->d_rvCOmCols;
+			g.partV = c->d_partV; g.partI = c->d_partI; g.rps = genRps; g.stages = genStages;
+			const size_t smem = sd_tma_gen_smem(c, genRps, genStages);
+			if (smem > c->tmaGenAttr) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaGenAttr = smem; }
+			k_sweep_tma_gen<<<grid, TMA_THREADS, smem, c->stream>>>(g);
+			c->stats.last_sweep_variant = 4;
+		}
+		else if (multiTerm) {
 			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
 			c->stats.last_sweep_variant = 3;
 		}
@@ -1083,7 +1297,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		sd_count_launch(c);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evD, c->stream));
 		// algorithmic bytes of the sweep: delta stream + per-observation weight and iStar + per-basis descriptors
-		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * c->basisCnt * (int64_t) N + (int64_t) N * 8 + c->basisCnt * 16;
+		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * c->termCnt * (int64_t) N + (c->rvd > 0 ? c->basisCnt * (int64_t) N : 0) + (int64_t) N * 8 + c->basisCnt * 16;
 
 		MergeArgs m;
 		m.partV = c->d_partV; m.partI = c->d_partI; m.nChunks = nChunks; m.NP = c->NP;

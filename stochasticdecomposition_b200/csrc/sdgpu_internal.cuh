@@ -121,6 +121,10 @@ struct sdgpu_ctx {
 	double  *d_piCbarX = nullptr;    // [SP]
 	double  *d_descA = nullptr, *d_descC = nullptr;   // per basis: sigma.pib, piCbarX of its first sigma
 	int32_t *d_descRow = nullptr, *d_descWin = nullptr; // per basis: lambda row, window (0 skip, 1 old, 2 new)
+	// per term of every basis (random-cost problems only, rvdOmCnt > 0): the descriptors the term-linear TMA sweep walks
+	double  *d_termA = nullptr, *d_termC = nullptr;     // sigma.pib, piCbarX of the term's sigma
+	int32_t *d_termRow = nullptr, *d_termMeta = nullptr, *d_termBasis = nullptr;   // lambda row; window | last-term << 2 | omegaIdx << 8; basis
+	size_t   tmaGenAttr = 0;
 	double  *d_partV = nullptr;      // [2][chunks][NP] per-chunk running maxima (old, new)
 	int32_t *d_partI = nullptr;      // [2][chunks][NP]
 	int32_t *d_iStar = nullptr;      // [NP]

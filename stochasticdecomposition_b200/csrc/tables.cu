@@ -609,6 +609,11 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	SD_TRY(sd_alloc(&c->d_x, (size_t) c->n1 + 2)); SD_TRY(sd_alloc(&c->d_piCbarX, (size_t) c->SP));
 	SD_TRY(sd_alloc(&c->d_descA, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_descC, (size_t) c->BP));
 	SD_TRY(sd_alloc(&c->d_descRow, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_descWin, (size_t) c->BP));
+	if (c->rvd > 0) {
+		SD_TRY(sd_alloc(&c->d_termA, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_termC, (size_t) c->termCap));
+		SD_TRY(sd_alloc(&c->d_termRow, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_termMeta, (size_t) c->termCap));
+		SD_TRY(sd_alloc(&c->d_termBasis, (size_t) c->termCap));
+	}
 	SD_TRY(sd_alloc(&c->d_partV, (size_t) 2 * c->maxChunks * c->NP)); SD_TRY(sd_alloc(&c->d_partI, (size_t) 2 * c->maxChunks * c->NP));
 	SD_TRY(sd_alloc(&c->d_iStar, (size_t) c->NP));
 	SD_TRY(sd_alloc(&c->d_tilePart, (size_t) c->nTiles * (4 + c->n1c + c->Q)));
@@ -629,7 +634,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 		c->d_sigmaLam, c->d_sigmaCk, c->d_delta, c->d_mask, c->d_bCk, c->d_bFeas, c->d_bPhiLen, c->d_bTermStart, c->d_tSigma, c->d_tOmega, c->d_state,
 		c->d_rvdOmCols, c->d_senx, c->d_fPiDet, c->d_fPhi, c->d_fGBar, c->d_fPsi, c->d_fCstat, c->d_fHas, c->d_fFlags,
 		c->d_vecIn, c->d_cand, c->d_candC, c->d_x, c->d_piCbarX, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin, c->d_partV, c->d_partI,
-		c->d_iStar, c->d_tilePart, c->d_cutPartial, c->d_cutOut };
+		c->d_iStar, c->d_tilePart, c->d_cutPartial, c->d_cutOut, c->d_termA, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis };
 	for (void *p : dev) if (p) cudaFree(p);
 	if (c->h_pinD) cudaFreeHost(c->h_pinD);
 	if (c->h_pinI) cudaFreeHost(c->h_pinI);

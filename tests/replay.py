@@ -37,8 +37,10 @@ def pi_eval_flag(k: int, dual_stability=1, pi_eval_start=0, pi_cycle=1) -> bool:
 
 def replay(api: Api, problem: Problem, trace: Trace, caps: Caps, tol=1e-3, lb=0.0, dual_stability=1,
            pi_eval_start=0, pi_cycle=1, infeasible_every=0, cut_every=1, device=0, sd_cut_variant="sd_cut",
-           feas_density=0.85) -> Record:
+           feas_density=0.85, sweep_variant=None) -> Record:
     t = api.create(problem, caps, device)
+    if sweep_variant is not None and api.has("set_sweep_variant"):
+        t.set_sweep_variant(sweep_variant)
     rec = Record(tables=t)
     rvd = problem.rvdOmCnt
     K = trace.observ.shape[0]

@@ -16,16 +16,21 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9   # BASELINE.json: "cut coefficients ... within 1e-9 relative"
 
 
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_trace_parity(name):
+def test_trace_parity(name, variant):
+    """variant 0: the size-based default (these small traces take the LDG / per-term-gather kernels); variant 2: the TMA rings
+    forced (k_sweep_tma, k_sweep_tma_q, and for the random-cost cases the term-linear k_sweep_tma_gen)."""
     pk, K, dpool, opool, phi_len, rk = CASES[name]
     prob = make_problem(1000 + len(name), **pk)
     trace = make_trace(prob, K, seed=77 + K, dual_pool=dpool, obs_pool=opool, phi_len=phi_len)
     caps = roomy_caps(K, phi_len)
     port = replay(oracle_loader.oracle(), prob, trace, caps, **rk)
-    gpu = replay(sd.load_library(), prob, trace, caps, **rk)
+    gpu = replay(sd.load_library(), prob, trace, caps, sweep_variant=variant, **rk)
     assert_records_match(port, gpu, exact_cut=False, rtol=RTOL)
     assert_tables_identical(port.tables, gpu.tables)
+    if variant == 2 and pk.get("rvd", 0) > 0:
+        assert gpu.tables.stats()["last_sweep_variant"] == 4
 
 
 @pytest.mark.parametrize("shape", ["pgp2", "20term_T", "ssn"])
@@ -95,6 +100,58 @@ def test_bulk_multi_tile_multi_chunk(D, N, Q, variant):
         t.calc_delta(True, oi)
     a = to.get_delta_block(0, D, N, N + 1); b = tg.get_delta_block(0, D, N, N + 1)
     assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("S,N,Q,phi,density", [(900, 1500, 0, 2, 0.8), (600, 1100, 2, 1, 0.5), (1300, 700, 0, 0, 0.9), (640, 1030, 3, 3, 0.7)])
+def test_random_cost_multi_tile_multi_chunk(S, N, Q, phi, density, variant):
+    """Random-cost shape (rvdOmCnt > 0) over several observation tiles and basis chunks: multi-term bases whose terms straddle
+    ring stages and descriptor batches, a sparse obsFeasible mask, infeasible bases, duplicated duals (ties), both windows.
+    variant 1 = the per-term gather kernels, variant 2 = the term-linear TMA ring; iStar must be bit-exact either way."""
+    rvd = 4
+    prob = make_problem(21, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=Q, rvd=rvd)
+    rng = np.random.default_rng(S + N + phi)
+    pis = rng.uniform(-1, 1, (S, prob.rows + 1)) * (rng.random((S, prob.rows + 1)) > 0.3)
+    for d in rng.choice(np.arange(1, S), size=max(1, S // 40), replace=False):
+        pis[d] = pis[rng.integers(0, d)]
+    nb = S // (1 + phi)
+    iters = np.ceil((np.arange(S) + 1) * (1.25 * N) / S).astype(np.int32)
+    obs = rng.normal(0, 1, (N, prob.numRV + 1)); obs[:, 0] = 0
+    obs[rng.choice(N, 8, replace=False)] = 0.0
+    weights = (1 + rng.poisson(0.25, N)).astype(np.int32)
+    k = int(weights.sum())
+    feas_basis = rng.random(nb) > 0.05
+    omega_idx = [[0] + [int(v) for v in rng.integers(1, rvd + 1, phi)] for _ in range(nb)]
+    masks = rng.random((nb, N)) < density
+    caps = Caps(S + 2, S + 2, nb + 2, N + 3, 1 + phi)
+    tabs = []
+    for api in (oracle_loader.oracle(), sd.load_library()):
+        t = api.create(prob, caps)
+        t.omega_append_bulk(obs, weights)
+        li, si = t.update_dual_bulk(pis, None, iters, -1.0)
+        t.calc_delta_block(0, S, 0, N)
+        for b in range(nb):
+            sig = [int(si[b * (1 + phi) + j]) for j in range(1 + phi)]
+            t.basis_append(int(iters[b * (1 + phi)]), bool(feas_basis[b]), sig, omega_idx[b])
+            if feas_basis[b]:
+                t.basis_set_obs_feasible_row(b, masks[b].tolist())
+        tabs.append(t)
+    to, tg = tabs
+    tg.set_sweep_variant(variant)
+    x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
+    for pi_eval in (0, 1):
+        co = to.sd_cut(x, k, pi_eval, 0.0); cg = tg.sd_cut(x, k, pi_eval, 0.0)
+        assert (co is None) == (cg is None)
+        assert tg.stats()["last_sweep_variant"] == (4 if variant == 2 else (3 if phi > 0 else 1))
+        if co is None:
+            continue
+        assert np.array_equal(co.iStar, cg.iStar), np.nonzero(co.iStar != cg.iStar)[0][:10]
+        assert len(set(co.iStar.tolist())) > 3
+        scale = max(abs(co.alpha), np.abs(co.beta[1:]).max())
+        assert abs(co.alpha - cg.alpha) <= RTOL * abs(co.alpha)
+        assert np.abs(co.beta - cg.beta).max() <= RTOL * scale
+        assert abs(co.cummOld - cg.cummOld) <= RTOL * max(abs(co.cummOld), 1e-300)
+        assert abs(co.cummAll - cg.cummAll) <= RTOL * max(abs(co.cummAll), 1e-300)
 
 
 def test_bulk_dedup_chain_matches_single_calls():
