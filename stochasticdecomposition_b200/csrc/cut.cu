@@ -56,18 +56,17 @@ __device__ __forceinline__ double sd_block_sum(double v, double *s_red) {
 }
 
 // sum_k col[k*stride] * s_x[k], left to right from 0.0 with separate multiply and add (vXv, cuts.c:106); the loads of a
-// batch of 8 are issued together so the chain of dependent adds does not also serialise the memory latency
+// batch of 32 are issued together (past the end: the last element again, not added) so the chain of dependent adds does not
+// also serialise the memory latency -- three round trips for the 89 columns of ssn instead of twelve
 __device__ __forceinline__ double sd_dot_strided(const double *__restrict__ col, size_t stride, const double *s_x, int n) {
 	double acc = 0.0;
-	int k = 0;
-	for (; k + 8 <= n; k += 8) {
-		double v[8];
+	for (int k = 0; k < n; k += 32) {
+		double v[32];
 #pragma unroll
-		for (int u = 0; u < 8; u++) v[u] = col[(size_t) (k + u) * stride];
+		for (int u = 0; u < 32; u++) v[u] = col[(size_t) min(k + u, n - 1) * stride];
 #pragma unroll
-		for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, __dmul_rn(v[u], s_x[k + u]));
+		for (int u = 0; u < 32; u++) if (k + u < n) acc = __dadd_rn(acc, __dmul_rn(v[u], s_x[k + u]));
 	}
-	for (; k < n; k++) acc = __dadd_rn(acc, __dmul_rn(col[(size_t) k * stride], s_x[k]));
 	return acc;
 }
 
@@ -634,6 +633,7 @@ struct MergeArgs {
 	const int32_t *bTermStart, *tSigma, *tOmega;
 	int randCost;                 // num->rvdOmCnt > 0: the cuts.c:142-159 branch
 	int32_t *iStar; int32_t *iStarHost; int iStarHostCap; double *tilePart; int P;
+	int mW;                       // observations per merge CTA: 64, 128, 256 or 512
 	// epilogue run by the last block: tile partials -> un-normalised cut [-> normalised cut in mapped host memory]
 	int n1; const int32_t *CCols, *qCols; double *partial; int fuseNormalise, numSamples; double *hostRes; SdDevState *st;
 	// NVLink peer exchange (peerRanks > 1): every rank's buffer, this rank's index, the sequence number of this cut
@@ -651,26 +651,28 @@ __device__ __forceinline__ unsigned *sd_peer_flag(unsigned char *buf, int G, int
 #define MG_THREADS SD_TILE_W
 
 #ifdef SD_PHASE_CLOCKS
+// debug build only (tools/merge_phases.py): global-timer stamps of the merge kernel's phases; phases 0-4 by block 0, 5.. by the last block
 __device__ long long g_sd_phase[16];
-#define SD_PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sd_phase[i] = clock64(); } while (0)
+__device__ __forceinline__ long long sd_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SD_PHASE(i) do { if ((((i) >= 5 && (i) < 10) || blockIdx.x == 0) && threadIdx.x == 0) g_sd_phase[i] = sd_gtime(); } while (0)
 extern "C" int sdgpu_debug_phase_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_sd_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -2; }
 #else
 #define SD_PHASE(i)
 #endif
 
-// running (max, first index) over the per-chunk partial maxima of one observation, chunks in ascending basis order; the
-// loads of 16 chunks are issued together (the compare chain is sequential, the memory latency must not be)
-__device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int nChunks, int64_t NP,
+// running (max, first index) over the per-chunk partial maxima [c0, c1) of one observation, chunks in ascending basis order; the
+// loads of 8 chunks are issued together (the compare chain is sequential, the memory latency must not be)
+__device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int c0, int c1, int64_t NP,
 		double &bestV, int &bestI) {
-	for (int c = 0; c < nChunks; c += 16) {
-		double v[16]; int ix[16];
+	for (int c = c0; c < c1; c += 8) {
+		double v[8]; int ix[8];
 #pragma unroll
-		for (int u = 0; u < 16; u++) {                       // past the end: re-read the last chunk, it cannot beat itself under strict '>'
-			const int cc = min(c + u, nChunks - 1);
+		for (int u = 0; u < 8; u++) {                        // past the end: re-read the last chunk, it cannot beat itself under strict '>'
+			const int cc = min(c + u, c1 - 1);
 			v[u] = __ldcg(pv + (size_t) cc * NP); ix[u] = __ldcg(pi + (size_t) cc * NP);
 		}
 #pragma unroll
-		for (int u = 0; u < 16; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
+		for (int u = 0; u < 8; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
 	}
 }
 
@@ -726,26 +728,50 @@ __global__ void k_cut_exchange(MergeArgs a) {
 	sd_cut_exchange_and_store(s_cut, a.peerRanks, a.peerRank, a.peerSeq, a.peerBufs, a.n1, a.partial, a.fuseNormalise, a.numSamples, a.hostRes);
 }
 
+// One CTA of 512 threads looks after W = a.mW observations (64, 128, 256 or 512 -- a whole delta tile only when there are many
+// tiles) with L = 512 / W threads per observation: thread (lane, observation) merges its contiguous share of the basis chunks,
+// all loads in flight at once, and lane 0 combines the L shares in lane order (strict '>': the lowest chunk wins ties).  With
+// few observations (real problems: N <= 5 000) this spreads the merge over ~80 SMs instead of 10 and turns eight dependent
+// memory round trips per window into one.
 __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	__shared__ int s_istar[SD_TILE_W];
 	__shared__ int s_w[SD_TILE_W];
 	__shared__ double s_red[32];
+	__shared__ double s_mv[2][MG_THREADS];
+	__shared__ int s_mi[2][MG_THREADS];
 	extern __shared__ double s_dyn[];        // [groups][n1c] partial sums of the sigma.piC part
-	const int tile = blockIdx.x, tid = threadIdx.x;
-	const int64_t o = (int64_t) tile * SD_TILE_W + tid;
+	const int W = a.mW, L = MG_THREADS / W;
+	const int sub = blockIdx.x, tid = threadIdx.x;
+	const int ol = tid & (W - 1), lane = tid / W;
+	const int64_t o = (int64_t) sub * W + ol;
 	const bool valid = o < a.omegaCnt;
 	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
-	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride + tid;
+	const double *tileBase = a.delta + (size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W);
 
 	double oldV = -DBL_MAX, newV = -DBL_MAX;
 	int oldI = -1, newI = -1, istar = -1, wgt = 0;
 	double tAlpha = 0.0, tOld = 0.0, tAll = 0.0, tMiss = 0.0;
 	SD_PHASE(0);
 	if (valid) {
-		sd_merge_chunks(a.partV + o, a.partI + o, a.nChunks, a.NP, oldV, oldI);
+		const int cpl = (a.nChunks + L - 1) / L, c0 = lane * cpl, c1 = min(a.nChunks, c0 + cpl);
+		sd_merge_chunks(a.partV + o, a.partI + o, c0, c1, a.NP, oldV, oldI);
+		if (a.pi_eval) sd_merge_chunks(a.partV + (size_t) a.nChunks * a.NP + o, a.partI + (size_t) a.nChunks * a.NP + o, c0, c1, a.NP, newV, newI);
+	}
+	SD_PHASE(10);
+	if (L > 1) {
+		s_mv[0][tid] = oldV; s_mi[0][tid] = oldI; s_mv[1][tid] = newV; s_mi[1][tid] = newI;
+		__syncthreads();
+		if (lane == 0)
+			for (int l = 1; l < L; l++) {                         // ascending lane = ascending basis index
+				const double ov = s_mv[0][l * W + ol], nv = s_mv[1][l * W + ol];
+				if (ov > oldV) { oldV = ov; oldI = s_mi[0][l * W + ol]; }
+				if (nv > newV) { newV = nv; newI = s_mi[1][l * W + ol]; }
+			}
+	}
+	const bool owner = valid && lane == 0;
+	if (owner) {
 		wgt = a.omegaW[o];
 		if (a.pi_eval) {
-			sd_merge_chunks(a.partV + (size_t) a.nChunks * a.NP + o, a.partI + (size_t) a.nChunks * a.NP + o, a.nChunks, a.NP, newV, newI);
 			double argmax = fmax(oldV, newV);                     // cuts.c:124
 			istar = (newV > oldV) ? newI : oldI;                  // cuts.c:125 (an empty window carries index -1)
 			tOld = fmax(oldV - a.lb, 0.0) * wgt;                  // cuts.c:127
@@ -753,6 +779,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		}
 		else
 			istar = oldI;                                         // cuts.c:132
+		SD_PHASE(11);
 		a.iStar[o] = istar;
 		if (o < a.iStarHostCap) a.iStarHost[o] = istar;           // small cuts: iStar lands in mapped host memory, no D2H copy
 		if (istar < 0) tMiss = 1.0;                               // cuts.c:136-139
@@ -772,9 +799,8 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		}
 	}
 	SD_PHASE(1);
-	s_istar[tid] = valid ? istar : -1;
-	s_w[tid] = wgt;
-	double *out = a.tilePart + (size_t) tile * a.P;
+	if (lane == 0) { s_istar[ol] = valid ? istar : -1; s_w[ol] = wgt; }
+	double *out = a.tilePart + (size_t) sub * a.P;
 	double r;
 	r = sd_block_sum(tAlpha, s_red); if (tid == 0) out[0] = r;
 	r = sd_block_sum(tOld, s_red);   if (tid == 0) out[1] = r;
@@ -785,7 +811,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	// delta.piC part of beta: one block sum per random T element   cuts.c:156-157 / :166-167
 	for (int q = 0; q < a.Q; q++) {
 		double v = 0.0;
-		if (valid && istar >= 0) {
+		if (owner && istar >= 0) {
 			if (!a.randCost)
 				v = __dmul_rn(tileBase[(size_t) a.sigmaLam[istar] * rowStride + (size_t) (1 + q) * SD_TILE_W], (double) wgt);
 			else
@@ -803,12 +829,12 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	__syncthreads();
 	SD_PHASE(3);
 	if (a.n1c > 0) {
-		const int kp = ((a.n1c + 31) / 32) * 32;
-		const int groups = max(1, MG_THREADS / kp);
-		const int g = tid / kp, k = tid % kp;
-		if (g < groups && k < a.n1c) {
-			const int per = (SD_TILE_W + groups - 1) / groups;
-			const int w0 = g * per, w1 = min(SD_TILE_W, w0 + per);
+		const int kp = min(((a.n1c + 31) / 32) * 32, MG_THREADS);
+		const int groups = MG_THREADS / kp;
+		const int g = tid / kp;
+		const int per = (W + groups - 1) / groups;
+		const int w0 = g * per, w1 = min(W, w0 + per);
+		for (int k = tid % kp; g < groups && k < a.n1c; k += kp) {
 			double acc = 0.0;
 			int w = w0;
 			if (!a.randCost) {
@@ -826,7 +852,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 				if (!a.randCost)
 					acc = __dadd_rn(acc, __dmul_rn(a.sigmaPiCr[(size_t) is * a.n1cP + k], (double) s_w[w]));
 				else {
-					const int64_t ow = (int64_t) tile * SD_TILE_W + w;
+					const int64_t ow = (int64_t) sub * W + w;
 					for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
 						int s = a.tSigma[t];
 						double m = (t == a.bTermStart[is]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + ow];
@@ -837,14 +863,14 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 			s_dyn[g * a.n1c + k] = acc;
 		}
 		__syncthreads();
-		if (tid < a.n1c) {
+		for (int k = tid; k < a.n1c; k += blockDim.x) {
 			double acc = 0.0;
-			for (int gg = 0; gg < groups; gg++) acc = __dadd_rn(acc, s_dyn[gg * a.n1c + tid]);
-			out[4 + tid] = acc;
+			for (int gg = 0; gg < groups; gg++) acc = __dadd_rn(acc, s_dyn[gg * a.n1c + k]);
+			out[4 + k] = acc;
 		}
 	}
 
-	// ---- epilogue: the last tile to finish sums the tile partials in tile order (cuts.c:155-167) and, on a single GPU,
+	// ---- epilogue: the last CTA to finish sums the per-CTA partials in CTA order (cuts.c:155-167) and, on a single GPU,
 	// applies cuts.c:184-188 and hands the cut to the host through mapped pinned memory
 	SD_PHASE(4);
 	if (!sd_is_last_block(&a.st->cutTicket)) return;
@@ -867,6 +893,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	}
 	for (int c = tid; c <= a.n1 + 3; c += blockDim.x) s_cut[c] = 0.0;
 	__syncthreads();
+	SD_PHASE(6);
 	// CCols are distinct columns, so the sigma.piC scatter is conflict free and runs one thread per column (a serial loop here
 	// costs one uncached index load per column: 45 us at n1c = 89); the few delta.piC columns may coincide with them and
 	// with each other, so they follow in q order, exactly the order of cuts.c:155-157 / :165-167 for every position
@@ -878,8 +905,9 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		s_cut[a.n1 + 1] = s_tot[1]; s_cut[a.n1 + 2] = s_tot[2]; s_cut[a.n1 + 3] = s_tot[3];
 	}
 	__syncthreads();
+	SD_PHASE(7);
 	sd_cut_exchange_and_store(s_cut, a.peerRanks, a.peerRank, a.peerSeq, a.peerBufs, a.n1, a.partial, a.fuseNormalise, a.numSamples, a.hostRes);
-	SD_PHASE(6);
+	SD_PHASE(8);
 }
 
 // cuts.c:184-188
@@ -1317,10 +1345,16 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		for (int r = 0; r < 16; r++) m.peerBufs[r] = peer && r < c->peerRanks ? c->d_peerBufs[r] : nullptr;
 		m.hostRes = c->d_cutRes; m.st = c->d_state;
 		c->cutFused = m.fuseNormalise != 0;
-		const int kp = ((c->n1c + 31) / 32) * 32;
-		const int groups = c->n1c > 0 ? std::max(1, MG_THREADS / kp) : 1;
+		// observations per merge CTA: as few as keeps the grid within two waves (the last CTA adds up one partial vector per CTA)
+		int smCount = 148;
+		cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, c->device);
+		int mW = 64;
+		while (mW < SD_TILE_W && (N + mW - 1) / mW > 2 * smCount) mW <<= 1;
+		m.mW = mW;
+		const int kp = std::min(((c->n1c + 31) / 32) * 32, MG_THREADS);
+		const int groups = c->n1c > 0 ? MG_THREADS / kp : 1;
 		const size_t dyn = (size_t) std::max(std::max(1, groups * c->n1c), P + c->n1 + 4) * 8;
-		k_cut_merge<<<tiles, MG_THREADS, dyn, c->stream>>>(m);
+		k_cut_merge<<<(N + mW - 1) / mW, MG_THREADS, dyn, c->stream>>>(m);
 		sd_count_launch(c);
 	}
 	else {

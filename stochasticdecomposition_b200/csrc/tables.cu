@@ -616,7 +616,7 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	}
 	SD_TRY(sd_alloc(&c->d_partV, (size_t) 2 * c->maxChunks * c->NP)); SD_TRY(sd_alloc(&c->d_partI, (size_t) 2 * c->maxChunks * c->NP));
 	SD_TRY(sd_alloc(&c->d_iStar, (size_t) c->NP));
-	SD_TRY(sd_alloc(&c->d_tilePart, (size_t) c->nTiles * (4 + c->n1c + c->Q)));
+	SD_TRY(sd_alloc(&c->d_tilePart, (size_t) c->nTiles * (SD_TILE_W / 64) * (4 + c->n1c + c->Q)));   // one partial vector per merge CTA (>= 64 observations each)
 	SD_TRY(sd_alloc(&c->d_cutPartial, (size_t) c->n1 + 4)); SD_TRY(sd_alloc(&c->d_cutOut, (size_t) c->n1 + 4));
 #undef SD_TRY
 	if (cudaDeviceSynchronize() != cudaSuccess) { sdgpu_fail("device error during create"); sdgpu_destroy(c); return SDGPU_ERR; }
