@@ -18,6 +18,7 @@
 // bit-identical to the CPU path; (max, index) merges keep the LOWEST index among equal maxima (strict '>'
 // in stocUpdate.c:178) and the old window wins ties against the new one (cuts.c:125): iStar is bit-exact.
 #include <cfloat>
+#include <cmath>
 #include <climits>
 #include <cstring>
 #include <cstdlib>
@@ -875,20 +876,34 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	SD_PHASE(4);
 	if (!sd_is_last_block(&a.st->cutTicket)) return;
 	SD_PHASE(5);
-	double *s_tot = s_dyn;                                   // [P], then the cut vector [n1+4]
-	double *s_cut = s_dyn + a.P;
+	// thread (group, column) adds the partials of its contiguous share of the CTAs, loads eight at a time; the group sums are
+	// combined in group order: fixed order, a fifth of the dependent round trips (P = 93 columns -> 5 groups)
 	const int nT = gridDim.x;
+	const int kpP = min(((a.P + 31) / 32) * 32, MG_THREADS), groupsP = MG_THREADS / kpP;
+	double *s_grp = s_dyn;                                   // [groupsP][P], then the totals [P], then the cut vector [n1+4]
+	double *s_tot = s_dyn + (size_t) groupsP * a.P;
+	double *s_cut = s_tot + a.P;
+	{
+		const int g = tid / kpP, perT = (nT + groupsP - 1) / groupsP;
+		const int t0 = g * perT, t1 = min(nT, t0 + perT);
+		for (int p = tid % kpP; g < groupsP && p < a.P; p += kpP) {
+			double acc = 0.0;
+			int t = t0;
+			for (; t + 8 <= t1; t += 8) {
+				double v[8];
+#pragma unroll
+				for (int u = 0; u < 8; u++) v[u] = __ldcg(a.tilePart + (size_t) (t + u) * a.P + p);
+#pragma unroll
+				for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
+			}
+			for (; t < t1; t++) acc = __dadd_rn(acc, __ldcg(a.tilePart + (size_t) t * a.P + p));
+			s_grp[g * a.P + p] = acc;
+		}
+	}
+	__syncthreads();
 	for (int p = tid; p < a.P; p += blockDim.x) {
 		double acc = 0.0;
-		int t = 0;
-		for (; t + 8 <= nT; t += 8) {
-			double v[8];
-#pragma unroll
-			for (int u = 0; u < 8; u++) v[u] = __ldcg(a.tilePart + (size_t) (t + u) * a.P + p);
-#pragma unroll
-			for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
-		}
-		for (; t < nT; t++) acc = __dadd_rn(acc, __ldcg(a.tilePart + (size_t) t * a.P + p));
+		for (int g = 0; g < groupsP; g++) acc = __dadd_rn(acc, s_grp[g * a.P + p]);
 		s_tot[p] = acc;
 	}
 	for (int c = tid; c <= a.n1 + 3; c += blockDim.x) s_cut[c] = 0.0;
@@ -1179,16 +1194,26 @@ static SweepGenArgs sd_gen_args(sdgpu_ctx *c, int chunkSize, int nChunks) {
 	return g;
 }
 
-// pick the basis-chunk count: enough CTAs to fill 148 SMs x 4 resident CTAs for a few waves, never more than the
-// scratch allows, never chunks smaller than one descriptor batch
+// pick the basis-chunk count.  The sweep kernels keep three CTAs per SM resident (444 slots on 148 SMs).  Measured on B200
+// (tools/chunk_probe.py, profiles/r01_chunk_probe.jsonl): what costs is a grid that ends just past a whole number of waves --
+// 256 tiles x 7 chunks = 4.04 waves ran at 6.87 TB/s, 5 / 12 / 26 / 52 chunks (2.9 / 6.9 / 15.0 / 30.0 waves) at 7.23-7.32 TB/s,
+// and with 10 tiles 44 chunks (one full wave) beat 64 (1.44 waves) -- and more, shorter CTAs shrink the tail.  So: as many chunks
+// as the scratch and a minimum chunk length allow, up to ~32 waves, then step down to the nearest count whose last wave is at
+// least 60 % full.
 static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks) {
 	int smCount = 148;
 	cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, c->device);
-	int64_t target = (int64_t) smCount * 4 * 3;
-	int64_t want = std::max<int64_t>(1, (target + tiles - 1) / tiles);
-	want = std::min<int64_t>(want, c->maxChunks);
-	want = std::min<int64_t>(want, std::max<int64_t>(1, (c->basisCnt + 31) / 32));   // at least four load batches per chunk: the merge
-	                                                                                 // kernel pays ~0.3 us of latency per 16 chunks and window
+	const double slots = (double) smCount * 3;
+	int64_t cmax = std::min<int64_t>(c->maxChunks, std::max<int64_t>(1, (c->basisCnt + 31) / 32));   // at least four load batches per chunk
+	cmax = std::min<int64_t>(cmax, std::max<int64_t>(1, (int64_t) ceil(32.0 * slots / tiles)));
+	int64_t want = cmax;
+	for (int64_t cc = cmax; cc >= std::max<int64_t>(1, cmax / 2); cc--) {
+		const double w = tiles * (double) cc / slots;
+		if (ceil(w) - w <= 0.4) { want = cc; break; }
+	}
+	static int envChunks = -1;                // SDGPU_CHUNKS = experiment knob (forces the chunk count, within the scratch limit)
+	if (envChunks < 0) { const char *e = getenv("SDGPU_CHUNKS"); envChunks = e ? atoi(e) : 0; }
+	if (envChunks > 0) want = std::min<int64_t>(std::min<int64_t>(envChunks, c->maxChunks), std::max<int64_t>(1, c->basisCnt));
 	int cs = (int) ((c->basisCnt + want - 1) / want);
 	cs = std::max(cs, 1);
 	*chunkSize = cs;
@@ -1345,15 +1370,16 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		for (int r = 0; r < 16; r++) m.peerBufs[r] = peer && r < c->peerRanks ? c->d_peerBufs[r] : nullptr;
 		m.hostRes = c->d_cutRes; m.st = c->d_state;
 		c->cutFused = m.fuseNormalise != 0;
-		// observations per merge CTA: as few as keeps the grid within two waves (the last CTA adds up one partial vector per CTA)
+		// observations per merge CTA: as few as keeps the grid within four CTAs per SM (the last CTA adds up one partial vector per CTA)
 		int smCount = 148;
 		cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, c->device);
 		int mW = 64;
-		while (mW < SD_TILE_W && (N + mW - 1) / mW > 2 * smCount) mW <<= 1;
+		while (mW < SD_TILE_W && (N + mW - 1) / mW > 4 * smCount) mW <<= 1;
 		m.mW = mW;
 		const int kp = std::min(((c->n1c + 31) / 32) * 32, MG_THREADS);
 		const int groups = c->n1c > 0 ? MG_THREADS / kp : 1;
-		const size_t dyn = (size_t) std::max(std::max(1, groups * c->n1c), P + c->n1 + 4) * 8;
+		const int groupsP = MG_THREADS / std::min(((P + 31) / 32) * 32, MG_THREADS);
+		const size_t dyn = (size_t) std::max(std::max(1, groups * c->n1c), (groupsP + 1) * P + c->n1 + 4) * 8;
 		k_cut_merge<<<(N + mW - 1) / mW, MG_THREADS, dyn, c->stream>>>(m);
 		sd_count_launch(c);
 	}
