@@ -324,16 +324,18 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) k_sweep_tma(SweepArgs a
 
 // The same ring for problems with random technology-matrix elements (Q > 0): in the tiled layout the 1+Q planes of one
 // dual row are contiguous, so one bulk copy of (1+Q) x 4 KiB brings delta.pib and all of delta.piC for 512 observations.
-// Rows per stage (rps, a power of two) keeps a stage near 32 KiB; two stages.
-__global__ void __launch_bounds__(TMA_THREADS, 2) k_sweep_tma_q(SweepArgs a, int rps) {
+// Rows per stage (rps: 1, 2, 4 or 8) and ring depth (stages: 2..4) are picked on the host for the most bytes in flight per SM;
+// lane r of the producer warp looks after row r of a stage.
+__global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_q(SweepArgs a, int rps, int stages) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int planes = 1 + a.Q;
 	const size_t rowDoubles = (size_t) planes * SD_TILE_W;
-	const size_t stageBytes = (size_t) rps * rowDoubles * 8;
+	const uint32_t rowBytes = (uint32_t) (rowDoubles * 8);
+	const size_t stageDoubles = (size_t) rps * rowDoubles;
 	double *ring = reinterpret_cast<double *>(smem_raw);
-	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 2 * stageBytes);
-	uint64_t *empty = full + 2;
-	double2 *s_ac = reinterpret_cast<double2 *>(empty + 2);
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t) stages * stageDoubles * 8);
+	uint64_t *empty = full + 4;
+	double2 *s_ac = reinterpret_cast<double2 *>(empty + 4);
 	int *s_win = reinterpret_cast<int *>(s_ac + SW_BATCH);
 	double *s_xq = reinterpret_cast<double *>(s_win + SW_BATCH);                          // [64]
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
@@ -341,31 +343,31 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_sweep_tma_q(SweepArgs a, int
 	const int nRows = b1 - b0, nIter = (nRows + rps - 1) / rps;
 	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowDoubles;
 	if (tid == 0) {
-		for (int s = 0; s < 2; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+		for (int s = 0; s < stages; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	for (int q = tid; q < a.Q; q += blockDim.x) s_xq[q] = a.x[a.rvCOmCols[q]];
 	__syncthreads();
 
 	if (tid >= TMA_CONSUMERS) {
-		if (tid == TMA_CONSUMERS) {
-			for (int it = 0; it < nIter; it++) {
-				const int s = it & 1;
-				sd_mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
-				const int r0 = it * rps, nr = min(rps, nRows - r0);
-				sd_mbar_expect_tx(&full[s], (uint32_t) (nr * rowDoubles * 8));
-				for (int r = 0; r < nr; r++) {
-					const int row = a.descRow[b0 + r0 + r];
-					sd_bulk_g2s(ring + (size_t) s * rps * rowDoubles + (size_t) r * rowDoubles, tileBase + (size_t) row * rowDoubles,
-							(uint32_t) (rowDoubles * 8), &full[s]);
-				}
-			}
+		const int lane = tid - TMA_CONSUMERS;
+		int s = 0, ph = 0;
+		for (int it = 0; it < nIter; it++) {
+			const int r0 = it * rps, nr = min(rps, nRows - r0);
+			const int row = lane < nr ? a.descRow[b0 + r0 + lane] : 0;
+			sd_mbar_wait(&empty[s], ph ^ 1);
+			if (lane == 0) sd_mbar_expect_tx(&full[s], (uint32_t) nr * rowBytes);
+			__syncwarp();
+			if (lane < nr)
+				sd_bulk_g2s(ring + (size_t) s * stageDoubles + (size_t) lane * rowDoubles, tileBase + (size_t) row * rowDoubles, rowBytes, &full[s]);
+			if (++s == stages) { s = 0; ph ^= 1; }
 		}
 		return;
 	}
 
 	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
 	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+	int s = 0, ph = 0;
 	for (int it = 0; it < nIter; it++) {
 		const int r0 = it * rps;
 		if (r0 % SW_BATCH == 0) {
@@ -376,13 +378,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_sweep_tma_q(SweepArgs a, int
 			s_win[tid] = ok ? a.descWin[b] : 0;
 			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
 		}
-		const int s = it & 1;
-		sd_mbar_wait(&full[s], (it >> 1) & 1);
+		sd_mbar_wait(&full[s], ph);
 		for (int r = 0; r < rps; r++) {
 			const int j = (r0 + r) % SW_BATCH;
 			const int win = s_win[j];
 			if (win == 0) continue;
-			const double2 *rowp = reinterpret_cast<const double2 *>(ring + (size_t) s * rps * rowDoubles + (size_t) r * rowDoubles) + tid;
+			const double2 *rowp = reinterpret_cast<const double2 *>(ring + (size_t) s * stageDoubles + (size_t) r * rowDoubles) + tid;
 			const double2 d = rowp[0];
 			const double2 ac = s_ac[j];
 			const int b = b0 + r0 + r;
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_sweep_tma_q(SweepArgs a, int
 		}
 		__syncwarp();
 		if ((tid & 31) == 0) sd_mbar_arrive(&empty[s]);
+		if (++s == stages) { s = 0; ph ^= 1; }
 	}
 	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
 	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
@@ -1245,13 +1247,33 @@ static int sd_launch_tma(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 	}
 }
 
+// ring of k_sweep_tma_q: <rows per stage, stages> with the most bytes in flight per SM (three CTAs at most: 72 registers x 288
+// threads), a lone CTA per SM discounted like in sd_tma_gen_shape.  SDGPU_Q_RPS / SDGPU_Q_STAGES override (experiment knobs).
+static size_t sd_tma_q_smem(int planes, int rps, int stages) {
+	return (size_t) stages * rps * planes * TMA_ROW_BYTES + 8 * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int)) + 64 * sizeof(double);
+}
+
 static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 	const int planes = 1 + c->Q;
-	int rps = 8;
-	while (rps > 1 && rps * planes > 8) rps >>= 1;                    // stage near 32 KiB
-	const size_t smem = (size_t) 2 * rps * planes * TMA_ROW_BYTES + 4 * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int)) + 64 * sizeof(double);
+	static int envRps = -1, envStages = -1;
+	if (envRps < 0) { const char *e = getenv("SDGPU_Q_RPS"); envRps = e ? atoi(e) : 0; e = getenv("SDGPU_Q_STAGES"); envStages = e ? atoi(e) : 0; }
+	const size_t smemPerSM = (size_t) 227 << 10;
+	int rps = 1, stages = 2;
+	double best = 0.0;
+	for (int st = 2; st <= 4; st++)
+		for (int r = 8; r >= 1; r >>= 1) {
+			const size_t sm = sd_tma_q_smem(planes, r, st) + 1024;
+			if (sm > smemPerSM) continue;
+			const int ctas = (int) std::min<size_t>(3, smemPerSM / sm);
+			const double score = (double) ctas * st * r * planes * TMA_ROW_BYTES * (ctas == 1 ? 0.7 : 1.0) + ctas - 0.1 * st;
+			if (score > best) { best = score; rps = r; stages = st; }
+		}
+	if (envRps > 0 && (envRps == 1 || envRps == 2 || envRps == 4 || envRps == 8)) rps = envRps;
+	if (envStages >= 2 && envStages <= 4) stages = envStages;
+	const size_t smem = sd_tma_q_smem(planes, rps, stages);
+	if (smem + 1024 > smemPerSM) return sdgpu_fail("sd_cut: ring of %zu bytes does not fit shared memory", smem);
 	if (smem > c->tmaQAttr) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaQAttr = smem; }
-	k_sweep_tma_q<<<grid, TMA_THREADS, smem, c->stream>>>(a, rps);
+	k_sweep_tma_q<<<grid, TMA_THREADS, smem, c->stream>>>(a, rps, stages);
 	return 0;
 }
 

@@ -105,6 +105,11 @@ def test_mid_size_no_pi_eval_nonzero_lb():
     _check(D=4096, N=20000, rv=32, n1=20, nsample=32, pi_eval=0, lb=-1.5)
 
 
+def test_many_observations_few_duals():
+    """N large enough that a merge CTA owns a whole 512-observation tile (one chunk lane) and the sweep grid has ~800 tiles."""
+    _check(D=512, N=400000, rv=16, n1=12, nsample=32)
+
+
 def test_baseline_full_size_64GiB():
     import torch
     free, _total = torch.cuda.mem_get_info()
