@@ -1265,7 +1265,7 @@ static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 			const size_t sm = sd_tma_q_smem(planes, r, st) + 1024;
 			if (sm > smemPerSM) continue;
 			const int ctas = (int) std::min<size_t>(3, smemPerSM / sm);
-			const double score = (double) ctas * st * r * planes * TMA_ROW_BYTES * (ctas == 1 ? 0.7 : 1.0) + ctas - 0.1 * st;
+			const double score = (double) ctas * st * r * planes * TMA_ROW_BYTES * (ctas == 1 ? 0.55 : 1.0) + ctas - 0.1 * st;
 			if (score > best) { best = score; rps = r; stages = st; }
 		}
 	if (envRps > 0 && (envRps == 1 || envRps == 2 || envRps == 4 || envRps == 8)) rps = envRps;
@@ -1286,7 +1286,7 @@ static size_t sd_tma_gen_smem(const sdgpu_ctx *c, int rps, int stages) {
 
 // ring shape <terms per stage, stages>: the one that keeps the most bytes in flight per SM, a lone CTA per SM discounted (8 consumer
 // warps alone do not hide the FP64 compare chains).  Measured on B200 (profiles/r01_variant_gen.jsonl): Q = 0 with 4 cost columns
-// <8,2> x 2 CTAs 6.25 TB/s, <4,2> x 3 6.09, <8,3> x 1 4.25; Q = 2 with 8 cost columns <4,3> x 1 6.45, <1,2> x 3 6.15.
+// <8,2> x 2 CTAs 6.25 TB/s, <4,2> x 3 6.09, <8,3> x 1 4.25; Q = 2 with 8 cost columns <2,2> x 2 6.89, <4,3> x 1 6.45, <1,2> x 3 6.15.
 // SDGPU_GEN_RPS / SDGPU_GEN_STAGES override (experiment knobs).  false = even the smallest ring does not fit.
 static bool sd_tma_gen_shape(const sdgpu_ctx *c, int *rps, int *stages) {
 	static int envRps = -1, envStages = -1;
@@ -1302,7 +1302,7 @@ static bool sd_tma_gen_shape(const sdgpu_ctx *c, int *rps, int *stages) {
 			const size_t smem = sd_tma_gen_smem(c, r, st) + 1024;              // + the per-CTA reservation
 			if (smem > smemPerSM) continue;
 			const int ctas = (int) std::min<size_t>(3, smemPerSM / smem);       // 70 registers x 288 threads: three CTAs at most
-			const double score = (double) ctas * st * r * slot * (ctas == 1 ? 0.7 : 1.0) + ctas;
+			const double score = (double) ctas * st * r * slot * (ctas == 1 ? 0.55 : 1.0) + ctas;
 			if (score > best) { best = score; *rps = r; *stages = st; }
 		}
 	return best > 0.0;
@@ -1325,7 +1325,10 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		// random-cost problems (mask and/or multi-term bases): the term-linear TMA ring from ~4M (term, observation) pairs up
 		int genRps = 0, genStages = 0;
 		const bool genFits = c->rvd > 0 && sd_tma_gen_shape(c, &genRps, &genStages);
-		const bool useGenTma = genFits && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->termCnt * N * (1 + c->Q) >= ((int64_t) 4 << 20)));
+		// (measured, profiles/r01_variant_bench.jsonl: multi-term bases 60 us against 139 us for the gather kernel already at 6 000 x 5 000;
+		// single-term bases with a mask: the LDG kernel wins at 5 000 x 5 000 (49 against 57 us), the ring from ~50M pairs up (170 against 283 us at 6 144 x 16 384))
+		const int64_t genFrom = multiTerm ? ((int64_t) 4 << 20) : ((int64_t) 48 << 20);
+		const bool useGenTma = genFits && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->termCnt * N * (1 + c->Q) >= genFrom));
 		if (sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, multiTerm && !useGenTma, useGenTma)) return SDGPU_ERR;
 		int chunkSize = 1, nChunks = 1;
 		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);

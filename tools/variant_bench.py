@@ -58,7 +58,9 @@ if __name__ == "__main__":
     for cfg in (dict(D=16384, N=131072, Q=0), dict(D=8192, N=131072, Q=2), dict(D=4096, N=131072, Q=8), dict(D=5000, N=5000, Q=8),
                 dict(D=6000, N=5000, Q=0, rvd=4, phi=2), dict(D=6000, N=5000, Q=2, rvd=4, phi=2), dict(D=5000, N=5000, Q=0, rvd=4, phi=0),
                 dict(D=6000, N=5000, Q=0, rvd=4, phi=2, variant=1), dict(D=5000, N=5000, Q=0, rvd=4, phi=0, variant=1),
-                dict(D=6144, N=65536, Q=0, rvd=4, phi=2), dict(D=6144, N=65536, Q=0, rvd=4, phi=2, variant=1), dict(D=6144, N=65536, Q=2, rvd=8, phi=1)):
+                dict(D=6144, N=65536, Q=0, rvd=4, phi=2), dict(D=6144, N=65536, Q=0, rvd=4, phi=2, variant=1), dict(D=6144, N=65536, Q=2, rvd=8, phi=1),
+                dict(D=6144, N=65536, Q=0, rvd=4, phi=0), dict(D=6144, N=65536, Q=0, rvd=4, phi=0, variant=1),
+                dict(D=6144, N=16384, Q=0, rvd=4, phi=0), dict(D=6144, N=16384, Q=0, rvd=4, phi=0, variant=1)):
         if len(sys.argv) > 1 and sys.argv[1] == "rc" and not cfg.get("rvd"):
             continue
         print(json.dumps(run(**cfg)), flush=True)
