@@ -127,14 +127,14 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(duals, obs):
-    """dram bytes per sweep launch from the committed ncu capture, if one exists for this shape."""
+def ncu_traffic(duals, obs, kernel=None):
+    """dram bytes per sweep launch from the committed ncu capture, if one exists for this shape (and kernel)."""
     path = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     try:
         with open(path) as fh:
             rec = json.load(fh)
         for r in rec.get("captures", []):
-            if r.get("duals") == duals and r.get("obs") == obs:
+            if r.get("duals") == duals and r.get("obs") == obs and (kernel is None or r.get("kernel", "").startswith(kernel)):
                 return r.get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -332,6 +332,7 @@ def gpu_arm(args):
     sweep_avg_ms = float(np.mean(sweep_ms))
     peak, peak_src = measured_peak()
     achieved = sweep_bytes / (sweep_avg_ms * 1e-3) / 1e9
+    sweep_kernel = {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general", 4: "k_sweep_tma_gen"}.get(st["last_sweep_variant"], "?")
 
     # ---- e2e: whole SD iterations through the C ABI with host buffers, wall clock --------------------------------
     def one_iteration(i):
@@ -374,8 +375,8 @@ def gpu_arm(args):
                        "sharding": ("observations split across ranks, lambda/sigma/basis replicated, one all-reduce of n1+4 doubles per cut ("
                                     + ("NVLink peer-memory exchange fused into the cut kernel" if args.collective == "peer" else "NCCL") + ")") if world > 1 else "single GPU",
                        "setup_s": round(setup_s, 2)},
-            "roofline": {"bound": "hbm", "kernel": {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general", 4: "k_sweep_tma_gen"}.get(st["last_sweep_variant"], "?"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": ncu_traffic(nb, N), "bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_avg_ms,
+            "roofline": {"bound": "hbm", "kernel": sweep_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": ncu_traffic(nb, N, sweep_kernel), "nominal_peak": 8000.0, "frac_of_nominal": achieved / 8000.0, "bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_avg_ms,
                          "sweep_share_of_step": sweep_avg_ms / ms_step},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks,

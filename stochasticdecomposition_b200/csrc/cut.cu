@@ -1360,9 +1360,12 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
 			a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
 			const bool hasMask = c->rvd > 0;
-			// variant 0 = automatic: the TMA ring wins from ~4M pairs up, the LDG kernel below that (tools/tma_check.py)
+			// variant 0 = automatic (tools/tma_check.py, profiles/r01_tma_check.jsonl): RHS-only, the LDG kernel wins up to ~100M pairs
+			// (5 000 x 5 000: 34 against 39 us), the two are level at 16 384 x 16 384 and the TMA ring wins beyond (7.31 against 7.02 TB/s
+			// at 65 536 x 131 072); with random T elements the ring wins from ~4M elements up
 			const bool tmaOk = !hasMask && (1 + c->Q) * TMA_ROW_BYTES <= 48 * 1024;      // one dual row (all planes) must fit a ring stage
-			const bool useTma = tmaOk && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N * (1 + c->Q) >= ((int64_t) 4 << 20)));
+			const int64_t tmaFrom = c->Q == 0 ? ((int64_t) 128 << 20) : ((int64_t) 4 << 20);
+			const bool useTma = tmaOk && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N * (1 + c->Q) >= tmaFrom));
 			c->stats.last_sweep_variant = useTma ? 2 : 1;
 			if (useTma) {
 				if (c->Q == 0 ? sd_launch_tma(c, grid, a) : sd_launch_tma_q(c, grid, a)) return SDGPU_ERR;
