@@ -74,7 +74,7 @@ struct sdgpu_ctx {
 	int32_t *d_cList = nullptr;
 	int32_t *d_rvCOmCols = nullptr;  // [Q]    1-based position in X / beta
 	int32_t *d_rvCols = nullptr;     // [Q]    1-based position in beta (plain branch, cuts.c:167)
-	int32_t *d_bBarCol = nullptr; double *d_bBarVal = nullptr; int bBarCnt = 0;
+	int32_t *d_bBarCol = nullptr; double *d_bBarVal = nullptr; int bBarCnt = 0, cbNnz = 0;
 	int32_t *d_cbStart = nullptr;    // [n1c+1] per CCols[k]: Cbar entries with that column, in nnz order
 	int32_t *d_cbRow = nullptr; double *d_cbVal = nullptr;
 
@@ -125,6 +125,7 @@ struct sdgpu_ctx {
 	double  *d_termA = nullptr, *d_termC = nullptr;     // sigma.pib, piCbarX of the term's sigma
 	int32_t *d_termRow = nullptr, *d_termMeta = nullptr, *d_termBasis = nullptr;   // lambda row; window | last-term << 2 | omegaIdx << 8; basis
 	size_t   tmaGenAttr = 0;
+	size_t   lambdaSmemAttr = 0;
 	double  *d_partV = nullptr;      // [2][chunks][NP] per-chunk running maxima (old, new)
 	int32_t *d_partI = nullptr;      // [2][chunks][NP]
 	int32_t *d_iStar = nullptr;      // [NP]

@@ -26,6 +26,16 @@ int sdgpu_fail(const char *fmt, ...) {
 extern "C" const char *sdgpu_last_error(void) { return g_sdgpu_err.c_str(); }
 extern "C" int sdgpu_abi_version(void) { return SDGPU_ABI_VERSION; }
 
+// 8-byte asynchronous copies global -> shared (LDGSTS): a thread queues a whole batch of operands without holding a register
+// per load, waits once, and reads them back from shared memory.  (With plain loads ptxas interleaves the loads with the
+// dependent add chain, three or four deep, whatever the source says: one memory round trip per few terms.)
+__device__ __forceinline__ void sd_cp_async8(double *smemDst, const double *gmemSrc) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t) __cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void sd_cp_async_wait_all() {
+	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // DBL_ABS of the reference: (x) > 0 ? (x) : -(x); a NaN difference therefore never counts as a mismatch
 __device__ __forceinline__ double sd_abs(double x) { return x > 0.0 ? x : -x; }
 
@@ -46,10 +56,15 @@ __device__ __forceinline__ void sd_publish(const SdDevState *st, SdDevState *hos
 __global__ void k_lambda_fused(const double *__restrict__ pi, int rows, const int32_t *__restrict__ rvRows, int R,
 		double *__restrict__ lambda, int64_t LP, int64_t cap, double tol,
 		const int32_t *__restrict__ bCol, const double *__restrict__ bVal, int bCnt, double mubBar,
-		const int32_t *__restrict__ cbStart, const int32_t *__restrict__ cbRow, const double *__restrict__ cbVal, int n1c,
-		double *__restrict__ vecDev, double *__restrict__ candC, SdDevState *st, SdDevState *hst) {
-	extern __shared__ double s_cand[];
-	for (int i = threadIdx.x; i < R; i += blockDim.x) s_cand[i] = pi[rvRows[i]];            // reduceVector :269
+		const int32_t *__restrict__ cbStart, const int32_t *__restrict__ cbRow, const double *__restrict__ cbVal, int n1c, int cbStage,
+		double *__restrict__ vecDev, double *__restrict__ candC, SdDevState *st, SdDevState *hst, int publish) {
+	extern __shared__ double s_cand[];              // [R] reduced candidate, [rows + 1] the whole vector, [bCnt] and [cbStage] products
+	double *s_pi = s_cand + R;
+	double *s_prod = s_pi + rows + 1;
+	double *s_cprod = s_prod + bCnt;
+	for (int i = threadIdx.x; i <= rows; i += blockDim.x) s_pi[i] = pi[i];                  // one trip to the (possibly host-mapped) vector
+	__syncthreads();
+	for (int i = threadIdx.x; i < R; i += blockDim.x) s_cand[i] = s_pi[rvRows[i]];          // reduceVector :269
 	__syncthreads();
 	const int cnt = st->lambdaCnt;
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,20 +84,28 @@ __global__ void k_lambda_fused(const double *__restrict__ pi, int rows, const in
 			idx = cnt; isNew = 1;
 		}
 	}
-	for (int i = threadIdx.x; i <= rows; i += blockDim.x) vecDev[i] = pi[i];                // keep pi on the device for calcSigma
+	// calcSigma's candidate from the same vector.  The products bBar.val[e] * pi[bBar.col[e]] and pi[Cbar.row[e]] * Cbar.val[e] are
+	// formed in parallel (each is rounded on its own in the reference too) and then added up left to right per sum, so the sums
+	// have the reference's bits without one dependent memory round trip per term.
+	for (int i = threadIdx.x; i <= rows; i += blockDim.x) vecDev[i] = s_pi[i];              // keep pi on the device for calcSigma
+	for (int e = threadIdx.x; e < bCnt; e += blockDim.x) s_prod[e] = __dmul_rn(bVal[e], s_pi[bCol[e]]);
+	const int nnz = cbStart[n1c];
+	const bool staged = nnz <= cbStage;
+	if (staged) for (int e = threadIdx.x; e < nnz; e += blockDim.x) s_cprod[e] = __dmul_rn(s_pi[cbRow[e]], cbVal[e]);
 	__syncthreads();
 	for (int k = threadIdx.x; k < n1c; k += blockDim.x) {                                    // vxMSparse + reduceVector :295-296
 		double t = 0.0;
-		for (int e = cbStart[k]; e < cbStart[k + 1]; e++) t += vecDev[cbRow[e]] * cbVal[e];
+		if (staged) for (int e = cbStart[k]; e < cbStart[k + 1]; e++) t = __dadd_rn(t, s_cprod[e]);
+		else for (int e = cbStart[k]; e < cbStart[k + 1]; e++) t = __dadd_rn(t, __dmul_rn(s_pi[cbRow[e]], cbVal[e]));
 		candC[k] = t;
 	}
 	if (threadIdx.x == 0) {
 		double sum = 0.0;                                                                    // vXvSparse :293
-		for (int e = 0; e < bCnt; e++) sum += bVal[e] * vecDev[bCol[e]];
-		st->pibBar = sum + mubBar;
+		for (int e = 0; e < bCnt; e++) sum = __dadd_rn(sum, s_prod[e]);
+		st->pibBar = __dadd_rn(sum, mubBar);
 		st->lambdaIdx = idx; st->newLambda = isNew; st->foundLambda = INT_MAX;
 		if (isNew) st->lambdaCnt = cnt + 1;
-		sd_publish(st, hst);
+		if (publish) sd_publish(st, hst);       // chained with calcSigma (sdgpu_update_dual): the sigma kernel publishes the whole state
 	}
 }
 
@@ -194,24 +217,10 @@ __global__ void k_sigma_prepare(const double *__restrict__ pi, const int32_t *__
 //   piC[c] = sum over the e with rvCOmCols[e] == rvCOmCols[c], in e order, of lambdaFull[rvCOmRows[e]] * omega_o[Rb+e]
 // lambdaFull is the lambda expanded to all rows, zero where the row carries no lambda entry (expandVector).
 // LamAt(p) / OmAt(j) fetch lambda position p and observation entry j (0-based) for the cell at hand.
+// The random-T planes of one cell (Q is small): piC[c] as above.
 template <class LamAt, class OmAt>
-__device__ __forceinline__ void sd_delta_cell(int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos,
-		const int32_t *__restrict__ cListStart, const int32_t *__restrict__ cList, LamAt lamAt, OmAt omAt,
-		double *__restrict__ out, size_t planeStride) {
-	double s = 0.0;
-	int j = 0;
-	for (; j + 8 <= Rb; j += 8) {            // operands of eight terms fetched together, the sum still strictly in index order
-		double ov[8], lv[8];
-#pragma unroll
-		for (int u = 0; u < 8; u++) { const int p = bLamPos[j + u]; ov[u] = omAt(j + u); lv[u] = p >= 0 ? lamAt(p) : 0.0; }
-#pragma unroll
-		for (int u = 0; u < 8; u++) s = __dadd_rn(s, __dmul_rn(ov[u], lv[u]));
-	}
-	for (; j < Rb; j++) {
-		const int p = bLamPos[j];
-		s = __dadd_rn(s, __dmul_rn(omAt(j), p >= 0 ? lamAt(p) : 0.0));
-	}
-	out[0] = s;
+__device__ __forceinline__ void sd_delta_cell_T(int Rb, int Q, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
+		const int32_t *__restrict__ cList, LamAt lamAt, OmAt omAt, double *__restrict__ out, size_t planeStride) {
 	for (int c = 0; c < Q; c++) {
 		double t = 0.0;
 		for (int n = cListStart[c]; n < cListStart[c + 1]; n++) {
@@ -222,38 +231,61 @@ __device__ __forceinline__ void sd_delta_cell(int Rb, int Q, const int32_t *__re
 	}
 }
 
+#define DC_THREADS 128     // threads per CTA of the row / column kernels
+#define DC_BATCH   32      // operands a thread keeps in flight (DC_BATCH x DC_THREADS x 8 bytes of shared memory)
+
 // calcDelta case II stocUpdate.c:230-254: a new dual -> one delta row, one thread per observation (coalesced
 // reads of omega, contiguous W-segment writes).  The lambda row sits in shared memory.
-__global__ void k_delta_row(const double *__restrict__ lambda, int64_t LP, int R, const double *__restrict__ omega, int64_t NP,
+__global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restrict__ lambda, int64_t LP, int R, const double *__restrict__ omega, int64_t NP,
 		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
 		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedRow) {
-	extern __shared__ double s_lam[];
+	__shared__ double s_buf[DC_BATCH][DC_THREADS];
+	extern __shared__ double s_lam[];            // [Rb] the lambda entry each random RHS row meets (0.0 where it meets none), then [R] the row itself
+	double *s_row = s_lam + Rb;
 	int l = forcedRow >= 0 ? forcedRow : (st->newLambda ? st->lambdaIdx : -1);
 	if (l < 0) return;
-	for (int i = threadIdx.x; i < R; i += blockDim.x) s_lam[i] = lambda[(size_t) i * LP + l];
+	for (int j = threadIdx.x; j < Rb; j += blockDim.x) { const int p = bLamPos[j]; s_lam[j] = p >= 0 ? lambda[(size_t) p * LP + l] : 0.0; }
+	for (int i = threadIdx.x; i < R; i += blockDim.x) s_row[i] = lambda[(size_t) i * LP + l];
 	__syncthreads();
 	int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (o >= st->omegaCnt) return;
-	sd_delta_cell(Rb, Q, bLamPos, cLamPos, cListStart, cList,
-			[&](int p) { return s_lam[p]; }, [&](int j) { return omega[(size_t) j * NP + o]; },
-			delta + sd_delta_off(Dcap, Q, l, 0, o), SD_TILE_W);
+	double s = 0.0;                                                                        // vXvSparse :244, index order
+	for (int j = 0; j < Rb; j += DC_BATCH) {
+		const int n = min(DC_BATCH, Rb - j);
+		for (int u = 0; u < n; u++) sd_cp_async8(&s_buf[u][threadIdx.x], omega + (size_t) (j + u) * NP + o);
+		sd_cp_async_wait_all();
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_buf[u][threadIdx.x], s_lam[j + u]));
+	}
+	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
+	out[0] = s;
+	sd_delta_cell_T(Rb, Q, cLamPos, cListStart, cList, [&](int p) { return s_row[p]; }, [&](int j) { return omega[(size_t) j * NP + o]; }, out, SD_TILE_W);
 }
 
 // calcDelta case I stocUpdate.c:206-229: a new observation -> one delta column, one thread per dual (coalesced
 // reads of lambda, strided 8-byte writes).  The observation sits in shared memory.
-__global__ void k_delta_col(const double *__restrict__ lambda, int64_t LP, const double *__restrict__ omega, int64_t NP, int numRV,
+__global__ void __launch_bounds__(DC_THREADS) k_delta_col(const double *__restrict__ lambda, int64_t LP, const double *__restrict__ omega, int64_t NP, int numRV,
 		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
 		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedCol) {
-	extern __shared__ double s_om[];
+	__shared__ double s_buf[DC_BATCH][DC_THREADS];
+	extern __shared__ double s_om[];             // [numRV] the observation, then [Rb] ints: position of each random RHS row inside a lambda
+	int32_t *s_pos = reinterpret_cast<int32_t *>(s_om + numRV);
 	int o = forcedCol >= 0 ? forcedCol : (st->newOmega ? st->omegaIdx : -1);
 	if (o < 0) return;
 	for (int j = threadIdx.x; j < numRV; j += blockDim.x) s_om[j] = omega[(size_t) j * NP + o];
+	for (int j = threadIdx.x; j < Rb; j += blockDim.x) s_pos[j] = bLamPos[j];
 	__syncthreads();
 	int64_t l = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (l >= st->lambdaCnt) return;
-	sd_delta_cell(Rb, Q, bLamPos, cLamPos, cListStart, cList,
-			[&](int p) { return lambda[(size_t) p * LP + l]; }, [&](int j) { return s_om[j]; },
-			delta + sd_delta_off(Dcap, Q, l, 0, o), SD_TILE_W);
+	double s = 0.0;                                                                        // vXvSparse :218, index order
+	for (int j = 0; j < Rb; j += DC_BATCH) {
+		const int n = min(DC_BATCH, Rb - j);
+		for (int u = 0; u < n; u++) { const int p = s_pos[j + u]; if (p >= 0) sd_cp_async8(&s_buf[u][threadIdx.x], lambda + (size_t) p * LP + l); }
+		sd_cp_async_wait_all();
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_om[j + u], s_pos[j + u] >= 0 ? s_buf[u][threadIdx.x] : 0.0));
+	}
+	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
+	out[0] = s;
+	sd_delta_cell_T(Rb, Q, cLamPos, cListStart, cList, [&](int p) { return lambda[(size_t) p * LP + l]; }, [&](int j) { return s_om[j]; }, out, SD_TILE_W);
 }
 
 // calcDelta for a whole block of (dual, observation) pairs -- the bulk loader of synthetic sweeps.  A CTA owns
@@ -558,7 +590,7 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 			if (p->Cbar.col[e] == CCols[k]) { cbRow.push_back(p->Cbar.row[e]); cbVal.push_back(p->Cbar.val[e]); }
 		cbStart[k + 1] = (int32_t) cbRow.size();
 	}
-	c->bBarCnt = p->bBar.cnt;
+	c->bBarCnt = p->bBar.cnt; c->cbNnz = (int) cbRow.size();
 	SD_TRY(sd_upload(&c->d_CCols, CCols)); SD_TRY(sd_upload(&c->d_rvRows, rvRows)); SD_TRY(sd_upload(&c->d_bLamPos, bLamPos));
 	SD_TRY(sd_upload(&c->d_cLamPos, cLamPos)); SD_TRY(sd_upload(&c->d_cListStart, cListStart)); SD_TRY(sd_upload(&c->d_cList, cList));
 	SD_TRY(sd_upload(&c->d_rvCOmCols, rvCOmCols)); SD_TRY(sd_upload(&c->d_rvCols, rvCols));
@@ -763,10 +795,16 @@ extern "C" int sdgpu_omega_append_bulk(sdgpu_ctx *c, int64_t n, const double *va
 
 // ---- lambda / sigma / delta --------------------------------------------------------------------------------
 // calcLambda in one launch; its last block also stages calcSigma's candidate (pibBar, piCBar) from the same vector
-static void sd_launch_lambda(sdgpu_ctx *c, const double *d_pi, double mubBar, double tol, int64_t lambdaUpper) {
-	k_lambda_fused<<<sd_blocks(lambdaUpper, 256), 256, (size_t) std::max(1, c->R) * 8, c->stream>>>(d_pi, c->rows, c->d_rvRows, c->R, c->d_lambda, c->LP,
-			c->caps.maxLambda, tol, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->n1c,
-			c->d_vecIn, c->d_candC, c->d_state, c->d_hstate);
+static void sd_launch_lambda(sdgpu_ctx *c, const double *d_pi, double mubBar, double tol, int64_t lambdaUpper, bool publish) {
+	const int cbStage = std::min(c->cbNnz, 2048);
+	const size_t smem = ((size_t) std::max(1, c->R) + c->rows + 1 + std::max(1, c->bBarCnt) + std::max(1, cbStage)) * 8;
+	if (smem > 48 * 1024 && smem > c->lambdaSmemAttr) {      // very long dual vectors: opt in to more dynamic shared memory (per device, remembered per context)
+		cudaFuncSetAttribute(k_lambda_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		c->lambdaSmemAttr = smem;
+	}
+	k_lambda_fused<<<sd_blocks(lambdaUpper, 256), 256, smem, c->stream>>>(d_pi, c->rows, c->d_rvRows, c->R, c->d_lambda, c->LP,
+			c->caps.maxLambda, tol, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->n1c, cbStage,
+			c->d_vecIn, c->d_candC, c->d_state, c->d_hstate, publish ? 1 : 0);
 	sd_count_launch(c);
 }
 
@@ -778,14 +816,14 @@ static void sd_launch_sigma(sdgpu_ctx *c, int iter, double tol, int64_t sigmaUpp
 
 static void sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
 	if (omegaUpper <= 0) return;
-	k_delta_row<<<sd_blocks(omegaUpper, 128), 128, (size_t) std::max(1, c->R) * 8, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
+	k_delta_row<<<sd_blocks(omegaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->R + c->Rb) * 8, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
 			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow);
 	sd_count_launch(c);
 }
 
 static void sd_launch_delta_col(sdgpu_ctx *c, int forcedCol, int64_t lambdaUpper) {
 	if (lambdaUpper <= 0) return;
-	k_delta_col<<<sd_blocks(lambdaUpper, 128), 128, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
+	k_delta_col<<<sd_blocks(lambdaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
 			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol);
 	sd_count_launch(c);
 }
@@ -794,7 +832,7 @@ extern "C" int sdgpu_calc_lambda(sdgpu_ctx *c, const double *Pi, double tol, int
 	if (!c || !Pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, Pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), 0.0, tol, c->lambdaCnt);
+	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), 0.0, tol, c->lambdaCnt, true);
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
 	return c->h_state->lambdaIdx;
@@ -837,7 +875,7 @@ extern "C" int sdgpu_update_dual(sdgpu_ctx *c, const double *pi, double mubBar, 
 	if (!c || !pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), mubBar, tol, c->lambdaCnt);   // stocUpdate.c:78 (+ staging of :293-296)
+	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), mubBar, tol, c->lambdaCnt, false);   // stocUpdate.c:78 (+ staging of :293-296)
 	sd_launch_sigma(c, currentIter, tol, c->sigmaCnt);                     // :81
 	sd_launch_delta_row(c, -1, c->omegaCnt);                               // :84-85 (kernel no-op unless the lambda was new)
 	if (sd_sync_state(c)) return SDGPU_ERR;
@@ -889,7 +927,7 @@ extern "C" int sdgpu_update_dual_bulk(sdgpu_ctx *c, int64_t n, const double *pis
 				const double *d_pi = d_pis + (size_t) i * stride;
 				double mb = mubBar ? mubBar[i0 + i] : 0.0;
 				int it = iters ? iters[i0 + i] : (int) (i0 + i + 1);
-				sd_launch_lambda(c, d_pi, mb, tol, c->lambdaCnt + i);
+				sd_launch_lambda(c, d_pi, mb, tol, c->lambdaCnt + i, false);
 				sd_launch_sigma(c, it, tol, c->sigmaCnt + i);
 				sd_launch_delta_row(c, -1, c->omegaCnt);
 				k_record_pair<<<1, 1, 0, c->stream>>>(c->d_state, d_li, d_si, i);
