@@ -1590,14 +1590,14 @@ extern "C" int sdgpu_reform_cuts_batch(sdgpu_ctx *c, int nCuts, const int32_t *i
 	for (int i = 0; i < nCuts; i++)
 		if (oc[i] < 0 || oc[i] > c->omegaCnt || (iStar && oc[i] > istarStride)) return sdgpu_fail("reform_cuts_batch: omegaCnt[%d] = %d out of range", i, oc[i]);
 	const int nOut = c->n1 + 2;
-	int32_t *d_is = nullptr, *d_ob = nullptr, *d_oc = nullptr; double *d_out = nullptr;
-	auto freeAll = [&]() { if (d_is) cudaFree(d_is); if (d_ob) cudaFree(d_ob); if (d_oc) cudaFree(d_oc); if (d_out) cudaFree(d_out); };
-	if (cudaMalloc((void **) &d_ob, (size_t) nReps * k * 4) != cudaSuccess || cudaMalloc((void **) &d_oc, (size_t) nCuts * 4) != cudaSuccess ||
-	    cudaMalloc((void **) &d_out, (size_t) nReps * nCuts * nOut * 8) != cudaSuccess ||
-	    (iStar && cudaMalloc((void **) &d_is, (size_t) nCuts * std::max(1, istarStride) * 4) != cudaSuccess)) {
-		freeAll();
-		return sdgpu_fail("reform_cuts_batch: allocation failed");
-	}
+	// one block of growable device scratch: [out doubles][observ ints][omegaCnt ints][iStar ints] -- no allocation per call
+	const size_t outBytes = (size_t) nReps * nCuts * nOut * 8, obBytes = (size_t) nReps * k * 4, ocBytes = (((size_t) nCuts * 4) + 7) / 8 * 8;
+	const size_t isBytes = iStar ? (size_t) nCuts * std::max(1, istarStride) * 4 : 0;
+	if (sd_scratch_reserve(c, outBytes + (obBytes + 7) / 8 * 8 + ocBytes + isBytes)) return SDGPU_ERR;
+	double *d_out = reinterpret_cast<double *>(c->d_scratch);
+	int32_t *d_ob = reinterpret_cast<int32_t *>(c->d_scratch + outBytes);
+	int32_t *d_oc = reinterpret_cast<int32_t *>(c->d_scratch + outBytes + (obBytes + 7) / 8 * 8);
+	int32_t *d_is = iStar ? reinterpret_cast<int32_t *>(c->d_scratch + outBytes + (obBytes + 7) / 8 * 8 + ocBytes) : nullptr;
 	cudaMemcpyAsync(d_ob, observ, (size_t) nReps * k * 4, cudaMemcpyHostToDevice, c->stream);
 	cudaMemcpyAsync(d_oc, oc.data(), (size_t) nCuts * 4, cudaMemcpyHostToDevice, c->stream);
 	if (iStar) cudaMemcpyAsync(d_is, iStar, (size_t) nCuts * istarStride * 4, cudaMemcpyHostToDevice, c->stream);
@@ -1611,13 +1611,12 @@ extern "C" int sdgpu_reform_cuts_batch(sdgpu_ctx *c, int nCuts, const int32_t *i
 	a.out = d_out;
 	const int nc = c->n1c + c->Q, kp = ((std::max(nc, 1) + 31) / 32) * 32, groups = std::max(1, 512 / kp);
 	const size_t dyn = ((size_t) groups * std::max(nc, 1) + 2 + nc + c->n1 + 1) * 8;
-	if (nc > 512) { freeAll(); return sdgpu_fail("reform_cuts_batch: more than 512 cut columns is not supported"); }
+	if (nc > 512) { return sdgpu_fail("reform_cuts_batch: more than 512 cut columns is not supported"); }
 	k_reform<<<dim3((unsigned) nCuts, (unsigned) nReps), 512, dyn, c->stream>>>(a);
 	sd_count_launch(c);
 	std::vector<double> h((size_t) nReps * nCuts * nOut);
 	cudaMemcpyAsync(h.data(), d_out, h.size() * 8, cudaMemcpyDeviceToHost, c->stream);
 	cudaError_t e = cudaStreamSynchronize(c->stream);
-	freeAll();
 	if (e != cudaSuccess) return sdgpu_fail("reform_cuts_batch: %s", cudaGetErrorString(e));
 	for (size_t i = 0; i < (size_t) nReps * nCuts; i++) {
 		alpha[i] = h[i * nOut];
@@ -1645,12 +1644,11 @@ extern "C" int sdgpu_feas_cuts(sdgpu_ctx *c, int obsFirst, int obsLast, int basi
 	if (po.size() > (size_t) std::max(0, maxOut)) return sdgpu_fail("feas_cuts: %zu cuts do not fit maxOut = %d", po.size(), maxOut);
 	if (n == 0) return 0;
 	SD_CUDA(cudaSetDevice(c->device));
-	int32_t *d_p = nullptr; double *d_o = nullptr;
 	const size_t n1p = (size_t) c->n1 + 1;
-	if (cudaMalloc((void **) &d_p, (size_t) 2 * n * 4) != cudaSuccess || cudaMalloc((void **) &d_o, (size_t) n * (1 + n1p) * 8) != cudaSuccess) {
-		if (d_p) cudaFree(d_p);
-		return sdgpu_fail("feas_cuts: allocation failed");
-	}
+	const size_t outBytes = (size_t) n * (1 + n1p) * 8;
+	if (sd_scratch_reserve(c, outBytes + (size_t) 2 * n * 4)) return SDGPU_ERR;
+	double *d_o = reinterpret_cast<double *>(c->d_scratch);
+	int32_t *d_p = reinterpret_cast<int32_t *>(c->d_scratch + outBytes);
 	cudaMemcpyAsync(d_p, po.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
 	cudaMemcpyAsync(d_p + n, pb.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
 	k_feas_cuts<<<sd_blocks(n, 128), 128, 0, c->stream>>>(n, d_p, d_p + n, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaPiCr, c->d_sigmaLam,
@@ -1659,7 +1657,6 @@ extern "C" int sdgpu_feas_cuts(sdgpu_ctx *c, int obsFirst, int obsLast, int basi
 	cudaMemcpyAsync(alpha, d_o, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
 	cudaMemcpyAsync(beta, d_o + n, (size_t) n * n1p * 8, cudaMemcpyDeviceToHost, c->stream);
 	cudaError_t e = cudaStreamSynchronize(c->stream);
-	cudaFree(d_p); cudaFree(d_o);
 	if (e != cudaSuccess) return sdgpu_fail("feas_cuts: %s", cudaGetErrorString(e));
 	return n;
 }

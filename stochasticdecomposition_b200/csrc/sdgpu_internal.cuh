@@ -115,6 +115,8 @@ struct sdgpu_ctx {
 	size_t   pinDcap = 0, pinIcap = 0;
 	unsigned char *h_aux = nullptr, *d_aux = nullptr;   // growable pinned + mapped scratch for the small batched calls
 	size_t   auxCap = 0;
+	unsigned char *d_scratch = nullptr;                 // growable device scratch of the batched calls (reformCuts, feasibility cuts)
+	size_t   scratchCap = 0;
 
 	// cut formation scratch
 	double  *d_x = nullptr;          // [n1+1]
@@ -195,6 +197,7 @@ __device__ __forceinline__ bool sd_is_last_block(unsigned int *ticket) {
 #endif
 
 int sd_aux_reserve(sdgpu_ctx *c, size_t bytes);  // grows h_aux / d_aux (pinned, mapped); contents are not preserved
+int sd_scratch_reserve(sdgpu_ctx *c, size_t bytes);  // grows d_scratch (device); contents are not preserved
 int sd_sync_state(sdgpu_ctx *c);                 // D2H of SdDevState + stream sync + mirror update
 int sd_nccl_allreduce(sdgpu_ctx *c, double *buf, int n);
 void sd_nccl_release(sdgpu_ctx *c);

@@ -502,6 +502,17 @@ int sd_aux_reserve(sdgpu_ctx *c, size_t bytes) {
 	return 0;
 }
 
+int sd_scratch_reserve(sdgpu_ctx *c, size_t bytes) {
+	if (bytes <= c->scratchCap) return 0;
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	if (c->d_scratch) cudaFree(c->d_scratch);
+	c->d_scratch = nullptr; c->scratchCap = 0;
+	size_t cap = std::max<size_t>(bytes * 2, 1 << 20);
+	if (cudaMalloc((void **) &c->d_scratch, cap) != cudaSuccess) return sdgpu_fail("device scratch of %zu bytes failed", cap);
+	c->scratchCap = cap;
+	return 0;
+}
+
 int sd_sync_state(sdgpu_ctx *c) {
 	SD_CUDA(cudaStreamSynchronize(c->stream));          // the commit kernels already published the state into h_state
 	c->omegaCnt = c->h_state->omegaCnt; c->lambdaCnt = c->h_state->lambdaCnt;
@@ -674,6 +685,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	if (c->h_cutRes) cudaFreeHost(c->h_cutRes);
 	if (c->h_iStar) cudaFreeHost(c->h_iStar);
 	if (c->h_aux) cudaFreeHost(c->h_aux);
+	if (c->d_scratch) cudaFree(c->d_scratch);
 	if (c->evA) cudaEventDestroy(c->evA);
 	if (c->evB) cudaEventDestroy(c->evB);
 	if (c->evC) cudaEventDestroy(c->evC);
