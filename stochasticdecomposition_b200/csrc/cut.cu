@@ -6,11 +6,13 @@
 // Pipeline of one cut (three launches on the context's stream, one host wait at the end):
 //   k_cut_prep     x as a kernel parameter; per basis (sigma.pib, piCbarX = sigma.piC . x[CCols], lambda row, window)
 //                                                                             cuts.c:105-106, stocUpdate.c:151-167
-//   k_sweep_*      2-D grid (observation tile x basis chunk): stream the delta tile (TMA bulk ring or LDG), keep running
-//                  (max, first index) per observation for the old and the new window   stocUpdate.c:161-184
-//   k_cut_merge    merge chunk maxima in index order, pick iStar (cuts.c:124-125,136-140), accumulate
-//                  w*(sigma.pib + delta.pib), w*sigma.piC, w*delta.piC, cummOld, cummAll per tile   cuts.c:127-168;
-//                  the last tile to finish sums the tile partials in tile order, scatters into beta (cuts.c:155-167),
+//   k_sweep_*      2-D grid (observation tile x basis chunk): stream the delta tile, keep running (max, first index) per
+//                  observation for the old and the new window   stocUpdate.c:161-184.  Five kernels, picked by shape and size:
+//                  k_sweep_tma (RHS-only, TMA ring), k_sweep_tma_q (random T elements), k_sweep_tma_gen (random cost: multi-term
+//                  bases + obsFeasible mask, term-linear ring), k_sweep_ldg<Q, MASK> (small cuts), k_sweep_general (small random-cost cuts)
+//   k_cut_merge    one CTA per 64..512 observations: merge chunk maxima in index order, pick iStar (cuts.c:124-125,136-140),
+//                  accumulate w*(sigma.pib + delta.pib), w*sigma.piC, w*delta.piC, cummOld, cummAll   cuts.c:127-168;
+//                  the last CTA to finish sums the per-CTA partials in CTA order, scatters into beta (cuts.c:155-167),
 //                  applies alpha/k, beta/k (cuts.c:184-188) and writes the cut into mapped pinned host memory
 //   [sharded: un-normalised vector -> NCCL all-reduce of n1+4 doubles -> k_cut_normalise]
 //
