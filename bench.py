@@ -332,7 +332,7 @@ def gpu_arm(args):
     sweep_avg_ms = float(np.mean(sweep_ms))
     peak, peak_src = measured_peak()
     achieved = sweep_bytes / (sweep_avg_ms * 1e-3) / 1e9
-    sweep_kernel = {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general", 4: "k_sweep_tma_gen"}.get(st["last_sweep_variant"], "?")
+    sweep_kernel = {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general", 4: "k_sweep_tma_gen", 5: "k_sweep_recompute"}.get(st["last_sweep_variant"], "?")
 
     # ---- e2e: whole SD iterations through the C ABI with host buffers, wall clock --------------------------------
     def one_iteration(i):

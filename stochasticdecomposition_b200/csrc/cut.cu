@@ -207,6 +207,94 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a) {
 }
 
 // ======================================================================================================
+// K6 for problems with very few random right-hand sides (Rb <= 8, e.g. pgp2 with 3): the contraction
+// delta.pib[l][o] = sum_j omega_o[j] * lambda_l[rvbOmRows[j]] costs 2 Rb flops, fewer cycles than the 8 bytes of the stored entry cost
+// in HBM time, so the sweep recomputes it from the factors instead of streaming the delta table -- the score[lambda, omega]
+// contraction fused with the per-observation argmax.  The observation's Rb values live in registers, the lambda entries of 256 bases
+// at a time in shared memory (broadcast reads); the sum runs in index order from 0.0 with separate multiply and add, exactly the
+// operations calcDelta performed (stocUpdate.c:218, :244), so the recomputed entry has the stored entry's bits and iStar is unchanged.
+// FP64-pipe bound (no HBM stream at all).  RHS-only problems without a feasibility mask (Q = 0, rvdOmCnt = 0).
+// ======================================================================================================
+#ifndef SD_RC_AUTO_MAX
+#define SD_RC_AUTO_MAX 4       // automatic use of the recompute sweep up to this many random right-hand sides
+#endif
+struct SweepRcArgs {
+	const double *omega; int64_t NP; const double *lambda; int64_t LP; const int32_t *bLamPos;
+	const double *descA, *descC; const int32_t *descRow, *descWin;
+	int basisCnt, chunkSize, nChunks;
+	double *partV; int32_t *partI;
+};
+
+template <int RB>
+__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_recompute(SweepRcArgs a) {
+	constexpr int RBP = (RB + 1) & ~1;                       // lambda entries per basis in shared memory, padded to a whole number of double2
+	__shared__ double2 s_ac[SW_BATCH];                       // (sigma.pib, piCbarX)
+	__shared__ int s_win[SW_BATCH];
+	__shared__ __align__(16) double s_lam[SW_BATCH][RBP];
+	__shared__ int s_pos[RB];
+	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
+	if (tid < RB) s_pos[tid] = a.bLamPos[tid];
+	double om0[RB], om1[RB];
+#pragma unroll
+	for (int j = 0; j < RB; j++) {
+		const double2 v = *reinterpret_cast<const double2 *>(a.omega + (size_t) j * a.NP + o);
+		om0[j] = v.x; om1[j] = v.y;
+	}
+	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
+	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+	for (int base = b0; base < b1; base += SW_BATCH) {
+		__syncthreads();
+		{
+			const int b = base + tid;
+			const bool ok = b < b1;
+			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
+			s_win[tid] = ok ? a.descWin[b] : 0;
+			const int row = ok ? a.descRow[b] : 0;
+#pragma unroll
+			for (int j = 0; j < RBP; j++) {                  // expandVector: 0.0 where the row carries no lambda entry
+				const int p = j < RB ? s_pos[j] : -1;
+				s_lam[tid][j] = (ok && p >= 0) ? a.lambda[(size_t) p * a.LP + row] : 0.0;
+			}
+		}
+		__syncthreads();
+		const int n = min(SW_BATCH, b1 - base);
+#pragma unroll 2
+		for (int r = 0; r < n; r++) {
+			const int win = s_win[r];
+			if (win == 0) continue;
+			double lam[RBP];
+#pragma unroll
+			for (int j = 0; j < RBP; j += 2) { const double2 v = *reinterpret_cast<const double2 *>(&s_lam[r][j]); lam[j] = v.x; lam[j + 1] = v.y; }
+			double d0 = 0.0, d1 = 0.0;                       // vXvSparse, index order   stocUpdate.c:218
+#pragma unroll
+			for (int j = 0; j < RB; j++) {
+				d0 = __dadd_rn(d0, __dmul_rn(om0[j], lam[j]));
+				d1 = __dadd_rn(d1, __dmul_rn(om1[j], lam[j]));
+			}
+			const double2 ac = s_ac[r];
+			const double s0 = __dsub_rn(__dadd_rn(ac.x, d0), ac.y);      // stocUpdate.c:174
+			const double s1 = __dsub_rn(__dadd_rn(ac.x, d1), ac.y);
+			const int b = base + r;
+			if (win == 1) {
+				if (s0 > oV0) { oV0 = s0; oI0 = b; }
+				if (s1 > oV1) { oV1 = s1; oI1 = b; }
+			}
+			else {
+				if (s0 > nV0) { nV0 = s0; nI0 = b; }
+				if (s1 > nV1) { nV1 = s1; nI1 = b; }
+			}
+		}
+	}
+	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
+	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
+	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
+	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
+	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
+}
+
+// ======================================================================================================
 // K6, variant 2: the same sweep fed by the TMA engine.  One producer warp issues 1-D bulk copies
 // (cp.async.bulk.shared::cluster.global, 4 KiB = one dual row of the observation tile each) into a ring of
 // shared-memory stages guarded by mbarriers; eight consumer warps read their 16 bytes per row with LDS.128 and
@@ -1362,6 +1450,30 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
 			a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
 			const bool hasMask = c->rvd > 0;
+			// very few random right-hand sides: recompute delta.pib from the factors instead of streaming it (FP64-pipe bound, no HBM stream).
+			// Measured (profiles/r01_recompute.jsonl) against the streaming kernels at 16 384 x 131 072; automatic up to SD_RC_AUTO_MAX.
+			const bool rcOk = c->Q == 0 && !hasMask && c->Rb >= 1 && c->Rb <= 8;
+			// 16 384 x 131 072: Rb = 1 / 3 / 4 / 5 / 6 -> 2.23 / 1.34 / 1.15 / 1.09 / 0.84e12 pairs/s against 0.90e12 streaming; 5 000 x 5 000: Rb <= 4 wins, 5 ties
+			const bool useRc = rcOk && (c->sweepVariant == 3 || (c->sweepVariant == 0 && (c->Rb <= SD_RC_AUTO_MAX ||
+					(c->Rb == SD_RC_AUTO_MAX + 1 && (int64_t) c->basisCnt * N >= ((int64_t) 128 << 20)))));
+			if (useRc) {
+				SweepRcArgs r;
+				r.omega = c->d_omega; r.NP = c->NP; r.lambda = c->d_lambda; r.LP = c->LP; r.bLamPos = c->d_bLamPos;
+				r.descA = c->d_descA; r.descC = c->d_descC; r.descRow = c->d_descRow; r.descWin = c->d_descWin;
+				r.basisCnt = (int) c->basisCnt; r.chunkSize = chunkSize; r.nChunks = nChunks; r.partV = c->d_partV; r.partI = c->d_partI;
+				switch (c->Rb) {
+				case 1: k_sweep_recompute<1><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				case 2: k_sweep_recompute<2><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				case 3: k_sweep_recompute<3><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				case 4: k_sweep_recompute<4><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				case 5: k_sweep_recompute<5><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				case 6: k_sweep_recompute<6><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				case 7: k_sweep_recompute<7><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				default: k_sweep_recompute<8><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				}
+				c->stats.last_sweep_variant = 5;
+			}
+			else {
 			// variant 0 = automatic (tools/tma_check.py, profiles/r01_tma_check.jsonl): RHS-only, the LDG kernel wins up to ~100M pairs
 			// (5 000 x 5 000: 34 against 39 us), the two are level at 16 384 x 16 384 and the TMA ring wins beyond (7.31 against 7.02 TB/s
 			// at 65 536 x 131 072); with random T elements the ring wins from ~4M elements up
@@ -1376,6 +1488,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			else if (c->Q > 0)       k_sweep_ldg<true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else if (hasMask)        k_sweep_ldg<false, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else                     k_sweep_ldg<false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
+			}
 		}
 		sd_count_launch(c);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evD, c->stream));
@@ -1501,7 +1614,7 @@ extern "C" int sdgpu_last_istar_device(sdgpu_ctx *c, void **devPtr, int *len) {
 
 extern "C" int sdgpu_set_sweep_variant(sdgpu_ctx *c, int variant) {
 	if (!c) return sdgpu_fail("null context");
-	if (variant < 0 || variant > 2) return sdgpu_fail("unknown sweep variant %d", variant);
+	if (variant < 0 || variant > 3) return sdgpu_fail("unknown sweep variant %d", variant);
 	c->sweepVariant = variant;
 	return 0;
 }

@@ -102,6 +102,42 @@ def test_bulk_multi_tile_multi_chunk(D, N, Q, variant):
     assert np.array_equal(a.view(np.int64), b.view(np.int64))
 
 
+@pytest.mark.parametrize("Rb,R", [(1, 4), (3, 3), (4, 9), (5, 12), (8, 8)])
+def test_recompute_sweep_matches_streaming(Rb, R):
+    """Very few random right-hand sides: the sweep that recomputes delta.pib from (lambda, omega) instead of streaming the table
+    (k_sweep_recompute, variant 3; automatic for Rb <= 4).  Same iStar as the oracle, and the cut is bit-identical to the one the
+    streaming kernel forms from the stored table (the recomputed entry has the stored entry's bits)."""
+    D, N = 900, 1700
+    prob = make_problem(31 + Rb, rows=30, cols=40, n1=10, n1c=8, R=R, Rb=Rb, Q=0)
+    rng = np.random.default_rng(100 + Rb)
+    pis = rng.uniform(-1, 1, (D, prob.rows + 1)) * (rng.random((D, prob.rows + 1)) > 0.3)
+    for d in rng.choice(np.arange(1, D), size=D // 40, replace=False):
+        pis[d] = pis[rng.integers(0, d)]
+    iters = np.ceil((np.arange(D) + 1) * (1.25 * N) / D).astype(np.int32)
+    obs = rng.normal(0, 1, (N, prob.numRV + 1)); obs[:, 0] = 0
+    obs[rng.choice(N, 16, replace=False)] = 0.0
+    weights = (1 + rng.poisson(0.25, N)).astype(np.int32)
+    k = int(weights.sum())
+    caps = Caps(D + 2, D + 2, D + 2, N + 3, 1)
+    to, lo, so = _bulk_tables(oracle_loader.oracle(), prob, pis, np.zeros(D), iters, obs, weights, caps)
+    tg, lg, sg = _bulk_tables(sd.load_library(), prob, pis, np.zeros(D), iters, obs, weights, caps)
+    x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
+    for pi_eval in (0, 1):
+        co = to.sd_cut(x, k, pi_eval, 0.0)
+        tg.set_sweep_variant(1); c1 = tg.sd_cut(x, k, pi_eval, 0.0)
+        assert tg.stats()["last_sweep_variant"] == 1
+        tg.set_sweep_variant(3); c3 = tg.sd_cut(x, k, pi_eval, 0.0)
+        assert tg.stats()["last_sweep_variant"] == 5
+        tg.set_sweep_variant(0); c0 = tg.sd_cut(x, k, pi_eval, 0.0)
+        assert tg.stats()["last_sweep_variant"] == (5 if Rb <= 4 else 1)
+        assert co is not None and c1 is not None and c3 is not None
+        assert np.array_equal(co.iStar, c3.iStar), np.nonzero(co.iStar != c3.iStar)[0][:10]
+        assert np.array_equal(c1.iStar, c3.iStar) and np.array_equal(c0.iStar, c3.iStar)
+        assert c1.alpha == c3.alpha and np.array_equal(c1.beta, c3.beta) and c1.cummOld == c3.cummOld and c1.cummAll == c3.cummAll
+        assert abs(co.alpha - c3.alpha) <= RTOL * abs(co.alpha)
+        assert np.abs(co.beta - c3.beta).max() <= RTOL * max(abs(co.alpha), np.abs(co.beta[1:]).max())
+
+
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("S,N,Q,phi,density", [(900, 1500, 0, 2, 0.8), (600, 1100, 2, 1, 0.5), (1300, 700, 0, 0, 0.9), (640, 1030, 3, 3, 0.7)])
 def test_random_cost_multi_tile_multi_chunk(S, N, Q, phi, density, variant):
