@@ -59,6 +59,9 @@ def run(D, N, R, Q, n1, two_sigma=False, reps=5):
            "variant": {1: "ldg", 2: "tma", 3: "general", 4: "tma_gen", 5: "recompute"}[st["last_sweep_variant"]], "sweep_ms": round(sm, 4), "cut_ms": round(cm, 4),
            "pairs_per_s": round(nb * N / (cm * 1e-3), 0), "sweep_alg_GBps": round(st["last_sweep_bytes"] / (sm * 1e-3) / 1e9, 1),
            "frac_of_measured_peak": round(st["last_sweep_bytes"] / (sm * 1e-3) / 1e9 / peak, 3), "setup_s": round(setup, 2)}
+    if out["variant"] == "recompute":
+        out["note"] = ("FP64-pipe bound: delta.pib is recomputed from (lambda, omega), the table is not read; sweep_alg_GBps is the rate "
+                       "an HBM-bound sweep would need for the same time")
     t.close()
     return out
 
