@@ -88,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -316,7 +316,6 @@ def gpu_arm(args):
         sweep_ms.append(t.stats()["last_sweep_ms"])
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
     st = t.stats()
     launches = st["total_launches"] - l0
     ms_total = ev0.elapsed_time(ev1)
@@ -332,7 +331,7 @@ def gpu_arm(args):
     sweep_avg_ms = float(np.mean(sweep_ms))
     peak, peak_src = measured_peak()
     achieved = sweep_bytes / (sweep_avg_ms * 1e-3) / 1e9
-    sweep_kernel = {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general", 4: "k_sweep_tma_gen", 5: "k_sweep_recompute"}.get(st["last_sweep_variant"], "?")
+    sweep_kernel = {1: "k_sweep_ldg", 2: "k_sweep_tma", 3: "k_sweep_general", 4: "k_sweep_tma_gen", 5: "k_sweep_recompute", 6: "k_sweep_tma_grp"}.get(st["last_sweep_variant"], "?")
 
     # ---- e2e: whole SD iterations through the C ABI with host buffers, wall clock --------------------------------
     def one_iteration(i):
@@ -349,6 +348,7 @@ def gpu_arm(args):
         one_iteration(i)
     barrier()
     e2e_s = (time.perf_counter() - w0)
+    clocks = sampler.stop()                                   # sampled through both timed regions (value and e2e)
     if dist is not None:
         mt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(mt, op=dist.ReduceOp.MAX)

@@ -271,14 +271,15 @@ typedef struct {
 	int64_t total_launches;     /* kernels launched since create                                        */
 	int64_t last_sweep_bytes;   /* algorithmic bytes of the most recent sweep    */
 	int64_t last_sweep_variant; /* 1 = LDG streaming, 2 = TMA bulk ring, 3 = per-term gathers (random cost), 4 = term-linear TMA ring (random cost),
-	                             * 5 = recompute from (lambda, omega), no delta stream (Rb <= 8) */
+	                             * 5 = recompute from (lambda, omega), no delta stream (Rb <= 8), 6 = TMA ring over bases grouped by lambda row */
 } sdgpu_stats;
 int  sdgpu_get_stats(sdgpu_ctx *ctx, sdgpu_stats *out);
 /* CUDA-event timing of the cut (last_cut_ms / last_sweep_ms) costs four event records per cut; off by default. */
 int  sdgpu_set_timing(sdgpu_ctx *ctx, int on);
 /* 0 = automatic by size (TMA bulk rings for large sweeps, LDG streaming / per-term gathers for small ones);
  * 1 forces the load-based kernels, 2 the TMA rings wherever one exists for the problem's shape, 3 the recompute sweep
- * where the problem qualifies (RHS-only, at most 8 random right-hand sides; automatic up to 4). */
+ * where the problem qualifies (RHS-only, at most 8 random right-hand sides; automatic up to 4), 4 the grouped ring
+ * (RHS-only; automatic when several bases share lambda rows). */
 int  sdgpu_set_sweep_variant(sdgpu_ctx *ctx, int variant);
 /* run subsequent work on an existing CUDA stream (cudaStream_t) instead of the context's own */
 int  sdgpu_set_stream(sdgpu_ctx *ctx, void *cudaStream);

@@ -412,6 +412,118 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) k_sweep_tma(SweepArgs a
 	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
 }
 
+// The RHS-only ring for tables in which several bases share a lambda row (calcSigma appends a sigma -- and stochasticUpdates a basis
+// -- whenever pi x bBar or pi x Cbar differ, while the entries on the random rows, the lambda, are already stored: stocUpdate.c:299-318).
+// The host keeps the bases sorted by (lambda row, basis index); the sweep walks that list, and an entry whose row equals its
+// predecessor's inside the same 8-entry stage re-uses the predecessor's ring slot instead of copying the row again: the delta stream
+// shrinks from one row per basis towards one row per distinct lambda (SURVEY.md section 8d counts the algorithmic bytes per distinct
+// row).  The walk is no longer in basis order, so the running maximum is kept lexicographically -- greater score, or equal score and
+// lower basis index -- which is what the strict '>' of stocUpdate.c:178 yields in basis order.
+struct SweepGrpArgs {
+	const double *delta; int64_t Dcap;
+	const double *descA, *descC; const int32_t *descWin;
+	const int32_t *entBasis, *entRow;                    // the bases sorted by (lambda row, basis index) and the row of each
+	int basisCnt, chunkSize, nChunks;
+	double *partV; int32_t *partI; int64_t NP;
+};
+
+#define GRP_ROWS 8
+#define GRP_STAGES 2
+
+__global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *ring = reinterpret_cast<double *>(smem_raw);                                   // [stage][slot][512]
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES);
+	uint64_t *empty = full + GRP_STAGES;
+	double2 *s_ac = reinterpret_cast<double2 *>(empty + GRP_STAGES);                        // [SW_BATCH] (sigma.pib, piCbarX)
+	int *s_win = reinterpret_cast<int *>(s_ac + SW_BATCH);                                 // [SW_BATCH]
+	int *s_bas = s_win + SW_BATCH;                                                         // [SW_BATCH] basis index of the entry
+	int *s_row = s_bas + SW_BATCH;                                                         // [SW_BATCH] lambda row of the entry
+	int *s_lead = s_row + SW_BATCH;                                                        // [SW_BATCH] ring slot (0..7) that holds the entry's row
+	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	const int e0 = chunk * a.chunkSize, e1 = min(a.basisCnt, e0 + a.chunkSize);
+	const int nEnt = e1 - e0, nIter = (nEnt + GRP_ROWS - 1) / GRP_ROWS;
+	const double *tileBase = a.delta + (size_t) tile * a.Dcap * SD_TILE_W;
+	if (tid == 0) {
+		for (int s = 0; s < GRP_STAGES; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	if (tid >= TMA_CONSUMERS) {
+		// ---------------- producer warp: lane r looks after entry r of the stage; only group leaders copy ----------------
+		const int lane = tid - TMA_CONSUMERS;
+		for (int it = 0; it < nIter; it++) {
+			const int s = it % GRP_STAGES;
+			const int e = e0 + it * GRP_ROWS + lane;
+			const bool in = lane < GRP_ROWS && e < e1;
+			const int row = in ? a.entRow[e] : -1;
+			const int prev = __shfl_up_sync(0xffffffffu, row, 1);
+			const bool leader = in && (lane == 0 || prev != row);
+			const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+			sd_mbar_wait(&empty[s], ((it / GRP_STAGES) & 1) ^ 1);
+			if (lane == 0) sd_mbar_expect_tx(&full[s], (uint32_t) __popc(leaders) * TMA_ROW_BYTES);
+			__syncwarp();
+			if (leader) sd_bulk_g2s(ring + ((size_t) s * GRP_ROWS + lane) * SD_TILE_W, tileBase + (size_t) row * SD_TILE_W, TMA_ROW_BYTES, &full[s]);
+		}
+		return;
+	}
+
+	// ---------------- consumers --------------------------------------------------------------------------------------
+	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
+	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+	for (int it = 0; it < nIter; it++) {
+		const int r0 = it * GRP_ROWS;
+		if (r0 % SW_BATCH == 0) {                                                           // refill the descriptor batch (consumers only)
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+			const int e = e0 + r0 + tid;
+			const bool ok = e < e1;
+			const int b = ok ? a.entBasis[e] : 0;
+			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
+			s_win[tid] = ok ? a.descWin[b] : 0;
+			s_bas[tid] = b;
+			s_row[tid] = ok ? a.entRow[e] : -1;
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+			int l = tid;                                                                    // walk back to the leader inside the 8-entry stage
+			while ((l % GRP_ROWS) != 0 && s_row[l - 1] == s_row[tid]) l--;
+			s_lead[tid] = l % GRP_ROWS;
+			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
+		}
+		const int s = it % GRP_STAGES;
+		sd_mbar_wait(&full[s], (it / GRP_STAGES) & 1);
+		const double2 *stage = reinterpret_cast<const double2 *>(ring + (size_t) s * GRP_ROWS * SD_TILE_W) + tid;
+		const int j0 = r0 % SW_BATCH;
+		double2 d[GRP_ROWS];
+#pragma unroll
+		for (int r = 0; r < GRP_ROWS; r++) d[r] = s_win[j0 + r] ? stage[(size_t) s_lead[j0 + r] * (SD_TILE_W / 2)] : make_double2(0.0, 0.0);
+		__syncwarp();
+		if ((tid & 31) == 0) sd_mbar_arrive(&empty[s]);                                    // this warp is done with the stage
+#pragma unroll
+		for (int r = 0; r < GRP_ROWS; r++) {
+			const int win = s_win[j0 + r];
+			if (win == 0) continue;
+			const double2 ac = s_ac[j0 + r];
+			const int b = s_bas[j0 + r];
+			const double s0 = __dsub_rn(__dadd_rn(ac.x, d[r].x), ac.y);                     // stocUpdate.c:174
+			const double s1 = __dsub_rn(__dadd_rn(ac.x, d[r].y), ac.y);
+			if (win == 1) {
+				if (s0 > oV0 || (s0 == oV0 && b < oI0)) { oV0 = s0; oI0 = b; }
+				if (s1 > oV1 || (s1 == oV1 && b < oI1)) { oV1 = s1; oI1 = b; }
+			}
+			else {
+				if (s0 > nV0 || (s0 == nV0 && b < nI0)) { nV0 = s0; nI0 = b; }
+				if (s1 > nV1 || (s1 == nV1 && b < nI1)) { nV1 = s1; nI1 = b; }
+			}
+		}
+	}
+	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
+	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
+	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
+	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
+	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
+	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
+}
+
 // The same ring for problems with random technology-matrix elements (Q > 0): in the tiled layout the 1+Q planes of one
 // dual row are contiguous, so one bulk copy of (1+Q) x 4 KiB brings delta.pib and all of delta.piC for 512 observations.
 // Rows per stage (rps: 1, 2, 4 or 8) and ring depth (stages: 2..4) are picked on the host for the most bytes in flight per SM;
@@ -727,6 +839,7 @@ struct MergeArgs {
 	int randCost;                 // num->rvdOmCnt > 0: the cuts.c:142-159 branch
 	int32_t *iStar; int32_t *iStarHost; int iStarHostCap; double *tilePart; int P;
 	int mW;                       // observations per merge CTA: 64, 128, 256 or 512
+	int lex;                      // chunk maxima are merged lexicographically (grouped sweep: chunks are not ascending basis ranges)
 	// epilogue run by the last block: tile partials -> un-normalised cut [-> normalised cut in mapped host memory]
 	int n1; const int32_t *CCols, *qCols; double *partial; int fuseNormalise, numSamples; double *hostRes; SdDevState *st;
 	// NVLink peer exchange (peerRanks > 1): every rank's buffer, this rank's index, the sequence number of this cut
@@ -756,7 +869,7 @@ extern "C" int sdgpu_debug_phase_clocks(long long *out) { return cudaMemcpyFromS
 // running (max, first index) over the per-chunk partial maxima [c0, c1) of one observation, chunks in ascending basis order; the
 // loads of 8 chunks are issued together (the compare chain is sequential, the memory latency must not be)
 __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, const int32_t *__restrict__ pi, int c0, int c1, int64_t NP,
-		double &bestV, int &bestI) {
+		bool lex, double &bestV, int &bestI) {
 	for (int c = c0; c < c1; c += 8) {
 		double v[8]; int ix[8];
 #pragma unroll
@@ -764,8 +877,9 @@ __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, c
 			const int cc = min(c + u, c1 - 1);
 			v[u] = __ldcg(pv + (size_t) cc * NP); ix[u] = __ldcg(pi + (size_t) cc * NP);
 		}
+		// lex: the chunks are not ascending basis ranges (grouped sweep), so equal maxima are settled by the lower basis index
 #pragma unroll
-		for (int u = 0; u < 8; u++) if (v[u] > bestV) { bestV = v[u]; bestI = ix[u]; }
+		for (int u = 0; u < 8; u++) if (v[u] > bestV || (lex && v[u] == bestV && ix[u] >= 0 && ix[u] < bestI)) { bestV = v[u]; bestI = ix[u]; }
 	}
 }
 
@@ -847,8 +961,8 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	SD_PHASE(0);
 	if (valid) {
 		const int cpl = (a.nChunks + L - 1) / L, c0 = lane * cpl, c1 = min(a.nChunks, c0 + cpl);
-		sd_merge_chunks(a.partV + o, a.partI + o, c0, c1, a.NP, oldV, oldI);
-		if (a.pi_eval) sd_merge_chunks(a.partV + (size_t) a.nChunks * a.NP + o, a.partI + (size_t) a.nChunks * a.NP + o, c0, c1, a.NP, newV, newI);
+		sd_merge_chunks(a.partV + o, a.partI + o, c0, c1, a.NP, a.lex != 0, oldV, oldI);
+		if (a.pi_eval) sd_merge_chunks(a.partV + (size_t) a.nChunks * a.NP + o, a.partI + (size_t) a.nChunks * a.NP + o, c0, c1, a.NP, a.lex != 0, newV, newI);
 	}
 	SD_PHASE(10);
 	if (L > 1) {
@@ -857,8 +971,9 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		if (lane == 0)
 			for (int l = 1; l < L; l++) {                         // ascending lane = ascending basis index
 				const double ov = s_mv[0][l * W + ol], nv = s_mv[1][l * W + ol];
-				if (ov > oldV) { oldV = ov; oldI = s_mi[0][l * W + ol]; }
-				if (nv > newV) { newV = nv; newI = s_mi[1][l * W + ol]; }
+				const int oi = s_mi[0][l * W + ol], ni = s_mi[1][l * W + ol];
+				if (ov > oldV || (a.lex && ov == oldV && oi >= 0 && oi < oldI)) { oldV = ov; oldI = oi; }
+				if (nv > newV || (a.lex && nv == newV && ni >= 0 && ni < newI)) { newV = nv; newI = ni; }
 			}
 	}
 	const bool owner = valid && lane == 0;
@@ -1398,6 +1513,63 @@ static bool sd_tma_gen_shape(const sdgpu_ctx *c, int *rps, int *stages) {
 	return best > 0.0;
 }
 
+// ---- bases grouped by lambda row (host bookkeeping of the grouped sweep) ------------------------------------------------------
+// sigma -> lambda row on the host: the tail that is missing is read back from the device (one small copy, only when sigmas were added)
+static int sd_refresh_host_lam(sdgpu_ctx *c) {
+	const size_t have = c->hostLam.size();
+	if ((int64_t) have >= c->sigmaCnt) return 0;
+	c->hostLam.resize((size_t) c->sigmaCnt);
+	SD_CUDA(cudaMemcpyAsync(c->hostLam.data() + have, c->d_sigmaLam + have, ((size_t) c->sigmaCnt - have) * 4, cudaMemcpyDeviceToHost, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+// number of distinct lambda rows among the bases (all single-term here), kept incrementally
+static int sd_group_count(sdgpu_ctx *c) {
+	if (c->grpCounted == c->basisCnt) return 0;
+	if (sd_refresh_host_lam(c)) return SDGPU_ERR;
+	if ((int64_t) c->grpRowCount.size() < c->lambdaCnt) c->grpRowCount.resize((size_t) c->lambdaCnt, 0);
+	for (int64_t b = c->grpCounted; b < c->basisCnt; b++) {
+		const int r = c->hostLam[c->basis[b].sigmaIdx[0]];
+		if (c->grpRowCount[r]++ == 0) c->grpDistinct++;
+	}
+	c->grpCounted = c->basisCnt;
+	return 0;
+}
+
+// the bases sorted by (row, basis index) on the device: a few new bases are inserted in place, many are re-sorted
+static int sd_group_sort(sdgpu_ctx *c) {
+	if (c->grpSorted == c->basisCnt) return 0;
+	const int64_t B = c->basisCnt;
+	int64_t dirtyFrom = B;
+	auto rowOf = [&](int64_t b) { return c->hostLam[c->basis[b].sigmaIdx[0]]; };
+	if (B - c->grpSorted > 64 || c->grpSorted == 0) {
+		std::vector<int32_t> idx((size_t) B);
+		for (int64_t b = 0; b < B; b++) idx[b] = (int32_t) b;
+		std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return rowOf(x) < rowOf(y); });     // stable: ascending basis index inside a row
+		c->grpBasis = idx;
+		c->grpRow.resize((size_t) B);
+		for (int64_t i = 0; i < B; i++) c->grpRow[i] = rowOf(idx[i]);
+		dirtyFrom = 0;
+	}
+	else {
+		for (int64_t b = c->grpSorted; b < B; b++) {
+			const int r = rowOf(b);
+			const int64_t pos = std::upper_bound(c->grpRow.begin(), c->grpRow.end(), r) - c->grpRow.begin();      // end of the row's group: b is the largest index so far
+			c->grpRow.insert(c->grpRow.begin() + pos, r);
+			c->grpBasis.insert(c->grpBasis.begin() + pos, (int32_t) b);
+			dirtyFrom = std::min(dirtyFrom, pos);
+		}
+	}
+	c->grpSorted = B;
+	if (dirtyFrom < B) {
+		SD_CUDA(cudaMemcpyAsync(c->d_entBasis + dirtyFrom, c->grpBasis.data() + dirtyFrom, (size_t) (B - dirtyFrom) * 4, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaMemcpyAsync(c->d_entRow + dirtyFrom, c->grpRow.data() + dirtyFrom, (size_t) (B - dirtyFrom) * 4, cudaMemcpyHostToDevice, c->stream));
+		SD_CUDA(cudaStreamSynchronize(c->stream));          // the vectors are pageable and may change before the next cut
+	}
+	return 0;
+}
+
 static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, bool fuseNormalise) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
 	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
@@ -1424,6 +1596,8 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);
 		dim3 grid((unsigned) tiles, (unsigned) nChunks);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
+		bool lexMerge = false;
+		int64_t sweepRows = c->termCnt;                    // delta rows the sweep has to read (one per term; one per distinct lambda when grouped)
 		if (useGenTma) {
 			SweepTGArgs g;
 			g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
@@ -1474,6 +1648,28 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 				c->stats.last_sweep_variant = 5;
 			}
 			else {
+			// several bases on one lambda row: walk the bases grouped by row and read each row once per stage (k_sweep_tma_grp) when at
+			// least 15 % of the row copies go away (variant 4 forces it)
+			bool useGrp = false;
+			if (c->Q == 0 && !hasMask && (c->sweepVariant == 4 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N >= ((int64_t) 128 << 20)))) {
+				if (sd_group_count(c)) return SDGPU_ERR;
+				useGrp = c->sweepVariant == 4 || c->grpDistinct * 100 <= c->basisCnt * 85;
+				if (useGrp && sd_group_sort(c)) return SDGPU_ERR;
+			}
+			if (useGrp) {
+				SweepGrpArgs g;
+				g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
+				g.entBasis = c->d_entBasis; g.entRow = c->d_entRow;
+				g.basisCnt = (int) c->basisCnt; g.chunkSize = chunkSize; g.nChunks = nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
+				const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + 4 * sizeof(int));
+				if (!c->tmaAttrSet[7]) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaAttrSet[7] = true; }
+				if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));          // (the host-side grouping above is not part of the sweep time)
+				k_sweep_tma_grp<<<grid, TMA_THREADS, smem, c->stream>>>(g);
+				c->stats.last_sweep_variant = 6;
+				lexMerge = true;
+				sweepRows = c->grpDistinct;
+			}
+			else {
 			// variant 0 = automatic (tools/tma_check.py, profiles/r01_tma_check.jsonl): RHS-only, the LDG kernel wins up to ~100M pairs
 			// (5 000 x 5 000: 34 against 39 us), the two are level at 16 384 x 16 384 and the TMA ring wins beyond (7.31 against 7.02 TB/s
 			// at 65 536 x 131 072); with random T elements the ring wins from ~4M elements up
@@ -1489,14 +1685,15 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			else if (hasMask)        k_sweep_ldg<false, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			else                     k_sweep_ldg<false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
 			}
+			}
 		}
 		sd_count_launch(c);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evD, c->stream));
 		// algorithmic bytes of the sweep: delta stream + per-observation weight and iStar + per-basis descriptors
-		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * c->termCnt * (int64_t) N + (c->rvd > 0 ? c->basisCnt * (int64_t) N : 0) + (int64_t) N * 8 + c->basisCnt * 16;
+		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * sweepRows * (int64_t) N + (c->rvd > 0 ? c->basisCnt * (int64_t) N : 0) + (int64_t) N * 8 + c->basisCnt * 16;
 
 		MergeArgs m;
-		m.partV = c->d_partV; m.partI = c->d_partI; m.nChunks = nChunks; m.NP = c->NP;
+		m.partV = c->d_partV; m.partI = c->d_partI; m.nChunks = nChunks; m.NP = c->NP; m.lex = lexMerge ? 1 : 0;
 		m.omegaCnt = N; m.pi_eval = pi_eval_flag != 0; m.lb = lb;
 		m.omegaW = c->d_omegaW; m.omega = c->d_omega; m.rvOffset2 = c->rvOffset[2];
 		m.delta = c->d_delta; m.Dcap = c->caps.maxLambda; m.Q = c->Q;
@@ -1614,7 +1811,7 @@ extern "C" int sdgpu_last_istar_device(sdgpu_ctx *c, void **devPtr, int *len) {
 
 extern "C" int sdgpu_set_sweep_variant(sdgpu_ctx *c, int variant) {
 	if (!c) return sdgpu_fail("null context");
-	if (variant < 0 || variant > 3) return sdgpu_fail("unknown sweep variant %d", variant);
+	if (variant < 0 || variant > 4) return sdgpu_fail("unknown sweep variant %d", variant);
 	c->sweepVariant = variant;
 	return 0;
 }

@@ -151,6 +151,13 @@ struct sdgpu_ctx {
 	bool    anyInfeasibleBasis = false;
 	std::vector<SdHostBasis> basis;
 	std::vector<std::vector<uint8_t>> hostMask;   // [b][NP] only when rvd > 0
+	// bases grouped by lambda row for the grouped sweep (several sigmas / bases on one lambda): host bookkeeping, device copies of the order
+	std::vector<int32_t> hostLam;                 // sigma -> lambda row (mirror of d_sigmaLam, refreshed on demand)
+	std::vector<int32_t> grpRowCount;             // bases per lambda row (single-term bases only)
+	int64_t grpCounted = 0, grpDistinct = 0;      // bases counted so far, distinct rows among them
+	std::vector<int32_t> grpBasis, grpRow;        // bases sorted by (row, basis index), and the row of each entry
+	int64_t grpSorted = 0;                        // bases present in the sorted arrays
+	int32_t *d_entBasis = nullptr, *d_entRow = nullptr;
 
 	// NVLink peer-memory exchange (sdgpu_peer_export / _attach): slots[2][G][n1+4] doubles then flags[2][G] uint32
 	static const int kMaxPeers = 16;

@@ -102,6 +102,54 @@ def test_bulk_multi_tile_multi_chunk(D, N, Q, variant):
     assert np.array_equal(a.view(np.int64), b.view(np.int64))
 
 
+@pytest.mark.parametrize("D,N,extra", [(500, 1500, 2), (900, 700, 1), (300, 1100, 5)])
+def test_grouped_sweep_shared_lambda_rows(D, N, extra):
+    """Several sigmas / bases per lambda row (calcSigma appends a sigma whenever pi x bBar or pi x Cbar differ while the lambda is
+    already stored): the grouped sweep (variant 4) walks the bases sorted by (row, basis index) and keeps the running maximum
+    lexicographically.  iStar equals the oracle's, and the cut is bit-identical to the plain kernels'.  Bases are interleaved
+    (second sigmas appended after all first ones) so the sorted walk is far from basis order; duplicated duals force ties
+    across groups."""
+    prob = make_problem(17, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=0)
+    rng = np.random.default_rng(D + N + extra)
+    pis = rng.uniform(-1, 1, (D, prob.rows + 1)) * (rng.random((D, prob.rows + 1)) > 0.3)
+    for d in rng.choice(np.arange(1, D), size=max(1, D // 50), replace=False):
+        pis[d] = pis[rng.integers(0, d)]
+    iters = np.ceil((np.arange(D) + 1) * (1.25 * N) / D).astype(np.int32)
+    obs = rng.normal(0, 1, (N, prob.numRV + 1)); obs[:, 0] = 0
+    obs[rng.choice(N, 16, replace=False)] = 0.0
+    weights = (1 + rng.poisson(0.25, N)).astype(np.int32)
+    k = int(weights.sum())
+    nb = D * (1 + extra)
+    caps = Caps(D + 2, nb + 2, nb + 2, N + 3, 1)
+    tabs = []
+    for api in (oracle_loader.oracle(), sd.load_library()):
+        t, li, si = _bulk_tables(api, prob, pis, np.zeros(D), iters, obs, weights, caps)
+        for e in range(extra):
+            for d in range(D):                  # every call appends a sigma (mubBar differs), so basis index == sigma index stays true (cuts.c:161)
+                s2, new = t.calc_sigma(pis[d], 1.0 + e + 0.25 * (d % 3), int(li[d]), False, int(iters[(d * 7 + e) % D]), 1e-3)
+                assert new
+                t.basis_append(int(iters[(d * 7 + e) % D]), True, [s2])
+        tabs.append(t)
+    to, tg = tabs
+    assert to.counts() == tg.counts() and tg.counts()["basis"] > D
+    x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
+    for pi_eval in (0, 1):
+        co = to.sd_cut(x, k, pi_eval, 0.0)
+        tg.set_sweep_variant(1); c1 = tg.sd_cut(x, k, pi_eval, 0.0)
+        tg.set_sweep_variant(4); c4 = tg.sd_cut(x, k, pi_eval, 0.0)
+        assert tg.stats()["last_sweep_variant"] == 6
+        assert co is not None and c1 is not None and c4 is not None
+        assert np.array_equal(co.iStar, c4.iStar), np.nonzero(co.iStar != c4.iStar)[0][:10]
+        assert np.array_equal(c1.iStar, c4.iStar)
+        assert c1.alpha == c4.alpha and np.array_equal(c1.beta, c4.beta) and c1.cummOld == c4.cummOld and c1.cummAll == c4.cummAll
+        assert (co.iStar >= D).any(), "no second-sigma basis ever won: the test does not exercise the groups"
+    # a basis appended after the grouping was built is inserted in place
+    s3, new = tg.calc_sigma(pis[3], 77.0, 3, False, 1, 1e-3); tg.basis_append(1, True, [s3])
+    s3o, _ = to.calc_sigma(pis[3], 77.0, 3, False, 1, 1e-3); to.basis_append(1, True, [s3o])
+    co = to.sd_cut(x, k, 1, 0.0); c4 = tg.sd_cut(x, k, 1, 0.0)
+    assert np.array_equal(co.iStar, c4.iStar)
+
+
 @pytest.mark.parametrize("Rb,R", [(1, 4), (3, 3), (4, 9), (5, 12), (8, 8)])
 def test_recompute_sweep_matches_streaming(Rb, R):
     """Very few random right-hand sides: the sweep that recomputes delta.pib from (lambda, omega) instead of streaming the table

@@ -56,7 +56,7 @@ def run(D, N, R, Q, n1, two_sigma=False, reps=5):
     peak, _ = bench.measured_peak()
     sm, cm = float(np.median(sweep)), float(np.median(cut))
     out = {"duals": D, "bases": nb, "observations": N, "R": R, "Q": Q, "n1": n1, "delta_GiB": round(8 * (1 + Q) * D * N / 2**30, 2),
-           "variant": {1: "ldg", 2: "tma", 3: "general", 4: "tma_gen", 5: "recompute"}[st["last_sweep_variant"]], "sweep_ms": round(sm, 4), "cut_ms": round(cm, 4),
+           "variant": {1: "ldg", 2: "tma", 3: "general", 4: "tma_gen", 5: "recompute", 6: "tma_grouped"}[st["last_sweep_variant"]], "sweep_ms": round(sm, 4), "cut_ms": round(cm, 4),
            "pairs_per_s": round(nb * N / (cm * 1e-3), 0), "sweep_alg_GBps": round(st["last_sweep_bytes"] / (sm * 1e-3) / 1e9, 1),
            "frac_of_measured_peak": round(st["last_sweep_bytes"] / (sm * 1e-3) / 1e9 / peak, 3), "setup_s": round(setup, 2)}
     if out["variant"] == "recompute":
