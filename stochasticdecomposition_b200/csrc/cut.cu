@@ -430,16 +430,17 @@ struct SweepGrpArgs {
 #define GRP_ROWS 8
 #define GRP_STAGES 2
 
+// greater score, or equal score and lower basis index; the equal case is rare, so the common path is one compare
+#define SD_LEX_UPDATE(sc, bb, bestV, bestI) do { if ((sc) >= (bestV)) { if ((sc) > (bestV) || (bb) < (bestI)) { (bestV) = (sc); (bestI) = (bb); } } } while (0)
+
 __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double *ring = reinterpret_cast<double *>(smem_raw);                                   // [stage][slot][512]
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES);
 	uint64_t *empty = full + GRP_STAGES;
 	double2 *s_ac = reinterpret_cast<double2 *>(empty + GRP_STAGES);                        // [SW_BATCH] (sigma.pib, piCbarX)
-	int *s_win = reinterpret_cast<int *>(s_ac + SW_BATCH);                                 // [SW_BATCH]
-	int *s_bas = s_win + SW_BATCH;                                                         // [SW_BATCH] basis index of the entry
-	int *s_row = s_bas + SW_BATCH;                                                         // [SW_BATCH] lambda row of the entry
-	int *s_lead = s_row + SW_BATCH;                                                        // [SW_BATCH] ring slot (0..7) that holds the entry's row
+	int *s_meta = reinterpret_cast<int *>(s_ac + SW_BATCH);                                // [SW_BATCH] window | leader slot << 2 | basis << 5
+	int *s_row = s_meta + SW_BATCH;                                                        // [SW_BATCH] lambda row of the entry
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	const int e0 = chunk * a.chunkSize, e1 = min(a.basisCnt, e0 + a.chunkSize);
 	const int nEnt = e1 - e0, nIter = (nEnt + GRP_ROWS - 1) / GRP_ROWS;
@@ -479,14 +480,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a
 			const int e = e0 + r0 + tid;
 			const bool ok = e < e1;
 			const int b = ok ? a.entBasis[e] : 0;
+			const int win = ok ? a.descWin[b] : 0;
 			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
-			s_win[tid] = ok ? a.descWin[b] : 0;
-			s_bas[tid] = b;
 			s_row[tid] = ok ? a.entRow[e] : -1;
 			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
 			int l = tid;                                                                    // walk back to the leader inside the 8-entry stage
 			while ((l % GRP_ROWS) != 0 && s_row[l - 1] == s_row[tid]) l--;
-			s_lead[tid] = l % GRP_ROWS;
+			s_meta[tid] = win | ((l % GRP_ROWS) << 2) | (b << 5);
 			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
 		}
 		const int s = it % GRP_STAGES;
@@ -494,26 +494,24 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a
 		const double2 *stage = reinterpret_cast<const double2 *>(ring + (size_t) s * GRP_ROWS * SD_TILE_W) + tid;
 		const int j0 = r0 % SW_BATCH;
 		double2 d[GRP_ROWS];
+		int meta[GRP_ROWS];
 #pragma unroll
-		for (int r = 0; r < GRP_ROWS; r++) d[r] = s_win[j0 + r] ? stage[(size_t) s_lead[j0 + r] * (SD_TILE_W / 2)] : make_double2(0.0, 0.0);
+		for (int r = 0; r < GRP_ROWS; r++) {
+			meta[r] = s_meta[j0 + r];
+			d[r] = (meta[r] & 3) ? stage[(size_t) ((meta[r] >> 2) & 7) * (SD_TILE_W / 2)] : make_double2(0.0, 0.0);
+		}
 		__syncwarp();
 		if ((tid & 31) == 0) sd_mbar_arrive(&empty[s]);                                    // this warp is done with the stage
 #pragma unroll
 		for (int r = 0; r < GRP_ROWS; r++) {
-			const int win = s_win[j0 + r];
+			const int win = meta[r] & 3;
 			if (win == 0) continue;
 			const double2 ac = s_ac[j0 + r];
-			const int b = s_bas[j0 + r];
+			const int b = meta[r] >> 5;
 			const double s0 = __dsub_rn(__dadd_rn(ac.x, d[r].x), ac.y);                     // stocUpdate.c:174
 			const double s1 = __dsub_rn(__dadd_rn(ac.x, d[r].y), ac.y);
-			if (win == 1) {
-				if (s0 > oV0 || (s0 == oV0 && b < oI0)) { oV0 = s0; oI0 = b; }
-				if (s1 > oV1 || (s1 == oV1 && b < oI1)) { oV1 = s1; oI1 = b; }
-			}
-			else {
-				if (s0 > nV0 || (s0 == nV0 && b < nI0)) { nV0 = s0; nI0 = b; }
-				if (s1 > nV1 || (s1 == nV1 && b < nI1)) { nV1 = s1; nI1 = b; }
-			}
+			if (win == 1) { SD_LEX_UPDATE(s0, b, oV0, oI0); SD_LEX_UPDATE(s1, b, oV1, oI1); }
+			else          { SD_LEX_UPDATE(s0, b, nV0, nI0); SD_LEX_UPDATE(s1, b, nV1, nI1); }
 		}
 	}
 	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
@@ -1651,7 +1649,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			// several bases on one lambda row: walk the bases grouped by row and read each row once per stage (k_sweep_tma_grp) when at
 			// least 15 % of the row copies go away (variant 4 forces it)
 			bool useGrp = false;
-			if (c->Q == 0 && !hasMask && (c->sweepVariant == 4 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N >= ((int64_t) 128 << 20)))) {
+			if (c->Q == 0 && !hasMask && c->basisCnt < (1 << 26) && (c->sweepVariant == 4 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N >= ((int64_t) 128 << 20)))) {
 				if (sd_group_count(c)) return SDGPU_ERR;
 				useGrp = c->sweepVariant == 4 || c->grpDistinct * 100 <= c->basisCnt * 85;
 				if (useGrp && sd_group_sort(c)) return SDGPU_ERR;
@@ -1661,7 +1659,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 				g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
 				g.entBasis = c->d_entBasis; g.entRow = c->d_entRow;
 				g.basisCnt = (int) c->basisCnt; g.chunkSize = chunkSize; g.nChunks = nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
-				const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + 4 * sizeof(int));
+				const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + 2 * sizeof(int));
 				if (!c->tmaAttrSet[7]) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaAttrSet[7] = true; }
 				if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));          // (the host-side grouping above is not part of the sweep time)
 				k_sweep_tma_grp<<<grid, TMA_THREADS, smem, c->stream>>>(g);
