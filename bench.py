@@ -208,6 +208,28 @@ def run_cpu(kind: str, args, steps: int, warmup: int):
             "ms_per_step": sec * 1e3, "pairs_per_step": nb * N}
 
 
+def sd_iterations_leg(iterations: int):
+    """BASELINE.json's third figure: SD iterations per second on an ssn-shaped instance (n1 = 89, 175 rows, 86 random right-hand
+    sides), the same host loop (tools/sd_highs_host.py: HiGHS for the subproblem LP and the master, not CPLEX; synthetic instance, the
+    SMPS file is not available offline) over this library's tables and over the reference's CPU tables (oracle/_ref)."""
+    try:
+        tools = os.path.join(ROOT, "tools")
+        if tools not in sys.path:
+            sys.path.insert(0, tools)
+        import oracle_loader
+        import stochasticdecomposition_b200 as sd
+        from sd_iterations_bench import run
+        g = run(sd.load_library(), "gpu", "ssn", iterations, 7)
+        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsdref.so")) or os.path.isdir("/root/reference")
+        r = run(oracle_loader.reference() if have_ref else oracle_loader.oracle(), "reference" if have_ref else "port", "ssn", iterations, 7)
+        return {"shape": "ssn-shaped synthetic instance", "iterations": iterations, "lp_solver": "HiGHS (scipy), not CPLEX",
+                "gpu_tables_it_per_s": g["iterations_per_s"], "gpu_argmax_seconds": g["argmax_seconds"], "gpu_argmax_share": g["argmax_share"],
+                "cpu_tables_it_per_s": r["iterations_per_s"], "cpu_argmax_seconds": r["argmax_seconds"], "cpu_argmax_share": r["argmax_share"],
+                "cpu_tables_kind": r["backend"], "same_incumbent_estimate": abs(g["incumbent_estimate"] - r["incumbent_estimate"]) <= 1e-9 * max(1.0, abs(r["incumbent_estimate"]))}
+    except Exception as exc:                                  # an optional extra: never let it take the bench line down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -363,6 +385,11 @@ def gpu_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = run_cpu("reference", args, 3, 1)
         cpu_omp = run_cpu("port_omp", args, 3, 1)
+    sdit = None
+    if rank == 0 and world == 1 and not args.no_cpu and args.sd_iterations > 0:
+        t.close()                                              # 64 GiB back before the second context
+        t = None
+        sdit = sd_iterations_leg(args.sd_iterations)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -384,11 +411,14 @@ def gpu_arm(args):
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline_omp_port"] = {k: cpu_omp[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if sdit is not None:
+            line["sd_iterations_ssn"] = sdit
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    t.close()
+    if t is not None:
+        t.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -407,6 +437,7 @@ def main():
     ap.add_argument("--cpu-duals", type=int, default=4096)
     ap.add_argument("--cpu-obs", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sd-iterations", type=int, default=600, help="ssn-shaped SD run for the iterations/s figure (0 = skip)")
     ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
