@@ -281,6 +281,9 @@ int  sdgpu_set_timing(sdgpu_ctx *ctx, int on);
  * where the problem qualifies (RHS-only, at most 8 random right-hand sides; automatic up to 4), 4 the grouped ring
  * (RHS-only; automatic when several bases share lambda rows). */
 int  sdgpu_set_sweep_variant(sdgpu_ctx *ctx, int variant);
+/* host-only: the 2-D sweep grid (observation tiles x basis chunks) the library would launch for a table of this shape on a
+ * GPU with smCount SMs -- the wave-aware chunk count of DESIGN.md section 4; needs no device */
+int  sdgpu_plan_sweep_grid(int smCount, int64_t observations, int64_t bases, int maxChunks, int *tiles, int *chunkSize, int *nChunks);
 /* run subsequent work on an existing CUDA stream (cudaStream_t) instead of the context's own */
 int  sdgpu_set_stream(sdgpu_ctx *ctx, void *cudaStream);
 

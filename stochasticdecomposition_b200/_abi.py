@@ -230,11 +230,19 @@ class Api:
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
             "get_stats": (i, [vp, C.POINTER(CStats)]),
             "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]),
+            "plan_sweep_grid": (i, [i, i64, i64, i, c_intp, c_intp, c_intp]),
         }
         for name, (res, args) in table.items():
             fn = self._fn(name)
             if fn is not None:
                 fn.restype, fn.argtypes = res, args
+
+    def plan_sweep_grid(self, sm_count: int, observations: int, bases: int, max_chunks: int = 64):
+        """(tiles, chunkSize, nChunks) of the 2-D sweep grid for a table of this shape; host-only, no device needed."""
+        t, cs, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+        if self._fn("plan_sweep_grid")(sm_count, observations, bases, max_chunks, C.byref(t), C.byref(cs), C.byref(nc)) != 0:
+            raise SdError(self.error())
+        return t.value, cs.value, nc.value
 
     def error(self) -> str:
         fn = self._fn("last_error")

@@ -1405,24 +1405,36 @@ static SweepGenArgs sd_gen_args(sdgpu_ctx *c, int chunkSize, int nChunks) {
 // and with 10 tiles 44 chunks (one full wave) beat 64 (1.44 waves) -- and more, shorter CTAs shrink the tail.  So: as many chunks
 // as the scratch and a minimum chunk length allow, up to ~32 waves, then step down to the nearest count whose last wave is at
 // least 60 % full.
-static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks) {
-	int smCount = 148;
-	cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, c->device);
+static void sd_pick_chunks_for(int smCount, int tiles, int64_t basisCnt, int maxChunks, int forced, int *chunkSize, int *nChunks) {
 	const double slots = (double) smCount * 3;
-	int64_t cmax = std::min<int64_t>(c->maxChunks, std::max<int64_t>(1, (c->basisCnt + 31) / 32));   // at least four load batches per chunk
+	int64_t cmax = std::min<int64_t>(maxChunks, std::max<int64_t>(1, (basisCnt + 31) / 32));   // at least four load batches per chunk
 	cmax = std::min<int64_t>(cmax, std::max<int64_t>(1, (int64_t) ceil(32.0 * slots / tiles)));
 	int64_t want = cmax;
 	for (int64_t cc = cmax; cc >= std::max<int64_t>(1, cmax / 2); cc--) {
 		const double w = tiles * (double) cc / slots;
 		if (ceil(w) - w <= 0.4) { want = cc; break; }
 	}
-	static int envChunks = -1;                // SDGPU_CHUNKS = experiment knob (forces the chunk count, within the scratch limit)
-	if (envChunks < 0) { const char *e = getenv("SDGPU_CHUNKS"); envChunks = e ? atoi(e) : 0; }
-	if (envChunks > 0) want = std::min<int64_t>(std::min<int64_t>(envChunks, c->maxChunks), std::max<int64_t>(1, c->basisCnt));
-	int cs = (int) ((c->basisCnt + want - 1) / want);
+	if (forced > 0) want = std::min<int64_t>(std::min<int64_t>(forced, maxChunks), std::max<int64_t>(1, basisCnt));
+	int cs = (int) ((basisCnt + want - 1) / want);
 	cs = std::max(cs, 1);
 	*chunkSize = cs;
-	*nChunks = (int) ((c->basisCnt + cs - 1) / cs);
+	*nChunks = (int) ((basisCnt + cs - 1) / cs);
+}
+
+static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks) {
+	int smCount = 148;
+	cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, c->device);
+	static int envChunks = -1;                // SDGPU_CHUNKS = experiment knob (forces the chunk count, within the scratch limit)
+	if (envChunks < 0) { const char *e = getenv("SDGPU_CHUNKS"); envChunks = e ? atoi(e) : 0; }
+	sd_pick_chunks_for(smCount, tiles, c->basisCnt, c->maxChunks, envChunks, chunkSize, nChunks);
+}
+
+// host-only view of the grid choice (no device needed): what the sweep would launch for a table of this shape
+extern "C" int sdgpu_plan_sweep_grid(int smCount, int64_t observations, int64_t bases, int maxChunks, int *tiles, int *chunkSize, int *nChunks) {
+	if (smCount <= 0 || observations <= 0 || bases <= 0 || maxChunks <= 0 || !tiles || !chunkSize || !nChunks) return sdgpu_fail("plan_sweep_grid: bad argument");
+	*tiles = (int) ((observations + SD_TILE_W - 1) / SD_TILE_W);
+	sd_pick_chunks_for(smCount, *tiles, bases, maxChunks, 0, chunkSize, nChunks);
+	return 0;
 }
 
 template <int ROWS, int STAGES, int CTAS>

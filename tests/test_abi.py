@@ -66,3 +66,24 @@ def test_dual_stability_tail_matches_oracle():
         fb = orc._fn("dual_stability")(old, allv, k, 3, scan, _pf64(rb))
         assert fa == fb
         assert np.array_equal(ra.view(np.int64), rb.view(np.int64))
+
+
+def test_sweep_grid_plan_is_wave_aware():
+    """Host-only check of the chunk-count rule ("Basis chunks"): with three resident CTAs per SM a grid must not
+    end just past a whole number of waves; chunks cover every basis exactly once and never exceed the scratch limit."""
+    import math
+    api = sd.load_library()
+    slots = 148 * 3
+    for N, B in [(131072, 65536), (5000, 5000), (5000, 7500), (1000, 1000), (16384, 16384), (1048576, 4096), (1048576, 16384), (64, 64),
+                 (400000, 512), (65536, 8192), (20000, 4096), (700, 2100), (300, 31), (513, 1)]:
+        tiles, cs, nc = api.plan_sweep_grid(148, N, B, 64)
+        assert tiles == (N + 511) // 512
+        assert 1 <= nc <= 64 and cs >= 1 and (nc - 1) * cs < B <= nc * cs          # every basis in exactly one chunk
+        assert nc == 1 or cs >= 16                                                # chunks stay long enough to amortise their start-up
+        waves = tiles * nc / slots
+        best_possible = max((tiles * c / slots) for c in range(1, min(64, max(1, (B + 31) // 32)) + 1))
+        if best_possible >= 2.0:                                                  # multi-wave regime: the last wave is at least 60 % full
+            assert math.ceil(waves) - waves <= 0.4 + 1e-9 or waves >= 30, (N, B, tiles, nc, waves)
+    # the two cases that motivated the rule: 256 tiles must not get 7 chunks (4.04 waves); 10 tiles get one full wave, not 1.44
+    assert api.plan_sweep_grid(148, 131072, 65536, 64)[2] != 7
+    assert api.plan_sweep_grid(148, 5000, 5000, 64)[2] == 44
