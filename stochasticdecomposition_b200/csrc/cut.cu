@@ -25,6 +25,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <type_traits>
 
 #include "sdgpu_internal.cuh"
 
@@ -132,12 +133,38 @@ struct SweepArgs {
 #define SW_BATCH 256    // basis descriptors staged per shared-memory refill
 #define SW_UNROLL 8     // delta rows in flight per thread
 
-template <bool HAS_Q, bool HAS_MASK>
-__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a) {
+// FUSED: the descriptors of k_cut_prep are computed here, by the CTA that needs them (small cuts: one launch and ~8 us less; every
+// observation tile repeats the piCbarX dots of its chunk, which is nothing next to a launch as long as the grid is a single wave)
+struct SweepPrepArgs {
+	SdXParam xp;
+	const double *piCk; int64_t SP; int n1c; const int32_t *CCols;
+	const int32_t *bCk, *bFeas, *bTermStart, *tSigma; const double *sigmaPib; const int32_t *sigmaLam;
+	int split, cutoff;
+};
+
+// k_cut_prep's arithmetic for one basis (cuts.c:105-106, stocUpdate.c:151-167): (sigma.pib, piCbarX) and (lambda row, window)
+__device__ __forceinline__ void sd_basis_descriptor(const SweepPrepArgs &pa, const double *s_xc, int b, double2 &ac, int2 &rw) {
+	const int sg = pa.tSigma[pa.bTermStart[b]];
+	const double acc = sd_dot_strided(pa.piCk + sg, (size_t) pa.SP, s_xc, pa.n1c);
+	const int ck = pa.bCk[b];
+	int win = 0;
+	if (pa.bFeas[b]) {
+		if (ck <= pa.cutoff) win = (ck > -INT_MAX) ? 1 : 0;
+		else win = pa.split ? 2 : 0;
+	}
+	ac = make_double2(pa.sigmaPib[sg], acc);
+	rw = make_int2(pa.sigmaLam[sg], win);
+}
+
+template <bool HAS_Q, bool HAS_MASK, bool FUSED>
+__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typename std::conditional<FUSED, SweepPrepArgs, int>::type pa_) {
+	const SweepPrepArgs &pa = *reinterpret_cast<const SweepPrepArgs *>(&pa_);      // only dereferenced when FUSED
 	__shared__ double2 s_ac[SW_BATCH];       // (sigma.pib, piCbarX)
 	__shared__ int2 s_rw[SW_BATCH];          // (lambda row, window)
 	__shared__ double s_xq[HAS_Q ? 64 : 1];
+	extern __shared__ double s_xc[];         // FUSED: x[CCols[k]]
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+	if (FUSED) for (int k = tid; k < pa.n1c; k += blockDim.x) s_xc[k] = pa.xp.v[pa.CCols[k]];
 	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
 	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
 	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride + 2 * tid;
@@ -152,8 +179,12 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a) {
 		{
 			int b = base + tid;
 			bool ok = b < b1;
-			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
-			s_rw[tid] = ok ? make_int2(a.descRow[b], a.descWin[b]) : make_int2(0, 0);
+			if (!FUSED) {
+				s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
+				s_rw[tid] = ok ? make_int2(a.descRow[b], a.descWin[b]) : make_int2(0, 0);
+			}
+			else if (ok) sd_basis_descriptor(pa, s_xc, b, s_ac[tid], s_rw[tid]);
+			else { s_ac[tid] = make_double2(0.0, 0.0); s_rw[tid] = make_int2(0, 0); }
 		}
 		__syncthreads();
 		const int n = min(SW_BATCH, b1 - base);
@@ -225,8 +256,10 @@ struct SweepRcArgs {
 	double *partV; int32_t *partI;
 };
 
-template <int RB>
-__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_recompute(SweepRcArgs a) {
+template <int RB, bool FUSED>
+__global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_recompute(SweepRcArgs a, typename std::conditional<FUSED, SweepPrepArgs, int>::type pa_) {
+	const SweepPrepArgs &pa = *reinterpret_cast<const SweepPrepArgs *>(&pa_);      // only dereferenced when FUSED
+	extern __shared__ double s_xc[];                         // FUSED: x[CCols[k]]
 	constexpr int RBP = (RB + 1) & ~1;                       // lambda entries per basis in shared memory, padded to a whole number of double2
 	__shared__ double2 s_ac[SW_BATCH];                       // (sigma.pib, piCbarX)
 	__shared__ int s_win[SW_BATCH];
@@ -236,6 +269,7 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_recompute(SweepRcArg
 	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
 	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
 	if (tid < RB) s_pos[tid] = a.bLamPos[tid];
+	if (FUSED) for (int k = tid; k < pa.n1c; k += blockDim.x) s_xc[k] = pa.xp.v[pa.CCols[k]];
 	double om0[RB], om1[RB];
 #pragma unroll
 	for (int j = 0; j < RB; j++) {
@@ -249,9 +283,15 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_recompute(SweepRcArg
 		{
 			const int b = base + tid;
 			const bool ok = b < b1;
-			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
-			s_win[tid] = ok ? a.descWin[b] : 0;
-			const int row = ok ? a.descRow[b] : 0;
+			double2 ac = make_double2(0.0, 0.0);
+			int2 rw = make_int2(0, 0);
+			if (ok) {
+				if (FUSED) sd_basis_descriptor(pa, s_xc, b, ac, rw);
+				else { ac = make_double2(a.descA[b], a.descC[b]); rw = make_int2(a.descRow[b], a.descWin[b]); }
+			}
+			s_ac[tid] = ac;
+			s_win[tid] = rw.y;
+			const int row = rw.x;
 #pragma unroll
 			for (int j = 0; j < RBP; j++) {                  // expandVector: 0.0 where the row carries no lambda entry
 				const int p = j < RB ? s_pos[j] : -1;
@@ -1601,14 +1641,24 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		// single-term bases with a mask: the LDG kernel wins at 5 000 x 5 000 (49 against 57 us), the ring from ~50M pairs up (170 against 283 us at 6 144 x 16 384))
 		const int64_t genFrom = multiTerm ? ((int64_t) 4 << 20) : ((int64_t) 48 << 20);
 		const bool useGenTma = genFits && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->termCnt * N * (1 + c->Q) >= genFrom));
-		if (sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, multiTerm && !useGenTma, useGenTma)) return SDGPU_ERR;
 		int chunkSize = 1, nChunks = 1;
 		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);
 		dim3 grid((unsigned) tiles, (unsigned) nChunks);
+		// tiny RHS-only cuts (the first thousand iterations of a real problem): no separate prologue launch, the sweep CTAs compute their own
+		// descriptors.  One CTA per SM at most: the fused kernels need ~128 registers (measured: 1 000 x 1 000 cut 44 -> 38 us; at
+		// 5 000 x 5 000, 440 CTAs, fusing loses 11 us).  The two predicates mirror the kernel choice below.
+		const int64_t pairs = (int64_t) c->basisCnt * N;
+		const bool plainShape = !multiTerm && c->Q == 0 && c->rvd == 0;
+		const bool willRc = plainShape && c->Rb >= 1 && c->Rb <= 8 && (c->sweepVariant == 3 || (c->sweepVariant == 0 &&
+				(c->Rb <= SD_RC_AUTO_MAX || (c->Rb == SD_RC_AUTO_MAX + 1 && pairs >= ((int64_t) 128 << 20)))));
+		const bool willLdg = plainShape && !willRc && (c->sweepVariant == 1 || (c->sweepVariant == 0 && pairs < ((int64_t) 128 << 20)));
+		const bool fusedPrep = (willRc || willLdg) && c->n1 + 1 <= 256 && c->n1c <= 1024 && (int64_t) tiles * nChunks <= 148;
+		if (!fusedPrep && sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, multiTerm && !useGenTma, useGenTma)) return SDGPU_ERR;
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
 		bool lexMerge = false;
 		int64_t sweepRows = c->termCnt;                    // delta rows the sweep has to read (one per term; one per distinct lambda when grouped)
 		if (useGenTma) {
+			if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
 			SweepTGArgs g;
 			g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
 			g.termA = c->d_termA; g.termC = c->d_termC; g.termRow = c->d_termRow; g.termMeta = c->d_termMeta; g.termBasis = c->d_termBasis;
@@ -1623,6 +1673,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			c->stats.last_sweep_variant = 4;
 		}
 		else if (multiTerm) {
+			if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
 			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
 			c->stats.last_sweep_variant = 3;
 		}
@@ -1645,16 +1696,28 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 				r.omega = c->d_omega; r.NP = c->NP; r.lambda = c->d_lambda; r.LP = c->LP; r.bLamPos = c->d_bLamPos;
 				r.descA = c->d_descA; r.descC = c->d_descC; r.descRow = c->d_descRow; r.descWin = c->d_descWin;
 				r.basisCnt = (int) c->basisCnt; r.chunkSize = chunkSize; r.nChunks = nChunks; r.partV = c->d_partV; r.partI = c->d_partI;
-				switch (c->Rb) {
-				case 1: k_sweep_recompute<1><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
-				case 2: k_sweep_recompute<2><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
-				case 3: k_sweep_recompute<3><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
-				case 4: k_sweep_recompute<4><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
-				case 5: k_sweep_recompute<5><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
-				case 6: k_sweep_recompute<6><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
-				case 7: k_sweep_recompute<7><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
-				default: k_sweep_recompute<8><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r); break;
+				SweepPrepArgs pa;
+				if (fusedPrep) {
+					memcpy(pa.xp.v, Xvect, ((size_t) c->n1 + 1) * sizeof(double));
+					pa.piCk = c->d_sigmaPiCk; pa.SP = c->SP; pa.n1c = c->n1c; pa.CCols = c->d_CCols;
+					pa.bCk = c->d_bCk; pa.bFeas = c->d_bFeas; pa.bTermStart = c->d_bTermStart; pa.tSigma = c->d_tSigma;
+					pa.sigmaPib = c->d_sigmaPib; pa.sigmaLam = c->d_sigmaLam;
+					pa.split = pi_eval_flag != 0; pa.cutoff = sd_window_cutoff(numSamples, pi_eval_flag != 0);
 				}
+				const size_t xs = (size_t) std::max(1, c->n1c) * 8;
+#define SD_RC_LAUNCH(RBV) do { if (fusedPrep) k_sweep_recompute<RBV, true><<<grid, SD_SWEEP_THREADS, xs, c->stream>>>(r, pa); \
+		else k_sweep_recompute<RBV, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r, 0); } while (0)
+				switch (c->Rb) {
+				case 1: SD_RC_LAUNCH(1); break;
+				case 2: SD_RC_LAUNCH(2); break;
+				case 3: SD_RC_LAUNCH(3); break;
+				case 4: SD_RC_LAUNCH(4); break;
+				case 5: SD_RC_LAUNCH(5); break;
+				case 6: SD_RC_LAUNCH(6); break;
+				case 7: SD_RC_LAUNCH(7); break;
+				default: SD_RC_LAUNCH(8); break;
+				}
+#undef SD_RC_LAUNCH
 				c->stats.last_sweep_variant = 5;
 			}
 			else {
@@ -1667,6 +1730,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 				if (useGrp && sd_group_sort(c)) return SDGPU_ERR;
 			}
 			if (useGrp) {
+				if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
 				SweepGrpArgs g;
 				g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
 				g.entBasis = c->d_entBasis; g.entRow = c->d_entRow;
@@ -1688,12 +1752,23 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 			const bool useTma = tmaOk && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N * (1 + c->Q) >= tmaFrom));
 			c->stats.last_sweep_variant = useTma ? 2 : 1;
 			if (useTma) {
-				if (c->Q == 0 ? sd_launch_tma(c, grid, a) : sd_launch_tma_q(c, grid, a)) return SDGPU_ERR;
+if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
+								if (c->Q == 0 ? sd_launch_tma(c, grid, a) : sd_launch_tma_q(c, grid, a)) return SDGPU_ERR;
 			}
-			else if (c->Q > 0 && hasMask) k_sweep_ldg<true, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
-			else if (c->Q > 0)       k_sweep_ldg<true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
-			else if (hasMask)        k_sweep_ldg<false, true><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
-			else                     k_sweep_ldg<false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a);
+			else if (c->Q > 0 && hasMask) k_sweep_ldg<true, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+			else if (c->Q > 0)       k_sweep_ldg<true, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+			else if (hasMask)        k_sweep_ldg<false, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+			else if (!fusedPrep)     k_sweep_ldg<false, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+			else if (!willLdg) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
+			else {
+				SweepPrepArgs pa;
+				memcpy(pa.xp.v, Xvect, ((size_t) c->n1 + 1) * sizeof(double));
+				pa.piCk = c->d_sigmaPiCk; pa.SP = c->SP; pa.n1c = c->n1c; pa.CCols = c->d_CCols;
+				pa.bCk = c->d_bCk; pa.bFeas = c->d_bFeas; pa.bTermStart = c->d_bTermStart; pa.tSigma = c->d_tSigma;
+				pa.sigmaPib = c->d_sigmaPib; pa.sigmaLam = c->d_sigmaLam;
+				pa.split = pi_eval_flag != 0; pa.cutoff = sd_window_cutoff(numSamples, pi_eval_flag != 0);
+				k_sweep_ldg<false, false, true><<<grid, SD_SWEEP_THREADS, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(a, pa);
+			}
 			}
 			}
 		}
