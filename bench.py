@@ -83,7 +83,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.first = index, [], None, 0
 
     def start(self):
         try:
@@ -97,13 +97,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        self.first = len(self.lines)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        timed = self.lines[self.first:] if len(self.lines) > self.first else self.lines
+        for ln in timed:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -324,11 +328,12 @@ def gpu_arm(args):
             raise RuntimeError(f"sd_cut failed ({st}): {api.error()}")
 
     # ---- value: K cuts over resident tables, CUDA events on the library's stream -------------------------------
-    for s in range(args.warmup):
-        one_cut(s, cut_dev)
     sampler = ClockSampler(local)
+    sampler.start()                                            # nvidia-smi takes a while to come up (longer with 8 GPUs): start it before the warm-up,
+    for s in range(args.warmup):                               # count only the samples taken inside the timed regions
+        one_cut(s, cut_dev)
     barrier()
-    sampler.start()
+    sampler.mark()
     l0 = t.stats()["total_launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
