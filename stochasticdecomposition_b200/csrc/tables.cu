@@ -517,6 +517,10 @@ int sd_sync_state(sdgpu_ctx *c) {
 	SD_CUDA(cudaStreamSynchronize(c->stream));          // the commit kernels already published the state into h_state
 	c->omegaCnt = c->h_state->omegaCnt; c->lambdaCnt = c->h_state->lambdaCnt;
 	c->sigmaCnt = c->h_state->sigmaCnt;
+	// sigma -> lambda row mirror of the grouped sweep: a sigma appended by the call that just finished is mirrored for free (the
+	// published state names it); anything else (bulk loads) is read back on demand by sd_refresh_host_lam
+	if (c->h_state->newSigma && c->h_state->lambdaIdx >= 0 && c->h_state->sigmaIdx == (int) c->hostLam.size() && (int64_t) c->hostLam.size() < c->sigmaCnt)
+		c->hostLam.push_back(c->h_state->lambdaIdx);
 	if (c->h_state->overflow) {
 		SD_CUDA(cudaMemsetAsync(&c->d_state->overflow, 0, sizeof(int), c->stream));
 		c->h_state->overflow = 0;
