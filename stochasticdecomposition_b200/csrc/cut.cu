@@ -1620,6 +1620,144 @@ static int sd_group_sort(sdgpu_ctx *c) {
 	return 0;
 }
 
+// ---- which sweep kernel, on which grid ----------------------------------------------------------------------------------------
+// One decision, taken once per cut from the problem's shape, the table sizes and the measured crossovers (profiles/):
+//   random cost (mask and / or multi-term bases)   term-linear TMA ring from ~4M (term, observation) pairs (multi-term: 60 us against
+//                                                  139 us already at 6 000 x 5 000) resp. ~50M pairs (single-term with a mask: the LDG
+//                                                  kernel wins at 5 000 x 5 000, 49 against 57 us); else per-term gathers / masked LDG
+//   RHS-only, Rb <= 4 (5 from 128M pairs)           recompute sweep (16 384 x 131 072: Rb = 1 / 3 / 4 / 5 / 6 -> 2.23 / 1.34 / 1.15 / 1.09 /
+//                                                  0.84e12 pairs/s against 0.90e12 streaming)
+//   RHS-only, >= 128M pairs                         TMA ring; grouped by lambda row when at least 15 % of the row copies go away
+//   random T elements, >= 4M elements               TMA ring with 1+Q planes per row
+//   everything smaller                             LDG streaming (5 000 x 5 000: 34 against 39 us for the ring)
+// sdgpu_set_sweep_variant: 1 forces the load-based kernels, 2 the TMA rings, 3 the recompute sweep, 4 the grouped ring (each where
+// the problem's shape allows it).  Tiny RHS-only cuts on the LDG / recompute kernels skip k_cut_prep (fused prologue).
+enum SdSweepKind { SD_SW_LDG, SD_SW_TMA, SD_SW_TMA_Q, SD_SW_GENERAL, SD_SW_TMA_GEN, SD_SW_RECOMPUTE, SD_SW_TMA_GRP };
+
+struct SdSweepPlan {
+	SdSweepKind kind; int variantId;          // variantId: what sdgpu_stats.last_sweep_variant reports
+	int chunkSize, nChunks;
+	int genRps, genStages;                    // ring shape of k_sweep_tma_gen
+	bool fusedPrep;                           // the sweep CTAs compute their own descriptors: no k_cut_prep launch
+	bool prepAllPiCbarX, prepTerms;           // what k_cut_prep has to produce beyond the per-basis descriptors
+};
+
+static int sd_plan_sweep(sdgpu_ctx *c, int N, int tiles, SdSweepPlan *p) {
+	const int v = c->sweepVariant;
+	const bool multiTerm = c->maxPhiLen > 0, hasMask = c->rvd > 0;
+	const int64_t pairs = (int64_t) c->basisCnt * N, big = (int64_t) 128 << 20;
+	p->genRps = p->genStages = 0; p->fusedPrep = p->prepAllPiCbarX = p->prepTerms = false;
+	sd_pick_chunks(c, tiles, &p->chunkSize, &p->nChunks);
+	if (hasMask || multiTerm) {
+		const bool genFits = hasMask && sd_tma_gen_shape(c, &p->genRps, &p->genStages);
+		const int64_t genFrom = multiTerm ? ((int64_t) 4 << 20) : ((int64_t) 48 << 20);
+		if (genFits && (v == 2 || (v == 0 && (int64_t) c->termCnt * N * (1 + c->Q) >= genFrom))) { p->kind = SD_SW_TMA_GEN; p->variantId = 4; p->prepTerms = true; }
+		else if (multiTerm) { p->kind = SD_SW_GENERAL; p->variantId = 3; p->prepAllPiCbarX = true; }
+		else { p->kind = SD_SW_LDG; p->variantId = 1; }
+		return 0;
+	}
+	if (c->Q == 0) {
+		const bool rcOk = c->Rb >= 1 && c->Rb <= 8;
+		if (rcOk && (v == 3 || (v == 0 && (c->Rb <= SD_RC_AUTO_MAX || (c->Rb == SD_RC_AUTO_MAX + 1 && pairs >= big))))) { p->kind = SD_SW_RECOMPUTE; p->variantId = 5; }
+		else if (c->basisCnt < (1 << 26) && (v == 4 || (v == 0 && pairs >= big))) {
+			if (sd_group_count(c)) return SDGPU_ERR;
+			if (v == 4 || c->grpDistinct * 100 <= c->basisCnt * 85) { p->kind = SD_SW_TMA_GRP; p->variantId = 6; }
+			else { p->kind = SD_SW_TMA; p->variantId = 2; }
+		}
+		else if (v == 2 || (v == 0 && pairs >= big)) { p->kind = SD_SW_TMA; p->variantId = 2; }
+		else { p->kind = SD_SW_LDG; p->variantId = 1; }
+		// one CTA per SM at most: the fused kernels need ~128 registers (1 000 x 1 000: cut 44 -> 38 us; at 5 000 x 5 000, 440 CTAs, fusing loses 11 us)
+		p->fusedPrep = (p->kind == SD_SW_LDG || p->kind == SD_SW_RECOMPUTE) && c->n1 + 1 <= 256 && c->n1c <= 1024 && (int64_t) tiles * p->nChunks <= 148;
+		return 0;
+	}
+	const bool tmaOk = (1 + c->Q) * TMA_ROW_BYTES <= 48 * 1024;                      // one dual row (all planes) must fit a ring stage
+	if (tmaOk && (v == 2 || (v == 0 && pairs * (1 + c->Q) >= ((int64_t) 4 << 20)))) { p->kind = SD_SW_TMA_Q; p->variantId = 2; }
+	else { p->kind = SD_SW_LDG; p->variantId = 1; }
+	return 0;
+}
+
+static SweepPrepArgs sd_fused_prep_args(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag) {
+	SweepPrepArgs pa;
+	memcpy(pa.xp.v, Xvect, ((size_t) c->n1 + 1) * sizeof(double));
+	pa.piCk = c->d_sigmaPiCk; pa.SP = c->SP; pa.n1c = c->n1c; pa.CCols = c->d_CCols;
+	pa.bCk = c->d_bCk; pa.bFeas = c->d_bFeas; pa.bTermStart = c->d_bTermStart; pa.tSigma = c->d_tSigma;
+	pa.sigmaPib = c->d_sigmaPib; pa.sigmaLam = c->d_sigmaLam;
+	pa.split = pi_eval_flag != 0; pa.cutoff = sd_window_cutoff(numSamples, pi_eval_flag != 0);
+	return pa;
+}
+
+static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const double *Xvect, int numSamples, int pi_eval_flag) {
+	const dim3 grid((unsigned) tiles, (unsigned) p.nChunks);
+	const size_t xs = (size_t) std::max(1, c->n1c) * 8;          // dynamic shared memory of the fused-prologue instantiations
+	switch (p.kind) {
+	case SD_SW_TMA_GEN: {
+		SweepTGArgs g;
+		g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
+		g.termA = c->d_termA; g.termC = c->d_termC; g.termRow = c->d_termRow; g.termMeta = c->d_termMeta; g.termBasis = c->d_termBasis;
+		g.bTermStart = c->d_bTermStart;
+		g.omegaCost = c->d_omega + (size_t) c->rvOffset[2] * c->NP; g.NP = c->NP; g.nCost = c->numRV - c->rvOffset[2];
+		g.basisCnt = (int) c->basisCnt; g.chunkSize = p.chunkSize; g.nChunks = p.nChunks;
+		g.mask = c->d_mask; g.Bcap = c->caps.maxBasis; g.x = c->d_x; g.rvCOmCols = c->d_rvCOmCols;
+		g.partV = c->d_partV; g.partI = c->d_partI; g.rps = p.genRps; g.stages = p.genStages;
+		const size_t smem = sd_tma_gen_smem(c, p.genRps, p.genStages);
+		if (smem > c->tmaGenAttr) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaGenAttr = smem; }
+		k_sweep_tma_gen<<<grid, TMA_THREADS, smem, c->stream>>>(g);
+		return 0;
+	}
+	case SD_SW_GENERAL:
+		k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, p.chunkSize, p.nChunks));
+		return 0;
+	case SD_SW_RECOMPUTE: {
+		SweepRcArgs r;
+		r.omega = c->d_omega; r.NP = c->NP; r.lambda = c->d_lambda; r.LP = c->LP; r.bLamPos = c->d_bLamPos;
+		r.descA = c->d_descA; r.descC = c->d_descC; r.descRow = c->d_descRow; r.descWin = c->d_descWin;
+		r.basisCnt = (int) c->basisCnt; r.chunkSize = p.chunkSize; r.nChunks = p.nChunks; r.partV = c->d_partV; r.partI = c->d_partI;
+		SweepPrepArgs pa;
+		if (p.fusedPrep) pa = sd_fused_prep_args(c, Xvect, numSamples, pi_eval_flag);
+#define SD_RC_LAUNCH(RBV) do { if (p.fusedPrep) k_sweep_recompute<RBV, true><<<grid, SD_SWEEP_THREADS, xs, c->stream>>>(r, pa); \
+		else k_sweep_recompute<RBV, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r, 0); } while (0)
+		switch (c->Rb) {
+		case 1: SD_RC_LAUNCH(1); break;
+		case 2: SD_RC_LAUNCH(2); break;
+		case 3: SD_RC_LAUNCH(3); break;
+		case 4: SD_RC_LAUNCH(4); break;
+		case 5: SD_RC_LAUNCH(5); break;
+		case 6: SD_RC_LAUNCH(6); break;
+		case 7: SD_RC_LAUNCH(7); break;
+		default: SD_RC_LAUNCH(8); break;
+		}
+#undef SD_RC_LAUNCH
+		return 0;
+	}
+	case SD_SW_TMA_GRP: {
+		SweepGrpArgs g;
+		g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
+		g.entBasis = c->d_entBasis; g.entRow = c->d_entRow;
+		g.basisCnt = (int) c->basisCnt; g.chunkSize = p.chunkSize; g.nChunks = p.nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
+		const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + 2 * sizeof(int));
+		if (!c->tmaAttrSet[7]) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaAttrSet[7] = true; }
+		k_sweep_tma_grp<<<grid, TMA_THREADS, smem, c->stream>>>(g);
+		return 0;
+	}
+	default: break;
+	}
+	SweepArgs a;
+	a.delta = c->d_delta; a.Dcap = c->caps.maxLambda; a.Q = c->Q;
+	a.descA = c->d_descA; a.descC = c->d_descC; a.descRow = c->d_descRow; a.descWin = c->d_descWin;
+	a.basisCnt = (int) c->basisCnt; a.chunkSize = p.chunkSize; a.nChunks = p.nChunks;
+	a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
+	a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
+	if (p.kind == SD_SW_TMA) return sd_launch_tma(c, grid, a);
+	if (p.kind == SD_SW_TMA_Q) return sd_launch_tma_q(c, grid, a);
+	const bool hasMask = c->rvd > 0;
+	if (c->Q > 0 && hasMask) k_sweep_ldg<true, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+	else if (c->Q > 0)       k_sweep_ldg<true, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+	else if (hasMask)        k_sweep_ldg<false, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+	else if (!p.fusedPrep)   k_sweep_ldg<false, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
+	else                     k_sweep_ldg<false, false, true><<<grid, SD_SWEEP_THREADS, xs, c->stream>>>(a, sd_fused_prep_args(c, Xvect, numSamples, pi_eval_flag));
+	return 0;
+}
+
 static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, bool fuseNormalise) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
 	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
@@ -1633,145 +1771,16 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 	c->lastOmegaCnt = N;
 	c->cutFused = false;
 	if (N > 0 && c->basisCnt > 0) {
-		const bool multiTerm = c->maxPhiLen > 0;
-		// random-cost problems (mask and/or multi-term bases): the term-linear TMA ring from ~4M (term, observation) pairs up
-		int genRps = 0, genStages = 0;
-		const bool genFits = c->rvd > 0 && sd_tma_gen_shape(c, &genRps, &genStages);
-		// (measured, profiles/r01_variant_bench.jsonl: multi-term bases 60 us against 139 us for the gather kernel already at 6 000 x 5 000;
-		// single-term bases with a mask: the LDG kernel wins at 5 000 x 5 000 (49 against 57 us), the ring from ~50M pairs up (170 against 283 us at 6 144 x 16 384))
-		const int64_t genFrom = multiTerm ? ((int64_t) 4 << 20) : ((int64_t) 48 << 20);
-		const bool useGenTma = genFits && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->termCnt * N * (1 + c->Q) >= genFrom));
-		int chunkSize = 1, nChunks = 1;
-		sd_pick_chunks(c, tiles, &chunkSize, &nChunks);
-		dim3 grid((unsigned) tiles, (unsigned) nChunks);
-		// tiny RHS-only cuts (the first thousand iterations of a real problem): no separate prologue launch, the sweep CTAs compute their own
-		// descriptors.  One CTA per SM at most: the fused kernels need ~128 registers (measured: 1 000 x 1 000 cut 44 -> 38 us; at
-		// 5 000 x 5 000, 440 CTAs, fusing loses 11 us).  The two predicates mirror the kernel choice below.
-		const int64_t pairs = (int64_t) c->basisCnt * N;
-		const bool plainShape = !multiTerm && c->Q == 0 && c->rvd == 0;
-		const bool willRc = plainShape && c->Rb >= 1 && c->Rb <= 8 && (c->sweepVariant == 3 || (c->sweepVariant == 0 &&
-				(c->Rb <= SD_RC_AUTO_MAX || (c->Rb == SD_RC_AUTO_MAX + 1 && pairs >= ((int64_t) 128 << 20)))));
-		const bool willLdg = plainShape && !willRc && (c->sweepVariant == 1 || (c->sweepVariant == 0 && pairs < ((int64_t) 128 << 20)));
-		const bool fusedPrep = (willRc || willLdg) && c->n1 + 1 <= 256 && c->n1c <= 1024 && (int64_t) tiles * nChunks <= 148;
-		if (!fusedPrep && sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, multiTerm && !useGenTma, useGenTma)) return SDGPU_ERR;
+		SdSweepPlan plan;
+		if (sd_plan_sweep(c, N, tiles, &plan)) return SDGPU_ERR;
+		const int nChunks = plan.nChunks;
+		if (!plan.fusedPrep && sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval_flag != 0), pi_eval_flag != 0, plan.prepAllPiCbarX, plan.prepTerms)) return SDGPU_ERR;
+		if (plan.kind == SD_SW_TMA_GRP && sd_group_sort(c)) return SDGPU_ERR;      // (host-side; before the sweep's start event)
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
-		bool lexMerge = false;
-		int64_t sweepRows = c->termCnt;                    // delta rows the sweep has to read (one per term; one per distinct lambda when grouped)
-		if (useGenTma) {
-			if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
-			SweepTGArgs g;
-			g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
-			g.termA = c->d_termA; g.termC = c->d_termC; g.termRow = c->d_termRow; g.termMeta = c->d_termMeta; g.termBasis = c->d_termBasis;
-			g.bTermStart = c->d_bTermStart;
-			g.omegaCost = c->d_omega + (size_t) c->rvOffset[2] * c->NP; g.NP = c->NP; g.nCost = c->numRV - c->rvOffset[2];
-			g.basisCnt = (int) c->basisCnt; g.chunkSize = chunkSize; g.nChunks = nChunks;
-			g.mask = c->d_mask; g.Bcap = c->caps.maxBasis; g.x = c->d_x; g.rvCOmCols = c->d_rvCOmCols;
-			g.partV = c->d_partV; g.partI = c->d_partI; g.rps = genRps; g.stages = genStages;
-			const size_t smem = sd_tma_gen_smem(c, genRps, genStages);
-			if (smem > c->tmaGenAttr) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaGenAttr = smem; }
-			k_sweep_tma_gen<<<grid, TMA_THREADS, smem, c->stream>>>(g);
-			c->stats.last_sweep_variant = 4;
-		}
-		else if (multiTerm) {
-			if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
-			k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, chunkSize, nChunks));
-			c->stats.last_sweep_variant = 3;
-		}
-		else {
-			SweepArgs a;
-			a.delta = c->d_delta; a.Dcap = c->caps.maxLambda; a.Q = c->Q;
-			a.descA = c->d_descA; a.descC = c->d_descC; a.descRow = c->d_descRow; a.descWin = c->d_descWin;
-			a.basisCnt = (int) c->basisCnt; a.chunkSize = chunkSize; a.nChunks = nChunks;
-			a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
-			a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
-			const bool hasMask = c->rvd > 0;
-			// very few random right-hand sides: recompute delta.pib from the factors instead of streaming it (FP64-pipe bound, no HBM stream).
-			// Measured (profiles/r01_recompute.jsonl) against the streaming kernels at 16 384 x 131 072; automatic up to SD_RC_AUTO_MAX.
-			const bool rcOk = c->Q == 0 && !hasMask && c->Rb >= 1 && c->Rb <= 8;
-			// 16 384 x 131 072: Rb = 1 / 3 / 4 / 5 / 6 -> 2.23 / 1.34 / 1.15 / 1.09 / 0.84e12 pairs/s against 0.90e12 streaming; 5 000 x 5 000: Rb <= 4 wins, 5 ties
-			const bool useRc = rcOk && (c->sweepVariant == 3 || (c->sweepVariant == 0 && (c->Rb <= SD_RC_AUTO_MAX ||
-					(c->Rb == SD_RC_AUTO_MAX + 1 && (int64_t) c->basisCnt * N >= ((int64_t) 128 << 20)))));
-			if (useRc) {
-				SweepRcArgs r;
-				r.omega = c->d_omega; r.NP = c->NP; r.lambda = c->d_lambda; r.LP = c->LP; r.bLamPos = c->d_bLamPos;
-				r.descA = c->d_descA; r.descC = c->d_descC; r.descRow = c->d_descRow; r.descWin = c->d_descWin;
-				r.basisCnt = (int) c->basisCnt; r.chunkSize = chunkSize; r.nChunks = nChunks; r.partV = c->d_partV; r.partI = c->d_partI;
-				SweepPrepArgs pa;
-				if (fusedPrep) {
-					memcpy(pa.xp.v, Xvect, ((size_t) c->n1 + 1) * sizeof(double));
-					pa.piCk = c->d_sigmaPiCk; pa.SP = c->SP; pa.n1c = c->n1c; pa.CCols = c->d_CCols;
-					pa.bCk = c->d_bCk; pa.bFeas = c->d_bFeas; pa.bTermStart = c->d_bTermStart; pa.tSigma = c->d_tSigma;
-					pa.sigmaPib = c->d_sigmaPib; pa.sigmaLam = c->d_sigmaLam;
-					pa.split = pi_eval_flag != 0; pa.cutoff = sd_window_cutoff(numSamples, pi_eval_flag != 0);
-				}
-				const size_t xs = (size_t) std::max(1, c->n1c) * 8;
-#define SD_RC_LAUNCH(RBV) do { if (fusedPrep) k_sweep_recompute<RBV, true><<<grid, SD_SWEEP_THREADS, xs, c->stream>>>(r, pa); \
-		else k_sweep_recompute<RBV, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r, 0); } while (0)
-				switch (c->Rb) {
-				case 1: SD_RC_LAUNCH(1); break;
-				case 2: SD_RC_LAUNCH(2); break;
-				case 3: SD_RC_LAUNCH(3); break;
-				case 4: SD_RC_LAUNCH(4); break;
-				case 5: SD_RC_LAUNCH(5); break;
-				case 6: SD_RC_LAUNCH(6); break;
-				case 7: SD_RC_LAUNCH(7); break;
-				default: SD_RC_LAUNCH(8); break;
-				}
-#undef SD_RC_LAUNCH
-				c->stats.last_sweep_variant = 5;
-			}
-			else {
-			// several bases on one lambda row: walk the bases grouped by row and read each row once per stage (k_sweep_tma_grp) when at
-			// least 15 % of the row copies go away (variant 4 forces it)
-			bool useGrp = false;
-			if (c->Q == 0 && !hasMask && c->basisCnt < (1 << 26) && (c->sweepVariant == 4 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N >= ((int64_t) 128 << 20)))) {
-				if (sd_group_count(c)) return SDGPU_ERR;
-				useGrp = c->sweepVariant == 4 || c->grpDistinct * 100 <= c->basisCnt * 85;
-				if (useGrp && sd_group_sort(c)) return SDGPU_ERR;
-			}
-			if (useGrp) {
-				if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
-				SweepGrpArgs g;
-				g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
-				g.entBasis = c->d_entBasis; g.entRow = c->d_entRow;
-				g.basisCnt = (int) c->basisCnt; g.chunkSize = chunkSize; g.nChunks = nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
-				const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + 2 * sizeof(int));
-				if (!c->tmaAttrSet[7]) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaAttrSet[7] = true; }
-				if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));          // (the host-side grouping above is not part of the sweep time)
-				k_sweep_tma_grp<<<grid, TMA_THREADS, smem, c->stream>>>(g);
-				c->stats.last_sweep_variant = 6;
-				lexMerge = true;
-				sweepRows = c->grpDistinct;
-			}
-			else {
-			// variant 0 = automatic (tools/tma_check.py, profiles/r01_tma_check.jsonl): RHS-only, the LDG kernel wins up to ~100M pairs
-			// (5 000 x 5 000: 34 against 39 us), the two are level at 16 384 x 16 384 and the TMA ring wins beyond (7.31 against 7.02 TB/s
-			// at 65 536 x 131 072); with random T elements the ring wins from ~4M elements up
-			const bool tmaOk = !hasMask && (1 + c->Q) * TMA_ROW_BYTES <= 48 * 1024;      // one dual row (all planes) must fit a ring stage
-			const int64_t tmaFrom = c->Q == 0 ? ((int64_t) 128 << 20) : ((int64_t) 4 << 20);
-			const bool useTma = tmaOk && (c->sweepVariant == 2 || (c->sweepVariant == 0 && (int64_t) c->basisCnt * N * (1 + c->Q) >= tmaFrom));
-			c->stats.last_sweep_variant = useTma ? 2 : 1;
-			if (useTma) {
-if (fusedPrep) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
-								if (c->Q == 0 ? sd_launch_tma(c, grid, a) : sd_launch_tma_q(c, grid, a)) return SDGPU_ERR;
-			}
-			else if (c->Q > 0 && hasMask) k_sweep_ldg<true, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-			else if (c->Q > 0)       k_sweep_ldg<true, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-			else if (hasMask)        k_sweep_ldg<false, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-			else if (!fusedPrep)     k_sweep_ldg<false, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-			else if (!willLdg) return sdgpu_fail("internal: fused prologue chosen for a sweep that needs k_cut_prep");
-			else {
-				SweepPrepArgs pa;
-				memcpy(pa.xp.v, Xvect, ((size_t) c->n1 + 1) * sizeof(double));
-				pa.piCk = c->d_sigmaPiCk; pa.SP = c->SP; pa.n1c = c->n1c; pa.CCols = c->d_CCols;
-				pa.bCk = c->d_bCk; pa.bFeas = c->d_bFeas; pa.bTermStart = c->d_bTermStart; pa.tSigma = c->d_tSigma;
-				pa.sigmaPib = c->d_sigmaPib; pa.sigmaLam = c->d_sigmaLam;
-				pa.split = pi_eval_flag != 0; pa.cutoff = sd_window_cutoff(numSamples, pi_eval_flag != 0);
-				k_sweep_ldg<false, false, true><<<grid, SD_SWEEP_THREADS, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(a, pa);
-			}
-			}
-			}
-		}
+		if (sd_launch_sweep(c, plan, tiles, Xvect, numSamples, pi_eval_flag)) return SDGPU_ERR;
+		c->stats.last_sweep_variant = plan.variantId;
+		const bool lexMerge = plan.kind == SD_SW_TMA_GRP;
+		const int64_t sweepRows = plan.kind == SD_SW_TMA_GRP ? c->grpDistinct : c->termCnt;   // delta rows the sweep reads: one per term, one per distinct lambda when grouped
 		sd_count_launch(c);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evD, c->stream));
 		// algorithmic bytes of the sweep: delta stream + per-observation weight and iStar + per-basis descriptors
