@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
 
 
-def _run(api, path):
+def _run(api, path, sweep_variant=None):
     g = np.load(path)
     pk = {k: int(v) for k, v in zip(g["pk_keys"], g["pk_vals"])}
     prob = make_problem(int(g["problem_seed"]), **pk)
@@ -25,7 +25,7 @@ def _run(api, path):
     trace = Trace(g["observ"], g["duals"], g["mubBar"], g["xs"], g["two_solves"],
                   g["phi"] if "phi" in g else None, g["phi_omega"] if "phi_omega" in g else None)
     n = 2 * K * (1 + phi_len) + 2
-    rec = replay(api, prob, trace, Caps(n, n, 2 * K + 2, K + 1, 1 + phi_len), **rk)
+    rec = replay(api, prob, trace, Caps(n, n, 2 * K + 2, K + 1, 1 + phi_len), sweep_variant=sweep_variant, **rk)
     return g, rec
 
 
@@ -64,10 +64,13 @@ def test_oracle_reproduces_reference_vectors(path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=["auto", "loads", "tma_rings", "recompute", "grouped"])
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
-def test_cuda_reproduces_reference_vectors(path):
+def test_cuda_reproduces_reference_vectors(path, variant):
+    """Every sweep family against the vectors the reference build produced (a forced family falls back to the load-based kernels
+    where the problem's shape rules it out, e.g. the recompute sweep with random T elements)."""
     import stochasticdecomposition_b200 as sd
-    g, rec = _run(sd.load_library(), path)
+    g, rec = _run(sd.load_library(), path, sweep_variant=variant)
     _check(g, rec, exact=False)
 
 
