@@ -20,6 +20,22 @@ def feas_mask(b: int, o: int, density: float = 0.85) -> bool:
     return (h % 1000) < int(density * 1000)
 
 
+class ForcedVariant:
+    """A bound library whose new contexts are switched to one sweep family (sdgpu_set_sweep_variant: 1 loads, 2 TMA rings,
+    3 recompute, 4 grouped ring; a family the problem's shape rules out falls back to the load-based kernels)."""
+
+    def __init__(self, api, variant):
+        self._api, self._variant = api, variant
+
+    def create(self, *args, **kwargs):
+        t = self._api.create(*args, **kwargs)
+        t.set_sweep_variant(self._variant)
+        return t
+
+    def __getattr__(self, name):
+        return getattr(self._api, name)
+
+
 @dataclass
 class Record:
     omega_idx: list = field(default_factory=list)

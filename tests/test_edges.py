@@ -4,6 +4,7 @@ import pytest
 
 import edge_cases
 import oracle_loader
+from replay import ForcedVariant
 
 
 @pytest.mark.skipif(not oracle_loader.have_reference(), reason="reference build unavailable")
@@ -14,26 +15,11 @@ def test_port_matches_reference(name):
     edge_cases.same(f(oracle_loader.reference()), f(oracle_loader.oracle()), exact=name != "two_contexts" or True)
 
 
-class _ForcedVariant:
-    """The bound library with every new context switched to one sweep family (sdgpu_set_sweep_variant)."""
-
-    def __init__(self, api, variant):
-        self._api, self._variant = api, variant
-
-    def create(self, *args, **kwargs):
-        t = self._api.create(*args, **kwargs)
-        t.set_sweep_variant(self._variant)
-        return t
-
-    def __getattr__(self, name):
-        return getattr(self._api, name)
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", [0, 2, 3, 4], ids=["auto", "tma_rings", "recompute", "grouped"])
 @pytest.mark.parametrize("name", sorted(edge_cases.CASES))
 def test_cuda_matches_port(name, variant):
     import stochasticdecomposition_b200 as sd
     f = edge_cases.CASES[name]
-    api = sd.load_library() if variant == 0 else _ForcedVariant(sd.load_library(), variant)
+    api = sd.load_library() if variant == 0 else ForcedVariant(sd.load_library(), variant)
     edge_cases.same(f(oracle_loader.oracle()), f(api), exact=False)

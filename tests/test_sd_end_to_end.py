@@ -58,6 +58,16 @@ def test_cuda_and_port_agree_over_a_whole_run(shape, K):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape,K,variant", [("ssn", 80, 2), ("20term_T", 80, 2), ("randcost_small", 100, 2), ("20term", 80, 4), ("pgp2", 150, 1)])
+def test_cuda_sweep_families_agree_over_a_whole_run(shape, K, variant):
+    """The same lock-step run with one sweep family forced: the TMA rings (plain, random T, term-linear random cost), the grouped
+    ring, the load-based kernels where the default would recompute."""
+    import stochasticdecomposition_b200 as sd
+    from replay import ForcedVariant
+    _lockstep([ForcedVariant(sd.load_library(), variant), oracle_loader.oracle()], shape, K, rtol=1e-9)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("shape,K", [("pgp2", 300), ("20term_T", 100), ("ssn", 100)])
 def test_independent_runs_reach_the_same_incumbent(shape, K):
     import stochasticdecomposition_b200 as sd
