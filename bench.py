@@ -381,7 +381,6 @@ def gpu_arm(args):
         dist.all_reduce(mt, op=dist.ReduceOp.MAX)
         e2e_s = float(mt.item())
     cnt = t.counts()
-    e2e_pairs = cnt["basis"] * cnt["omega"] * world          # tables grew by one per iteration; use the final size (upper bound within 0.01 %)
     e2e_value = (nb * N * world) / (e2e_s / args.steps)
     h2d = 8 * (prob.numRV + 1) + 8 * (prob.rows + 1) + 8 * (prob.prevCols + 1)
     d2h = 8 * (prob.prevCols + 4) + 4 * cnt["omega"] + 64
