@@ -36,7 +36,7 @@ def run(D, N, g, reps=8, R=40, n1=63):
     x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
     out = {"lambda_rows": D, "bases": g * D, "observations": N}
     cuts = {}
-    for name, v in (("ldg", 1), ("tma", 2), ("auto", 0)):
+    for name, v in (("ldg", 1), ("tma", 2), ("auto", 0), ("grouped", 4)):
         t.set_sweep_variant(v)
         cuts[name] = t.sd_cut(x, k, 1, 0.0)
         ms = []
@@ -45,10 +45,11 @@ def run(D, N, g, reps=8, R=40, n1=63):
             ms.append(t.stats()["last_sweep_ms"])
         m = float(np.median(ms))
         out[f"{name}_variant"] = t.stats()["last_sweep_variant"]
+        out[f"{name}_cut_ms"] = round(t.stats()["last_cut_ms"], 4)
         out[f"{name}_sweep_ms"] = round(m, 4)
         out[f"{name}_pairs_per_s"] = float(f"{g * D * N / (m * 1e-3):.4g}")
         out[f"{name}_GBps_per_distinct_row"] = round(8.0 * D * N / (m * 1e-3) / 1e9, 1)
-    for a in ("ldg", "tma"):
+    for a in ("ldg", "tma", "grouped"):
         assert np.array_equal(cuts[a].iStar, cuts["auto"].iStar) and cuts[a].alpha == cuts["auto"].alpha
     out["identical"] = True
     t.close()
@@ -56,5 +57,6 @@ def run(D, N, g, reps=8, R=40, n1=63):
 
 
 if __name__ == "__main__":
-    for g in (1, 2, 4, 8):
-        print(json.dumps(run(4096, 131072, g)), flush=True)
+    shapes = [(int(a), int(b), int(c)) for a, b, c in (x.split("x") for x in sys.argv[1:])] or [(4096, 131072, g) for g in (1, 2, 4, 8)]
+    for D, N, g in shapes:
+        print(json.dumps(run(D, N, g)), flush=True)
