@@ -29,8 +29,12 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_line_reduced_size():
-    d = _one_json_line(["--duals", "4096", "--obs-per-gpu", "16384", "--rv", "32", "--steps", "5", "--warmup", "3", "--cpu-duals", "256", "--cpu-obs", "1024"])
-    assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks"} <= set(d)
+    d = _one_json_line(["--duals", "4096", "--obs-per-gpu", "16384", "--rv", "32", "--steps", "5", "--warmup", "3", "--cpu-duals", "256", "--cpu-obs", "1024",
+                        "--sd-iterations", "40"])
+    assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks", "sd_iterations_ssn"} <= set(d)
+    it = d["sd_iterations_ssn"]
+    assert "unavailable" not in it, it
+    assert it["iterations"] == 40 and it["gpu_tables_it_per_s"] > 0 and it["cpu_tables_it_per_s"] > 0 and it["same_incumbent_estimate"] is True
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["achieved"] > 0
     assert d["gpu_launches"] == 3 * d["steps"]                       # prep, sweep, merge per cut
