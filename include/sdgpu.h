@@ -284,6 +284,10 @@ int  sdgpu_set_sweep_variant(sdgpu_ctx *ctx, int variant);
 /* host-only: the 2-D sweep grid (observation tiles x basis chunks) the library would launch for a table of this shape on a
  * GPU with smCount SMs -- the wave-aware chunk count of DESIGN.md section 4; needs no device */
 int  sdgpu_plan_sweep_grid(int smCount, int64_t observations, int64_t bases, int maxChunks, int *tiles, int *chunkSize, int *nChunks);
+/* host-only: the sweep family (the value sdgpu_stats.last_sweep_variant would report) the library picks for a problem of this
+ * shape and these table sizes under sdgpu_set_sweep_variant(variant), and whether the cut skips the separate prologue launch */
+int  sdgpu_plan_sweep_kind(int rvCOmCnt, int rvdOmCnt, int rvbOmCnt, int maxPhiLength, int costColumns, int n1, int n1c,
+                           int64_t bases, int64_t terms, int64_t distinctLambdaRows, int64_t observations, int variant, int *fusedPrologue);
 /* run subsequent work on an existing CUDA stream (cudaStream_t) instead of the context's own */
 int  sdgpu_set_stream(sdgpu_ctx *ctx, void *cudaStream);
 

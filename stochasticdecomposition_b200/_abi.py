@@ -231,6 +231,7 @@ class Api:
             "get_stats": (i, [vp, C.POINTER(CStats)]),
             "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]),
             "plan_sweep_grid": (i, [i, i64, i64, i, c_intp, c_intp, c_intp]),
+            "plan_sweep_kind": (i, [i, i, i, i, i, i, i, i64, i64, i64, i64, i, c_intp]),
         }
         for name, (res, args) in table.items():
             fn = self._fn(name)
@@ -243,6 +244,16 @@ class Api:
         if self._fn("plan_sweep_grid")(sm_count, observations, bases, max_chunks, C.byref(t), C.byref(cs), C.byref(nc)) != 0:
             raise SdError(self.error())
         return t.value, cs.value, nc.value
+
+    def plan_sweep_kind(self, observations, bases, Q=0, rvd=0, Rb=10, max_phi=0, cost_cols=0, n1=10, n1c=10, terms=None,
+                        distinct_rows=None, variant=0):
+        """(sweep family id as in stats()["last_sweep_variant"], fused prologue?) for this shape; host-only."""
+        fused = C.c_int(0)
+        k = self._fn("plan_sweep_kind")(Q, rvd, Rb, max_phi, cost_cols, n1, n1c, bases, bases if terms is None else terms,
+                                        bases if distinct_rows is None else distinct_rows, observations, variant, C.byref(fused))
+        if k < 0:
+            raise SdError(self.error())
+        return k, bool(fused.value)
 
     def error(self) -> str:
         fn = self._fn("last_error")

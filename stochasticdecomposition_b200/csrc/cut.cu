@@ -1676,6 +1676,22 @@ static int sd_plan_sweep(sdgpu_ctx *c, int N, int tiles, SdSweepPlan *p) {
 	return 0;
 }
 
+// host-only view of the kernel choice (no device needed): which sweep family the library would run for a problem of this shape
+extern "C" int sdgpu_plan_sweep_kind(int rvCOmCnt, int rvdOmCnt, int rvbOmCnt, int maxPhiLength, int costColumns, int n1, int n1c,
+		int64_t bases, int64_t terms, int64_t distinctLambdaRows, int64_t observations, int variant, int *fusedPrologue) {
+	if (bases <= 0 || observations <= 0 || terms < bases || variant < 0 || variant > 4) return sdgpu_fail("plan_sweep_kind: bad argument");
+	sdgpu_ctx tmp;
+	tmp.Q = rvCOmCnt; tmp.rvd = rvdOmCnt; tmp.Rb = rvbOmCnt; tmp.maxPhiLen = maxPhiLength; tmp.n1 = n1; tmp.n1c = n1c;
+	tmp.numRV = costColumns; tmp.rvOffset[2] = 0;                    // only the difference (the number of cost columns) matters here
+	tmp.basisCnt = bases; tmp.termCnt = terms; tmp.sweepVariant = variant; tmp.maxChunks = SD_MAX_CHUNKS;
+	tmp.grpCounted = bases; tmp.grpDistinct = distinctLambdaRows;    // the count the library keeps incrementally
+	SdSweepPlan plan;
+	const int tiles = (int) ((observations + SD_TILE_W - 1) / SD_TILE_W);
+	if (sd_plan_sweep(&tmp, (int) observations, tiles, &plan)) return SDGPU_ERR;
+	if (fusedPrologue) *fusedPrologue = plan.fusedPrep ? 1 : 0;
+	return plan.variantId;
+}
+
 static SweepPrepArgs sd_fused_prep_args(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag) {
 	SweepPrepArgs pa;
 	memcpy(pa.xp.v, Xvect, ((size_t) c->n1 + 1) * sizeof(double));

@@ -87,3 +87,27 @@ def test_sweep_grid_plan_is_wave_aware():
     # the two cases that motivated the rule: 256 tiles must not get 7 chunks (4.04 waves); 10 tiles get one full wave, not 1.44
     assert api.plan_sweep_grid(148, 131072, 65536, 64)[2] != 7
     assert api.plan_sweep_grid(148, 5000, 5000, 64)[2] == 44
+
+
+def test_sweep_family_plan():
+    """Host-only check of the kernel choice: 1 loads, 2 TMA ring, 3 per-term gathers, 4 term-linear ring,
+    5 recompute, 6 grouped ring; and the fused prologue of tiny cuts."""
+    api = sd.load_library()
+    big, real = (131072, 65536), (5000, 5000)                                   # (observations, bases)
+    assert api.plan_sweep_kind(*big) == (2, False)                              # the bench workload: plain TMA ring
+    assert api.plan_sweep_kind(*real) == (1, False)                             # a late real-problem cut: LDG, separate prologue (440 CTAs)
+    assert api.plan_sweep_kind(1000, 1000) == (1, True)                         # an early one: LDG with the prologue fused
+    assert api.plan_sweep_kind(576, 300, Rb=3, n1=4, n1c=4) == (5, True)        # pgp2: recompute, fused
+    assert api.plan_sweep_kind(*big, Rb=3) == (5, False) and api.plan_sweep_kind(*big, Rb=5) == (5, False)
+    assert api.plan_sweep_kind(*real, Rb=5)[0] == 1 and api.plan_sweep_kind(*big, Rb=6)[0] == 2
+    assert api.plan_sweep_kind(*big, distinct_rows=30000)[0] == 6               # several bases per lambda row: grouped ring
+    assert api.plan_sweep_kind(*big, distinct_rows=60000)[0] == 2               # less than 15 % to gain: plain ring
+    assert api.plan_sweep_kind(*real, distinct_rows=2500)[0] == 1               # below L2 size grouping buys nothing
+    assert api.plan_sweep_kind(*real, Q=8)[0] == 2 and api.plan_sweep_kind(300, 300, Q=2)[0] == 1
+    rc = dict(rvd=4, cost_cols=4)
+    assert api.plan_sweep_kind(5000, 2000, max_phi=2, terms=6000, **rc)[0] == 4          # multi-term: the ring from ~4M pairs
+    assert api.plan_sweep_kind(300, 200, max_phi=2, terms=600, **rc)[0] == 3
+    assert api.plan_sweep_kind(*real, **rc)[0] == 1 and api.plan_sweep_kind(65536, 6144, **rc)[0] == 4   # mask only: LDG until ~50M pairs
+    assert api.plan_sweep_kind(5000, 2000, max_phi=2, terms=6000, rvd=40, cost_cols=60)[0] == 3          # cost block does not fit shared memory
+    for v, want in ((1, 1), (2, 2), (3, 1), (4, 6)):                            # forced families (3: Rb = 10 rules the recompute sweep out)
+        assert api.plan_sweep_kind(*real, variant=v)[0] == want
