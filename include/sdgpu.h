@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SDGPU_ABI_VERSION 1
+#define SDGPU_ABI_VERSION 2
 #define SDGPU_NONE (-1)
 #define SDGPU_ERR  (-2)
 
@@ -212,6 +212,10 @@ int  sdgpu_nccl_init(sdgpu_ctx *ctx, int nranks, int rank, const void *id128); /
  * sdgpu_peer_export fills handle64 (64 bytes, cudaIpcMemHandle_t); handles = nranks x 64 bytes in rank order. */
 int  sdgpu_peer_export(sdgpu_ctx *ctx, int nranks, void *handle64);
 int  sdgpu_peer_attach(sdgpu_ctx *ctx, int nranks, int rank, const void *handles);
+/* Which exchange sdgpu_sd_cut() uses when both an NCCL communicator and a peer exchange are attached (the two may be attached in either
+ * order and are torn down independently): 0 = automatic (the peer exchange if attached, else NCCL), 1 = NCCL, 2 = peer exchange.
+ * All ranks must choose the same one for a given cut. */
+int  sdgpu_set_collective(sdgpu_ctx *ctx, int mode);
 
 /* ---- one host thread, several GPUs (the reference's host is a single process) -------------------------------------------
  * A group owns one context per device of this process.  Observations are dealt round-robin (global observation o lives on
@@ -270,8 +274,12 @@ typedef struct {
 	int64_t last_cut_launches;  /* kernels launched by the most recent sd_cut                           */
 	int64_t total_launches;     /* kernels launched since create                                        */
 	int64_t last_sweep_bytes;   /* algorithmic bytes of the most recent sweep    */
-	int64_t last_sweep_variant; /* 1 = LDG streaming, 2 = TMA bulk ring, 3 = per-term gathers (random cost), 4 = term-linear TMA ring (random cost),
-	                             * 5 = recompute from (lambda, omega), no delta stream (Rb <= 8), 6 = TMA ring over bases grouped by lambda row */
+	int64_t last_sweep_variant; /* 1 = LDG streaming, 2 = bulk-copy (UBLKCP) ring, 3 = per-term gathers (random cost), 4 = term-linear bulk-copy ring
+	                             * (random cost), 5 = recompute from (lambda, omega), no delta stream (Rb <= 8), 6 = bulk-copy ring over bases grouped by lambda row */
+	/* ABI 2: the split of last_cut_ms (same events; all zero unless sdgpu_set_timing is on) */
+	double  last_prep_ms;       /* prologue: piCbarX + basis descriptors (0 when fused into the sweep)            */
+	double  last_merge_ms;      /* merge + accumulate kernel (includes the NVLink peer exchange when that is the collective) */
+	double  last_collective_ms; /* everything after the merge kernel: NCCL all-reduce + normalise, iStar copy    */
 } sdgpu_stats;
 int  sdgpu_get_stats(sdgpu_ctx *ctx, sdgpu_stats *out);
 /* CUDA-event timing of the cut (last_cut_ms / last_sweep_ms) costs four event records per cut; off by default. */

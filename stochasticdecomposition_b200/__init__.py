@@ -29,7 +29,7 @@ def load_library(path: str | None = None) -> Api:
         raise SdError(f"{p} not found: build it with `python -m stochasticdecomposition_b200.build` "
                       "(nvcc, sm_100a).  There is no CPU fallback.")
     api = Api(ctypes.CDLL(p), "sdgpu_")
-    if api._fn("abi_version")() != 1:
+    if api._fn("abi_version")() != 2:
         raise SdError("libsdgpu.so ABI version mismatch")
     if path is None:
         _api = api

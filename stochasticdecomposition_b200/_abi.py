@@ -59,7 +59,8 @@ class CCut(C.Structure):
 
 class CStats(C.Structure):
     _fields_ = [("last_cut_ms", C.c_double), ("last_sweep_ms", C.c_double), ("last_cut_launches", C.c_int64),
-                ("total_launches", C.c_int64), ("last_sweep_bytes", C.c_int64), ("last_sweep_variant", C.c_int64)]
+                ("total_launches", C.c_int64), ("last_sweep_bytes", C.c_int64), ("last_sweep_variant", C.c_int64),
+                ("last_prep_ms", C.c_double), ("last_merge_ms", C.c_double), ("last_collective_ms", C.c_double)]
 
 
 def _i32(a) -> np.ndarray:
@@ -229,7 +230,7 @@ class Api:
             "group_sd_cut": (i, [vp, c_f64p, i, i, d, C.POINTER(CCut)]),
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
             "get_stats": (i, [vp, C.POINTER(CStats)]),
-            "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]),
+            "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]), "set_collective": (i, [vp, i]),
             "plan_sweep_grid": (i, [i, i64, i64, i, c_intp, c_intp, c_intp]),
             "plan_sweep_kind": (i, [i, i, i, i, i, i, i, i64, i64, i64, i64, i, c_intp]),
         }
@@ -292,6 +293,10 @@ class Group:
         if self.h:
             self.api._fn("group_destroy")(self.h)
             self.h = None
+
+    def reset(self):
+        """cleanCellType (setup.c:242-246) for every member: counts to zero, memory and the peer exchange kept"""
+        self._ok(self.api._fn("group_reset")(self.h), "reset")
 
     def counts(self):
         c = CCounts()
@@ -596,6 +601,10 @@ class Tables:
 
     def set_sweep_variant(self, v: int):
         self._check(self._call("set_sweep_variant", v), "set_sweep_variant")
+
+    def set_collective(self, mode: int):
+        """0 automatic (peer exchange if attached, else NCCL), 1 NCCL, 2 NVLink peer exchange"""
+        self._check(self._call("set_collective", mode), "set_collective")
 
     # -- the reference's stochasticUpdates, minus the CPLEX calls ----------------------------------------
     def stochastic_updates(self, omegaIdx, newOmegaFlag, piDet, mubBar, currentIter, tol, feasFlag=True,

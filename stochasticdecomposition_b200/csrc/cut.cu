@@ -1257,6 +1257,7 @@ struct ReformArgs {
 	const int32_t *bTermStart, *tSigma, *tOmega;
 	int n1, lbType, lb; const int32_t *CCols, *qCols;
 	double *out;        // [rep][cut][n1+2]: alpha, beta[0..n1]
+	int basisCnt; int *errFlag;   // bounds checks on host-supplied observ[] / iStar[] (1: negative observation index, 2: iStar outside the basis list)
 };
 
 #define RF_CHUNK 4096
@@ -1284,8 +1285,10 @@ __global__ void __launch_bounds__(512) k_reform(ReformArgs a) {
 		for (int i = tid; i < cn; i += blockDim.x) {
 			const int o = observ[n0 + i];
 			int is = -1;
-			if (o < oc) {                                                   // optimal.c:205
+			if (o < 0) atomicExch(a.errFlag, 1);                            // (the reference would read out of bounds here)
+			else if (o < oc) {                                              // optimal.c:205
 				is = iStar[o];
+				if (is < 0 || is >= a.basisCnt) { atomicExch(a.errFlag, 2); is = -1; s_o[i] = o; s_b[i] = is; continue; }
 				const double *cellBase = a.delta + (size_t) (o / SD_TILE_W) * a.Dcap * rowStride + (o % SD_TILE_W);
 				for (int t = a.bTermStart[is]; t < a.bTermStart[is + 1]; t++) {
 					const int sg = a.tSigma[t], l = a.sigmaLam[sg];
@@ -1413,10 +1416,12 @@ static int sd_launch_prep(sdgpu_ctx *c, const double *X, int cutoff, int split, 
 		xDevIn = c->d_x;
 	}
 	const int64_t n = std::max<int64_t>(std::max<int64_t>(c->basisCnt, wantAllPiCbarX ? c->sigmaCnt : 0), 1);
+	if (sd_smem_optin(c, k_cut_prep, SD_SMEM_PREP, 0, (size_t) std::max(1, c->n1c) * 8, "k_cut_prep")) return SDGPU_ERR;
 	k_cut_prep<<<sd_blocks(n, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(xp, xDevIn, c->d_x, c->n1, c->d_sigmaPiCk, c->SP, c->n1c,
 			c->d_CCols, (int) c->sigmaCnt, wantAllPiCbarX ? c->d_piCbarX : nullptr, c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma,
 			c->d_sigmaPib, c->d_sigmaLam, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin,
 			c->d_tOmega, wantTerms ? c->d_termA : nullptr, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis);
+	SD_LAUNCH_OK("k_cut_prep");
 	sd_count_launch(c);
 	return 0;
 }
@@ -1794,6 +1799,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		if (plan.kind == SD_SW_TMA_GRP && sd_group_sort(c)) return SDGPU_ERR;      // (host-side; before the sweep's start event)
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evC, c->stream));
 		if (sd_launch_sweep(c, plan, tiles, Xvect, numSamples, pi_eval_flag)) return SDGPU_ERR;
+		SD_LAUNCH_OK("sweep kernel");
 		c->stats.last_sweep_variant = plan.variantId;
 		const bool lexMerge = plan.kind == SD_SW_TMA_GRP;
 		const int64_t sweepRows = plan.kind == SD_SW_TMA_GRP ? c->grpDistinct : c->termCnt;   // delta rows the sweep reads: one per term, one per distinct lambda when grouped
@@ -1814,8 +1820,8 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		m.iStar = c->d_iStar; m.tilePart = c->d_tilePart; m.P = P;
 		m.iStarHost = c->d_iStarHost; m.iStarHostCap = N <= c->iStarHostCap ? N : 0;
 		m.n1 = c->n1; m.CCols = c->d_CCols; m.qCols = c->rvd > 0 ? c->d_rvCOmCols : c->d_rvCols;       // cuts.c:157 vs :167
-		const bool peer = c->peerRanks > 1;
-		m.partial = c->d_cutPartial; m.fuseNormalise = (peer || c->ncclComm == nullptr) && fuseNormalise; m.numSamples = numSamples;
+		const bool peer = sd_use_peer(c);
+		m.partial = c->d_cutPartial; m.fuseNormalise = (peer || !sd_use_nccl(c)) && fuseNormalise; m.numSamples = numSamples;
 		m.peerRanks = peer ? c->peerRanks : 0; m.peerRank = c->peerRank; m.peerSeq = peer ? ++c->peerSeq : 0;
 		for (int r = 0; r < 16; r++) m.peerBufs[r] = peer && r < c->peerRanks ? c->d_peerBufs[r] : nullptr;
 		m.hostRes = c->d_cutRes; m.st = c->d_state;
@@ -1830,19 +1836,23 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		const int groups = c->n1c > 0 ? MG_THREADS / kp : 1;
 		const int groupsP = MG_THREADS / std::min(((P + 31) / 32) * 32, MG_THREADS);
 		const size_t dyn = (size_t) std::max(std::max(1, groups * c->n1c), (groupsP + 1) * P + c->n1 + 4) * 8;
+		// static: s_istar, s_w (2 x 2 KiB), s_red, s_mv (8 KiB), s_mi (4 KiB)
+		if (sd_smem_optin(c, k_cut_merge, SD_SMEM_MERGE, 17 * 1024, dyn, "k_cut_merge")) return SDGPU_ERR;
 		k_cut_merge<<<(N + mW - 1) / mW, MG_THREADS, dyn, c->stream>>>(m);
+		SD_LAUNCH_OK("k_cut_merge");
 		sd_count_launch(c);
+		if (c->timing) SD_CUDA(cudaEventRecord(c->evE, c->stream));
 	}
 	else {
 		// no observation or no basis at all: nothing to sweep; with observations every one is missing its maximiser (cuts.c:136-139)
-		if (c->timing) { SD_CUDA(cudaEventRecord(c->evC, c->stream)); SD_CUDA(cudaEventRecord(c->evD, c->stream)); }
+		if (c->timing) { SD_CUDA(cudaEventRecord(c->evC, c->stream)); SD_CUDA(cudaEventRecord(c->evD, c->stream)); SD_CUDA(cudaEventRecord(c->evE, c->stream)); }
 		c->stats.last_sweep_bytes = 0;
 		std::vector<double> zero((size_t) c->n1 + 4, 0.0);
 		zero[c->n1 + 3] = (double) N;
 		SD_CUDA(cudaMemcpyAsync(c->d_cutPartial, zero.data(), zero.size() * 8, cudaMemcpyHostToDevice, c->stream));
 		if (N > 0) SD_CUDA(cudaMemsetAsync(c->d_iStar, 0xff, (size_t) N * 4, c->stream));
 		SD_CUDA(cudaStreamSynchronize(c->stream));
-		if (c->peerRanks > 1) {                      // the other ranks exchange inside their merge kernel: take part, with zero sums
+		if (sd_use_peer(c)) {                        // the other ranks exchange inside their merge kernel: take part, with zero sums
 			MergeArgs m;
 			memset(&m, 0, sizeof m);
 			m.n1 = c->n1; m.partial = c->d_cutPartial; m.fuseNormalise = fuseNormalise; m.numSamples = numSamples; m.hostRes = c->d_cutRes;
@@ -1854,6 +1864,26 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		}
 	}
 	c->stats.last_cut_launches = c->stats.total_launches - launches0;
+	return 0;
+}
+
+// A rank that cannot form its part of a cut still has to take part in the peer exchange the other ranks are waiting in: it
+// contributes zero sums and an error marker in the `missing` slot, which makes sdgpu_sd_cut_finish fail on every rank.
+int sd_peer_poison_cut(sdgpu_ctx *c) {
+	if (!sd_use_peer(c)) return 0;
+	SD_CUDA(cudaSetDevice(c->device));
+	std::vector<double> v((size_t) c->n1 + 4, 0.0);
+	v[c->n1 + 3] = 3.0e9;
+	SD_CUDA(cudaMemcpyAsync(c->d_cutPartial, v.data(), v.size() * 8, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaStreamSynchronize(c->stream));
+	MergeArgs m;
+	memset(&m, 0, sizeof m);
+	m.n1 = c->n1; m.partial = c->d_cutPartial; m.fuseNormalise = 1; m.numSamples = 1; m.hostRes = c->d_cutRes;
+	m.peerRanks = c->peerRanks; m.peerRank = c->peerRank; m.peerSeq = ++c->peerSeq;
+	for (int r = 0; r < c->peerRanks; r++) m.peerBufs[r] = c->d_peerBufs[r];
+	k_cut_exchange<<<1, 128, ((size_t) c->n1 + 4) * 8, c->stream>>>(m);
+	sd_count_launch(c);
+	c->cutFused = true;
 	return 0;
 }
 
@@ -1888,11 +1918,15 @@ extern "C" int sdgpu_sd_cut_finish(sdgpu_ctx *c, int numSamples, sdgpu_cut *cut)
 		float ms = 0.f;
 		if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->stats.last_cut_ms = ms;
 		if (cudaEventElapsedTime(&ms, c->evC, c->evD) == cudaSuccess) c->stats.last_sweep_ms = ms;
+		if (cudaEventElapsedTime(&ms, c->evA, c->evC) == cudaSuccess) c->stats.last_prep_ms = ms;
+		if (cudaEventElapsedTime(&ms, c->evD, c->evE) == cudaSuccess) c->stats.last_merge_ms = ms;
+		if (cudaEventElapsedTime(&ms, c->evE, c->evB) == cudaSuccess) c->stats.last_collective_ms = ms;
 	}
 	c->stats.last_cut_launches += c->stats.total_launches - launches0;
 	cut->omegaCnt = c->lastOmegaCnt; cut->numSamples = numSamples;
 	cut->cummOld = h[c->n1 + 1]; cut->cummAll = h[c->n1 + 2];
 	const double missing = h[c->n1 + 3];
+	if (missing >= 3.0e9 && c->peerRanks > 1) return sdgpu_fail("sd_cut: a peer rank failed to form its part of this cut");
 	if (missing >= 2.0e9 && c->peerRanks > 1) return sdgpu_fail("sd_cut: peer exchange timed out (a rank did not reach this cut)");
 	if (missing >= 1.0e9) return sdgpu_fail("sd_cut: iStar used as a sigma index is out of range (cuts.c:161)");
 	if (missing > 0.0) { sdgpu_fail("sd_cut: failed to identify maximal Pi for %g observation(s)", missing); return SDGPU_NONE; }
@@ -1906,7 +1940,7 @@ extern "C" int sdgpu_sd_cut(sdgpu_ctx *c, const double *Xvect, int numSamples, i
 	if (!cut || !cut->beta) return sdgpu_fail("null argument");
 	int rc = sd_cut_partial_impl(c, Xvect, numSamples, pi_eval_flag, lb, true);
 	if (rc != 0) return rc;
-	if (c->ncclComm && !c->cutFused) {              // (with a peer exchange attached the merge kernel has already reduced)
+	if (sd_use_nccl(c) && !c->cutFused) {           // (with the peer exchange selected the merge kernel has already reduced)
 		rc = sd_nccl_allreduce(c, c->d_cutPartial, c->n1 + 4);
 		if (rc != 0) return rc;
 	}
@@ -2015,14 +2049,17 @@ extern "C" int sdgpu_reform_cuts_batch(sdgpu_ctx *c, int nCuts, const int32_t *i
 	// one block of growable device scratch: [out doubles][observ ints][omegaCnt ints][iStar ints] -- no allocation per call
 	const size_t outBytes = (size_t) nReps * nCuts * nOut * 8, obBytes = (size_t) nReps * k * 4, ocBytes = (((size_t) nCuts * 4) + 7) / 8 * 8;
 	const size_t isBytes = iStar ? (size_t) nCuts * std::max(1, istarStride) * 4 : 0;
-	if (sd_scratch_reserve(c, outBytes + (obBytes + 7) / 8 * 8 + ocBytes + isBytes)) return SDGPU_ERR;
+	const size_t scratchTotal = outBytes + (obBytes + 7) / 8 * 8 + ocBytes + (isBytes + 7) / 8 * 8 + 8;
+	if (sd_scratch_reserve(c, scratchTotal)) return SDGPU_ERR;
 	double *d_out = reinterpret_cast<double *>(c->d_scratch);
 	int32_t *d_ob = reinterpret_cast<int32_t *>(c->d_scratch + outBytes);
 	int32_t *d_oc = reinterpret_cast<int32_t *>(c->d_scratch + outBytes + (obBytes + 7) / 8 * 8);
 	int32_t *d_is = iStar ? reinterpret_cast<int32_t *>(c->d_scratch + outBytes + (obBytes + 7) / 8 * 8 + ocBytes) : nullptr;
-	cudaMemcpyAsync(d_ob, observ, (size_t) nReps * k * 4, cudaMemcpyHostToDevice, c->stream);
-	cudaMemcpyAsync(d_oc, oc.data(), (size_t) nCuts * 4, cudaMemcpyHostToDevice, c->stream);
-	if (iStar) cudaMemcpyAsync(d_is, iStar, (size_t) nCuts * istarStride * 4, cudaMemcpyHostToDevice, c->stream);
+	SD_CUDA(cudaMemcpyAsync(d_ob, observ, (size_t) nReps * k * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(d_oc, oc.data(), (size_t) nCuts * 4, cudaMemcpyHostToDevice, c->stream));
+	if (iStar) SD_CUDA(cudaMemcpyAsync(d_is, iStar, (size_t) nCuts * istarStride * 4, cudaMemcpyHostToDevice, c->stream));
+	int *d_err = reinterpret_cast<int *>(c->d_scratch + scratchTotal - 8);      // bounds-check flag of k_reform, at the end of the scratch block
+	SD_CUDA(cudaMemsetAsync(d_err, 0, 4, c->stream));
 	ReformArgs a;
 	a.iStar = iStar ? d_is : c->d_iStar; a.istarStride = istarStride; a.omegaCnt = d_oc; a.nCuts = nCuts; a.observ = d_ob; a.k = k;
 	a.omega = c->d_omega; a.NP = c->NP; a.rvOffset2 = c->rvOffset[2];
@@ -2030,16 +2067,22 @@ extern "C" int sdgpu_reform_cuts_batch(sdgpu_ctx *c, int nCuts, const int32_t *i
 	a.sigmaPib = c->d_sigmaPib; a.sigmaPiCr = c->d_sigmaPiCr; a.sigmaLam = c->d_sigmaLam; a.n1c = c->n1c; a.n1cP = c->n1cP;
 	a.bTermStart = c->d_bTermStart; a.tSigma = c->d_tSigma; a.tOmega = c->d_tOmega;
 	a.n1 = c->n1; a.lbType = lbType; a.lb = lb; a.CCols = c->d_CCols; a.qCols = c->d_rvCOmCols;      // optimal.c:220 scatters with rvCOmCols
-	a.out = d_out;
+	a.out = d_out; a.basisCnt = (int) c->basisCnt; a.errFlag = d_err;
 	const int nc = c->n1c + c->Q, kp = ((std::max(nc, 1) + 31) / 32) * 32, groups = std::max(1, 512 / kp);
 	const size_t dyn = ((size_t) groups * std::max(nc, 1) + 2 + nc + c->n1 + 1) * 8;
 	if (nc > 512) { return sdgpu_fail("reform_cuts_batch: more than 512 cut columns is not supported"); }
+	if (sd_smem_optin(c, k_reform, SD_SMEM_REFORM, (size_t) 2 * RF_CHUNK * 4 + 512, dyn, "k_reform")) return SDGPU_ERR;
 	k_reform<<<dim3((unsigned) nCuts, (unsigned) nReps), 512, dyn, c->stream>>>(a);
+	SD_LAUNCH_OK("k_reform");
 	sd_count_launch(c);
 	std::vector<double> h((size_t) nReps * nCuts * nOut);
-	cudaMemcpyAsync(h.data(), d_out, h.size() * 8, cudaMemcpyDeviceToHost, c->stream);
+	int hErr = 0;
+	SD_CUDA(cudaMemcpyAsync(h.data(), d_out, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+	SD_CUDA(cudaMemcpyAsync(&hErr, d_err, 4, cudaMemcpyDeviceToHost, c->stream));
 	cudaError_t e = cudaStreamSynchronize(c->stream);
 	if (e != cudaSuccess) return sdgpu_fail("reform_cuts_batch: %s", cudaGetErrorString(e));
+	if (hErr == 1) return sdgpu_fail("reform_cuts_batch: observ[] holds a negative observation index");
+	if (hErr == 2) return sdgpu_fail("reform_cuts_batch: iStar[] names a basis outside 0..%lld", (long long) c->basisCnt - 1);
 	for (size_t i = 0; i < (size_t) nReps * nCuts; i++) {
 		alpha[i] = h[i * nOut];
 		memcpy(beta + i * (c->n1 + 1), h.data() + i * nOut + 1, ((size_t) c->n1 + 1) * 8);
@@ -2071,13 +2114,14 @@ extern "C" int sdgpu_feas_cuts(sdgpu_ctx *c, int obsFirst, int obsLast, int basi
 	if (sd_scratch_reserve(c, outBytes + (size_t) 2 * n * 4)) return SDGPU_ERR;
 	double *d_o = reinterpret_cast<double *>(c->d_scratch);
 	int32_t *d_p = reinterpret_cast<int32_t *>(c->d_scratch + outBytes);
-	cudaMemcpyAsync(d_p, po.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
-	cudaMemcpyAsync(d_p + n, pb.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
+	SD_CUDA(cudaMemcpyAsync(d_p, po.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
+	SD_CUDA(cudaMemcpyAsync(d_p + n, pb.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
 	k_feas_cuts<<<sd_blocks(n, 128), 128, 0, c->stream>>>(n, d_p, d_p + n, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaPiCr, c->d_sigmaLam,
 			c->n1c, c->n1cP, c->d_delta, c->caps.maxLambda, c->Q, c->d_CCols, c->d_rvCols, c->n1, d_o, d_o + n);
+	SD_LAUNCH_OK("k_feas_cuts");
 	sd_count_launch(c);
-	cudaMemcpyAsync(alpha, d_o, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream);
-	cudaMemcpyAsync(beta, d_o + n, (size_t) n * n1p * 8, cudaMemcpyDeviceToHost, c->stream);
+	SD_CUDA(cudaMemcpyAsync(alpha, d_o, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream));
+	SD_CUDA(cudaMemcpyAsync(beta, d_o + n, (size_t) n * n1p * 8, cudaMemcpyDeviceToHost, c->stream));
 	cudaError_t e = cudaStreamSynchronize(c->stream);
 	if (e != cudaSuccess) return sdgpu_fail("feas_cuts: %s", cudaGetErrorString(e));
 	return n;

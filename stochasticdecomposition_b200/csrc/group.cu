@@ -3,6 +3,7 @@
 // observation shards, the replicated dual-side tables and the peer-memory exchange are exactly those of the
 // one-process-per-GPU path (sharding.py); only the plumbing differs (direct peer pointers instead of CUDA IPC).
 #include <cstring>
+#include <string>
 #include <vector>
 #include <algorithm>
 
@@ -44,7 +45,8 @@ extern "C" int sdgpu_group_create(const sdgpu_problem *prob, const sdgpu_caps *c
 extern "C" int sdgpu_group_reset(sdgpu_group *g) {
 	if (!g) return sdgpu_fail("null group");
 	for (sdgpu_ctx *c : g->m) if (sdgpu_reset(c) != 0) return SDGPU_ERR;
-	for (sdgpu_ctx *c : g->m) c->peerSeq = 0;
+	// the exchange sequence number is NOT reset: the flags of the previous replication stay in the exchange buffers, and a
+	// restarted sequence could meet a stale flag of the same value (the in-kernel wait would then read a stale slot)
 	g->totalObs = 0;
 	return 0;
 }
@@ -126,8 +128,18 @@ extern "C" int sdgpu_group_sd_cut(sdgpu_group *g, const double *Xvect, int numSa
 	const int G = (int) g->m.size();
 	if (G == 1) return sdgpu_sd_cut(g->m[0], Xvect, numSamples, pi_eval_flag, lb, cut);
 	// launch every member's cut first (asynchronous: the merge kernels meet in the peer exchange), only then wait for any of them
-	for (int r = 0; r < G; r++)
-		if (sdgpu_sd_cut_partial(g->m[r], Xvect, numSamples, pi_eval_flag, lb) != 0) return SDGPU_ERR;
+	const unsigned seq0 = g->m[0]->peerSeq;
+	int launchRc = 0;
+	for (int r = 0; r < G && launchRc == 0; r++)
+		launchRc = sdgpu_sd_cut_partial(g->m[r], Xvect, numSamples, pi_eval_flag, lb);
+	if (launchRc != 0) {
+		// a member failed to launch: the members already launched wait for it inside their merge kernels.  Every member that has not
+		// taken part in exchange seq0 + 1 does so now with an error marker, so that all sequences stay in step and every kernel ends.
+		const std::string why = g_sdgpu_err;
+		for (int r = 0; r < G; r++) if (g->m[r]->peerSeq == seq0) sd_peer_poison_cut(g->m[r]);
+		for (int r = 0; r < G; r++) { cudaSetDevice(g->m[r]->device); cudaStreamSynchronize(g->m[r]->stream); }
+		return sdgpu_fail("group_sd_cut: a member failed to launch its cut (%s); the exchange was completed with an error marker", why.c_str());
+	}
 	int rc = 0;
 	const int n1 = g->m[0]->n1;
 	std::vector<double> beta((size_t) n1 + 1);

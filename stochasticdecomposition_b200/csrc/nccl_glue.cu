@@ -62,11 +62,25 @@ int sd_nccl_allreduce(sdgpu_ctx *c, double *buf, int n) {
 
 static void sd_peer_release(sdgpu_ctx *c);
 
+// The two exchanges are independent: attaching / replacing the NCCL communicator leaves an attached peer exchange alone (and
+// the other way round); sdgpu_destroy tears both down.
 void sd_nccl_release(sdgpu_ctx *c) {
 	if (c->ncclComm && c->ownComm && g_nccl.commDestroy) g_nccl.commDestroy(c->ncclComm);
 	c->ncclComm = nullptr; c->ownComm = false;
-	sd_peer_release(c);                       // destroy path: also drop the peer mappings and the exported buffer
+}
+
+void sd_peer_teardown(sdgpu_ctx *c) {
+	sd_peer_release(c);
 	if (c->d_peerLocal) { cudaFree(c->d_peerLocal); c->d_peerLocal = nullptr; }
+}
+
+extern "C" int sdgpu_set_collective(sdgpu_ctx *c, int mode) {
+	if (!c) return sdgpu_fail("null context");
+	if (mode < 0 || mode > 2) return sdgpu_fail("set_collective: unknown mode %d", mode);
+	if (mode == 1 && !c->ncclComm) return sdgpu_fail("set_collective: no NCCL communicator attached");
+	if (mode == 2 && c->peerRanks <= 1) return sdgpu_fail("set_collective: no peer exchange attached");
+	c->collective = mode;
+	return 0;
 }
 
 extern "C" int sdgpu_attach_nccl(sdgpu_ctx *c, void *ncclComm) {
@@ -145,7 +159,7 @@ extern "C" int sdgpu_peer_attach(sdgpu_ctx *c, int nranks, int rank, const void 
 		if (e != cudaSuccess) { sd_peer_release(c); return sdgpu_fail("peer_attach: cannot open rank %d's buffer: %s", r, cudaGetErrorString(e)); }
 		c->d_peerBufs[r] = (unsigned char *) p;
 	}
-	c->peerRanks = nranks; c->peerRank = rank; c->peerSeq = 0;
+	c->peerRanks = nranks; c->peerRank = rank; c->peerSeq = 0;        // fresh, zeroed buffers on every rank: the sequence restarts with them
 	return 0;
 }
 

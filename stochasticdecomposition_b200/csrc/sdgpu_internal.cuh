@@ -57,7 +57,7 @@ struct sdgpu_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool ownStream = true;
-	cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
+	cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr, evE = nullptr;   // cut start / end, sweep start / end, merge end
 
 	sdgpu_num num{};
 	sdgpu_caps caps{};
@@ -127,7 +127,7 @@ struct sdgpu_ctx {
 	double  *d_termA = nullptr, *d_termC = nullptr;     // sigma.pib, piCbarX of the term's sigma
 	int32_t *d_termRow = nullptr, *d_termMeta = nullptr, *d_termBasis = nullptr;   // lambda row; window | last-term << 2 | omegaIdx << 8; basis
 	size_t   tmaGenAttr = 0;
-	size_t   lambdaSmemAttr = 0;
+	size_t   smemAttr[12] = {};      // dynamic shared memory opted in per kernel on this context's device (index: SdSmemSlot)
 	double  *d_partV = nullptr;      // [2][chunks][NP] per-chunk running maxima (old, new)
 	int32_t *d_partI = nullptr;      // [2][chunks][NP]
 	int32_t *d_iStar = nullptr;      // [NP]
@@ -165,8 +165,9 @@ struct sdgpu_ctx {
 	unsigned char *d_peerBufs[kMaxPeers] = {};     // every rank's buffer as seen from this device (own entry = d_peerLocal)
 	int      peerRanks = 0, peerRank = -1;
 	bool     peerLocalGroup = false;               // peers are contexts of this process (plain peer pointers, nothing to close)
-	unsigned peerSeq = 0;
+	unsigned peerSeq = 0;                          // monotonic for the life of the exchange buffer (never reset: a stale flag must not match)
 	size_t   peerBytes = 0;
+	int      collective = 0;                       // sdgpu_set_collective: 0 automatic (peer if attached, else NCCL), 1 NCCL, 2 peer
 
 	// NCCL (resolved with dlopen so that the library loads on a box without NCCL)
 	void *ncclComm = nullptr;
@@ -176,6 +177,25 @@ struct sdgpu_ctx {
 };
 
 static inline int64_t sd_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// Kernels whose dynamic shared memory grows with the problem: opt in above 48 KiB (static + dynamic), fail loudly above the 227 KiB
+// a CTA can have on sm_100 -- a rejected launch must not pass for a finished call.
+enum SdSmemSlot { SD_SMEM_OMEGA, SD_SMEM_LAMBDA, SD_SMEM_DELTA_ROW, SD_SMEM_DELTA_COL, SD_SMEM_MERGE, SD_SMEM_REFORM, SD_SMEM_PREP, SD_SMEM_LDG_FUSED,
+                  SD_SMEM_RC_FUSED, SD_SMEM_UPD1, SD_SMEM_UPD2, SD_SMEM_SPARE };
+#define SD_SMEM_LIMIT ((size_t) 227 * 1024)
+template <class K>
+static inline int sd_smem_optin(sdgpu_ctx *c, K kernel, int slot, size_t staticBytes, size_t dynBytes, const char *what) {
+	if (staticBytes + dynBytes > SD_SMEM_LIMIT)
+		return sdgpu_fail("%s needs %zu bytes of shared memory per CTA (limit %zu): problem dimension too large for this build", what, staticBytes + dynBytes, SD_SMEM_LIMIT);
+	if (staticBytes + dynBytes > 48 * 1024 && dynBytes > c->smemAttr[slot]) {
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dynBytes);
+		if (e != cudaSuccess) return sdgpu_fail("%s: cudaFuncSetAttribute(%zu bytes) -> %s", what, dynBytes, cudaGetErrorString(e));
+		c->smemAttr[slot] = dynBytes;
+	}
+	return 0;
+}
+// after a kernel launch: a rejected configuration surfaces here, not at some later synchronisation
+#define SD_LAUNCH_OK(what) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return sdgpu_fail("%s launch -> %s", what, cudaGetErrorString(e_)); } while (0)
 
 // delta element (l, plane q, observation o) in the tiled layout
 __host__ __device__ static inline size_t sd_delta_off(int64_t Dcap, int Q, int64_t l, int q, int64_t o) {
@@ -207,5 +227,10 @@ int sd_aux_reserve(sdgpu_ctx *c, size_t bytes);  // grows h_aux / d_aux (pinned,
 int sd_scratch_reserve(sdgpu_ctx *c, size_t bytes);  // grows d_scratch (device); contents are not preserved
 int sd_sync_state(sdgpu_ctx *c);                 // D2H of SdDevState + stream sync + mirror update
 int sd_nccl_allreduce(sdgpu_ctx *c, double *buf, int n);
-void sd_nccl_release(sdgpu_ctx *c);
+void sd_nccl_release(sdgpu_ctx *c);              // drops the NCCL communicator only
+void sd_peer_teardown(sdgpu_ctx *c);             // closes the peer mappings and frees this rank's exchange buffer
+int  sd_peer_poison_cut(sdgpu_ctx *c);           // takes part in the current peer exchange with an error marker (keeps the sequence in step)
+// which exchange the next cut uses: the peer exchange (true) or NCCL / none (false)
+static inline bool sd_use_peer(const sdgpu_ctx *c) { return c->peerRanks > 1 && (c->collective == 2 || (c->collective == 0)); }
+static inline bool sd_use_nccl(const sdgpu_ctx *c) { return c->ncclComm != nullptr && !sd_use_peer(c) && c->collective != 2; }
 static inline void sd_count_launch(sdgpu_ctx *c, int n = 1) { c->stats.total_launches += n; }

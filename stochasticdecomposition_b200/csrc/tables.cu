@@ -575,7 +575,7 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 #define SD_TRY(x) do { if ((x) != 0) { sdgpu_destroy(c); return SDGPU_ERR; } } while (0)
 	cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
 	if (ce != cudaSuccess) { sdgpu_fail("cudaStreamCreate: %s", cudaGetErrorString(ce)); sdgpu_destroy(c); return SDGPU_ERR; }
-	cudaEventCreate(&c->evA); cudaEventCreate(&c->evB); cudaEventCreate(&c->evC); cudaEventCreate(&c->evD);
+	cudaEventCreate(&c->evA); cudaEventCreate(&c->evB); cudaEventCreate(&c->evC); cudaEventCreate(&c->evD); cudaEventCreate(&c->evE);
 
 	// ---- static maps (host, once) ---------------------------------------------------------------------
 	auto lamPosOfRow = [&](int row) {          // expandVector: the LAST lambda entry written to that row wins
@@ -631,7 +631,7 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	// ---- staging ----------------------------------------------------------------------------------------
 	size_t vecLen = (size_t) std::max(std::max(c->rows, c->numRV), c->n1) + 2;
 	SD_TRY(sd_alloc(&c->d_vecIn, vecLen)); SD_TRY(sd_alloc(&c->d_cand, (size_t) std::max(c->R, c->numRV) + 1)); SD_TRY(sd_alloc(&c->d_candC, (size_t) c->n1cP));
-	c->pinDcap = vecLen + (size_t) c->n1 + 16; c->pinIcap = 64;
+	c->pinDcap = vecLen + (size_t) c->n1 + 16; c->pinIcap = std::max<size_t>(64, 8 + 2 * (size_t) c->caps.maxTerms);   // basis_append stages 5 + 2 (1 + phiLength) ints
 	if (cudaHostAlloc((void **) &c->h_pinD, c->pinDcap * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
 	    cudaHostAlloc((void **) &c->h_pinI, c->pinIcap * sizeof(int32_t), cudaHostAllocMapped) != cudaSuccess ||
 	    cudaHostAlloc((void **) &c->h_state, sizeof(SdDevState), cudaHostAllocMapped) != cudaSuccess ||
@@ -677,6 +677,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	sd_nccl_release(c);
+	sd_peer_teardown(c);
 	void *dev[] = { c->d_CCols, c->d_rvRows, c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_rvCOmCols, c->d_rvCols, c->d_bBarCol,
 		c->d_bBarVal, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->d_omega, c->d_omegaW, c->d_lambda, c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr,
 		c->d_sigmaLam, c->d_sigmaCk, c->d_delta, c->d_mask, c->d_bCk, c->d_bFeas, c->d_bPhiLen, c->d_bTermStart, c->d_tSigma, c->d_tOmega, c->d_state,
@@ -695,6 +696,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	if (c->evB) cudaEventDestroy(c->evB);
 	if (c->evC) cudaEventDestroy(c->evC);
 	if (c->evD) cudaEventDestroy(c->evD);
+	if (c->evE) cudaEventDestroy(c->evE);
 	if (c->stream && c->ownStream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -745,8 +747,10 @@ extern "C" int sdgpu_get_stats(sdgpu_ctx *c, sdgpu_stats *out) {
 static int sd_launch_omega(sdgpu_ctx *c, const double *observ, double tol, int mode, int weight) {
 	if (sd_stage_vec(c, observ, c->numRV + 1)) return SDGPU_ERR;
 	const int blocks = mode == 2 ? 1 : sd_blocks(c->omegaCnt, 256);
+	if (sd_smem_optin(c, k_omega_fused, SD_SMEM_OMEGA, 64, (size_t) std::max(1, c->numRV) * 8, "k_omega_fused")) return SDGPU_ERR;
 	k_omega_fused<<<blocks, 256, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(sd_staged_source(c, c->numRV + 1, mode == 2 ? 0 : c->omegaCnt), c->numRV, c->d_omega, c->d_omegaW, c->NP,
 			c->caps.maxOmega, tol, mode, weight, c->d_state, c->d_hstate);
+	SD_LAUNCH_OK("k_omega_fused");
 	sd_count_launch(c);
 	return sd_sync_state(c);
 }
@@ -813,44 +817,51 @@ extern "C" int sdgpu_omega_append_bulk(sdgpu_ctx *c, int64_t n, const double *va
 
 // ---- lambda / sigma / delta --------------------------------------------------------------------------------
 // calcLambda in one launch; its last block also stages calcSigma's candidate (pibBar, piCBar) from the same vector
-static void sd_launch_lambda(sdgpu_ctx *c, const double *d_pi, double mubBar, double tol, int64_t lambdaUpper, bool publish) {
+static int sd_launch_lambda(sdgpu_ctx *c, const double *d_pi, double mubBar, double tol, int64_t lambdaUpper, bool publish) {
 	const int cbStage = std::min(c->cbNnz, 2048);
 	const size_t smem = ((size_t) std::max(1, c->R) + c->rows + 1 + std::max(1, c->bBarCnt) + std::max(1, cbStage)) * 8;
-	if (smem > 48 * 1024 && smem > c->lambdaSmemAttr) {      // very long dual vectors: opt in to more dynamic shared memory (per device, remembered per context)
-		cudaFuncSetAttribute(k_lambda_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		c->lambdaSmemAttr = smem;
-	}
+	if (sd_smem_optin(c, k_lambda_fused, SD_SMEM_LAMBDA, 64, smem, "k_lambda_fused")) return SDGPU_ERR;   // very long dual vectors: opt in (per device, remembered per context)
 	k_lambda_fused<<<sd_blocks(lambdaUpper, 256), 256, smem, c->stream>>>(d_pi, c->rows, c->d_rvRows, c->R, c->d_lambda, c->LP,
 			c->caps.maxLambda, tol, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->n1c, cbStage,
 			c->d_vecIn, c->d_candC, c->d_state, c->d_hstate, publish ? 1 : 0);
+	SD_LAUNCH_OK("k_lambda_fused");
 	sd_count_launch(c);
+	return 0;
 }
 
-static void sd_launch_sigma(sdgpu_ctx *c, int iter, double tol, int64_t sigmaUpper) {
+static int sd_launch_sigma(sdgpu_ctx *c, int iter, double tol, int64_t sigmaUpper) {
 	k_sigma_fused<<<sd_blocks(sigmaUpper, 256), 256, 0, c->stream>>>(c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr, c->d_sigmaLam, c->d_sigmaCk, c->SP,
 			c->n1c, c->n1cP, c->d_candC, tol, iter, c->caps.maxSigma, c->d_state, c->d_hstate);
+	SD_LAUNCH_OK("k_sigma_fused");
 	sd_count_launch(c);
+	return 0;
 }
 
-static void sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
-	if (omegaUpper <= 0) return;
+static int sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
+	if (omegaUpper <= 0) return 0;
+	if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->R + c->Rb) * 8, "k_delta_row")) return SDGPU_ERR;
 	k_delta_row<<<sd_blocks(omegaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->R + c->Rb) * 8, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
 			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow);
+	SD_LAUNCH_OK("k_delta_row");
 	sd_count_launch(c);
+	return 0;
 }
 
-static void sd_launch_delta_col(sdgpu_ctx *c, int forcedCol, int64_t lambdaUpper) {
-	if (lambdaUpper <= 0) return;
+static int sd_launch_delta_col(sdgpu_ctx *c, int forcedCol, int64_t lambdaUpper) {
+	if (lambdaUpper <= 0) return 0;
+	if (sd_smem_optin(c, k_delta_col, SD_SMEM_DELTA_COL, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, "k_delta_col")) return SDGPU_ERR;
 	k_delta_col<<<sd_blocks(lambdaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
 			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol);
+	SD_LAUNCH_OK("k_delta_col");
 	sd_count_launch(c);
+	return 0;
 }
 
 extern "C" int sdgpu_calc_lambda(sdgpu_ctx *c, const double *Pi, double tol, int *newLambdaFlag) {
 	if (!c || !Pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, Pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), 0.0, tol, c->lambdaCnt, true);
+	if (sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), 0.0, tol, c->lambdaCnt, true)) return SDGPU_ERR;
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
 	return c->h_state->lambdaIdx;
@@ -865,8 +876,9 @@ extern "C" int sdgpu_calc_sigma(sdgpu_ctx *c, const double *pi, double mubBar, i
 	// stand-alone form: stage (pibBar, piCBar) with the caller's lambda index / flag, then scan + commit
 	k_sigma_prepare<<<sd_blocks(c->n1c + 1, 128), 128, 0, c->stream>>>(c->d_pinD, c->d_bBarCol, c->d_bBarVal, c->bBarCnt, mubBar, c->d_cbStart,
 			c->d_cbRow, c->d_cbVal, c->n1c, c->d_candC, c->d_state, newLambdaFlag != 0, idxLambda);
+	SD_LAUNCH_OK("k_sigma_prepare");
 	sd_count_launch(c);
-	sd_launch_sigma(c, currentIter, tol, c->sigmaCnt);
+	if (sd_launch_sigma(c, currentIter, tol, c->sigmaCnt)) return SDGPU_ERR;
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (newSigmaFlag) *newSigmaFlag = c->h_state->newSigma;
 	return c->h_state->sigmaIdx;
@@ -877,11 +889,11 @@ extern "C" int sdgpu_calc_delta(sdgpu_ctx *c, int newOmegaFlag, int elemIdx) {
 	SD_CUDA(cudaSetDevice(c->device));
 	if (newOmegaFlag) {
 		if (elemIdx < 0 || elemIdx >= c->omegaCnt) return sdgpu_fail("calc_delta: observation %d out of range", elemIdx);
-		sd_launch_delta_col(c, elemIdx, c->lambdaCnt);
+		if (sd_launch_delta_col(c, elemIdx, c->lambdaCnt)) return SDGPU_ERR;
 	}
 	else {
 		if (elemIdx < 0 || elemIdx >= c->lambdaCnt) return sdgpu_fail("calc_delta: lambda %d out of range", elemIdx);
-		sd_launch_delta_row(c, elemIdx, c->omegaCnt);
+		if (sd_launch_delta_row(c, elemIdx, c->omegaCnt)) return SDGPU_ERR;
 	}
 	// no host wait: later calls are ordered behind this one on the context's stream (a fault surfaces at the next sync)
 	SD_CUDA(cudaGetLastError());
@@ -893,9 +905,9 @@ extern "C" int sdgpu_update_dual(sdgpu_ctx *c, const double *pi, double mubBar, 
 	if (!c || !pi) return sdgpu_fail("null argument");
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
-	sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), mubBar, tol, c->lambdaCnt, false);   // stocUpdate.c:78 (+ staging of :293-296)
-	sd_launch_sigma(c, currentIter, tol, c->sigmaCnt);                     // :81
-	sd_launch_delta_row(c, -1, c->omegaCnt);                               // :84-85 (kernel no-op unless the lambda was new)
+	if (sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), mubBar, tol, c->lambdaCnt, false)) return SDGPU_ERR;   // stocUpdate.c:78 (+ staging of :293-296)
+	if (sd_launch_sigma(c, currentIter, tol, c->sigmaCnt)) return SDGPU_ERR;                     // :81
+	if (sd_launch_delta_row(c, -1, c->omegaCnt)) return SDGPU_ERR;                               // :84-85 (kernel no-op unless the lambda was new)
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (lambdaIdx) *lambdaIdx = c->h_state->lambdaIdx;
 	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
@@ -945,13 +957,13 @@ extern "C" int sdgpu_update_dual_bulk(sdgpu_ctx *c, int64_t n, const double *pis
 				const double *d_pi = d_pis + (size_t) i * stride;
 				double mb = mubBar ? mubBar[i0 + i] : 0.0;
 				int it = iters ? iters[i0 + i] : (int) (i0 + i + 1);
-				sd_launch_lambda(c, d_pi, mb, tol, c->lambdaCnt + i, false);
-				sd_launch_sigma(c, it, tol, c->sigmaCnt + i);
-				sd_launch_delta_row(c, -1, c->omegaCnt);
+				if (sd_launch_lambda(c, d_pi, mb, tol, c->lambdaCnt + i, false) || sd_launch_sigma(c, it, tol, c->sigmaCnt + i) ||
+				    sd_launch_delta_row(c, -1, c->omegaCnt)) { rc = SDGPU_ERR; break; }
 				k_record_pair<<<1, 1, 0, c->stream>>>(c->d_state, d_li, d_si, i);
 				sd_count_launch(c);
 			}
-			rc = sd_sync_state(c);
+			if (rc == 0) rc = sd_sync_state(c);
+			else cudaStreamSynchronize(c->stream);
 			if (rc == 0 && lambdaIdx) if (cudaMemcpy(lambdaIdx + i0, d_li, (size_t) m * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = sdgpu_fail("copy back failed");
 			if (rc == 0 && sigmaIdx) if (cudaMemcpy(sigmaIdx + i0, d_si, (size_t) m * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = sdgpu_fail("copy back failed");
 		}

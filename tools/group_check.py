@@ -25,24 +25,32 @@ def main():
     trace = make_trace(prob, K, seed=11, dual_pool=20, obs_pool=30)
     n = 2 * K + 2
     grp = Group(sd.load_library(), prob, Caps(n, n, n, K + 1, 1), list(range(G)))
-    cuts = []
-    for it in range(K):
-        k = it + 1
-        oi, onew = grp.calc_omega(trace.observ[it], 1e-3)
-        for sv in ((0, 1) if trace.two_solves[it] else (0,)):
-            grp.stochastic_updates(oi, onew, trace.duals[it, sv], trace.mubBar[it, sv], k, 1e-3)
-            onew = False
-            cuts.append(grp.sd_cut(trace.xs[it, sv], k, pi_eval_flag(k), 0.0))
-    single = replay(oracle_loader.oracle(), prob, trace, Caps(n, n, n, K + 1, 1))
-    assert grp.counts() == single.counts, (grp.counts(), single.counts)
-    assert len(cuts) == len(single.cuts)
-    for c, ref in zip(cuts, single.cuts):
-        assert np.array_equal(c.iStar, ref.iStar)
-        scale = max(abs(ref.alpha), np.abs(ref.beta[1:]).max())
-        assert abs(c.alpha - ref.alpha) <= 1e-9 * abs(ref.alpha) and np.abs(c.beta - ref.beta).max() <= 1e-9 * scale
-        assert abs(c.cummAll - ref.cummAll) <= 1e-9 * max(abs(ref.cummAll), 1e-300)
+    total = 0
+    # three replications through sdgpu_group_reset (setup.c:242-246): the second one forms only two cuts, so that a restarted
+    # exchange sequence would meet the first replication's stale flags (the sequence number is monotonic for that reason)
+    for rep, (Kr, seed) in enumerate(((K, 11), (2, 12), (40, 13))):
+        tr = trace if rep == 0 else make_trace(prob, Kr, seed=seed, dual_pool=20, obs_pool=30)
+        if rep > 0:
+            grp.reset()
+        cuts = []
+        for it in range(Kr):
+            k = it + 1
+            oi, onew = grp.calc_omega(tr.observ[it], 1e-3)
+            for sv in ((0, 1) if tr.two_solves[it] else (0,)):
+                grp.stochastic_updates(oi, onew, tr.duals[it, sv], tr.mubBar[it, sv], k, 1e-3)
+                onew = False
+                cuts.append(grp.sd_cut(tr.xs[it, sv], k, pi_eval_flag(k), 0.0))
+        single = replay(oracle_loader.oracle(), prob, tr, Caps(n, n, n, K + 1, 1))
+        assert grp.counts() == single.counts, (grp.counts(), single.counts)
+        assert len(cuts) == len(single.cuts)
+        for c, ref in zip(cuts, single.cuts):
+            assert np.array_equal(c.iStar, ref.iStar), rep
+            scale = max(abs(ref.alpha), np.abs(ref.beta[1:]).max())
+            assert abs(c.alpha - ref.alpha) <= 1e-9 * abs(ref.alpha) and np.abs(c.beta - ref.beta).max() <= 1e-9 * scale, rep
+            assert abs(c.cummAll - ref.cummAll) <= 1e-9 * max(abs(ref.cummAll), 1e-300), rep
+        total += len(cuts)
     grp.close()
-    print(f"GROUP_OK devices={G} cuts={len(cuts)}", flush=True)
+    print(f"GROUP_OK devices={G} cuts={total} replications=3", flush=True)
 
 
 if __name__ == "__main__":

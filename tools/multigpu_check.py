@@ -29,12 +29,19 @@ def main():
     K = 60
     trace = make_trace(prob, K, seed=11, dual_pool=20, obs_pool=0)
     n = 2 * K + 2
-    for mode in ("library_nccl", "torch", "peer"):
+    for mode in ("library_nccl", "torch", "peer", "peer_then_nccl", "both_pick_nccl"):
         sh = ShardedTables(sd.load_library().create(prob, Caps(n, n, n, K + 1, 1), local), rank, world)
         if mode == "library_nccl":
             sh.attach_library_nccl()
         if mode == "peer":
             sh.attach_peer_exchange()
+        if mode == "peer_then_nccl":                # attaching NCCL afterwards must leave the peer exchange alone (automatic choice: peer)
+            sh.attach_peer_exchange()
+            sh.attach_library_nccl()
+        if mode == "both_pick_nccl":                # both attached, NCCL selected explicitly
+            sh.attach_library_nccl()
+            sh.attach_peer_exchange()
+            sh.t.set_collective(1)
         cuts = []
         for it in range(K):
             k = it + 1
