@@ -25,6 +25,7 @@ typedef struct {
 	coordType    coord;
 	sparseVector bBar;
 	sparseMatrix Cbar;
+	sparseVector dBar;          /* second-stage cost vector, read by calcBasis (randCost.c:70); sdref_set_dbar */
 	sdgpu_caps   caps;
 	iVector      rvdOmCols; char *senx;
 	cellType    *cell;          /* only the fields updtFeasCutPool / addCut2Pool(FEASIBILITY) read */
@@ -337,6 +338,50 @@ int sdref_check_feasibility_basis(void *vc, int b, double tol, uint8_t *flagsOut
 		c->basis->obsFeasible[b][o] = refPairFeasible(c, b, o, tol);
 		if (flagsOut) flagsOut[o] = c->basis->obsFeasible[b][o];
 	}
+	return 0;
+}
+
+/* ---- the reference's own stochasticUpdates (stocUpdate.c:14-133) on a replayed solve ---------------------------------------
+ * Everything before the table arithmetic asks the solver for the basis, the duals and (random cost) rows of the basis inverse:
+ * the replay LP of oracle/shim/solver_cplex.h answers from one recorded solve.  Used by tests/test_host_patch.py as the unpatched
+ * side of the lock step with the patched host (oracle/hooks_driver.c). */
+int sdref_set_dbar(void *vc, int cnt, const int32_t *col, const double *val) {
+	refCtx *c = (refCtx *) vc;
+	c->dBar.cnt = cnt; c->dBar.col = dupInts(col, cnt); c->dBar.val = dupDbls(val, cnt);
+	return 0;
+}
+
+int sdref_stochastic_updates(void *vc, const sdReplayLP *lp, int omegaIdx, int newOmegaFlag, int currentIter, double tol,
+		int subFeasFlag, int *newBasisFlag) {
+	refCtx *c = (refCtx *) vc;
+	probType prob;
+	oneProblem sp;
+	coordType coord = c->coord;
+	bool nb = newBasisFlag ? (*newBasisFlag != 0) : true;
+	int status;
+	memset(&prob, 0, sizeof prob); memset(&sp, 0, sizeof sp);
+	coord.rvdOmCols = c->rvdOmCols;
+	sp.senx = c->senx;
+	prob.num = &c->num; prob.coord = &coord; prob.sp = &sp; prob.bBar = &c->bBar; prob.Cbar = &c->Cbar; prob.dBar = &c->dBar;
+	status = stochasticUpdates(&prob, (LPptr) lp, c->basis, c->lambda, c->sigma, c->delta, (int) c->caps.maxOmega, c->omega, omegaIdx,
+			newOmegaFlag != 0, currentIter, tol, &nb, subFeasFlag != 0);
+	if (newBasisFlag) *newBasisFlag = nb;
+	return status;
+}
+
+/* one record of the host's basis list (stoc.h:72-97); obsFeasible may be NULL, its first omega->cnt entries are copied */
+int sdref_basis_info(void *vc, int b, int *ck, int *weight, int *phiLength, int *feasFlag, double *mubBar, int32_t *sigmaIdx,
+		int32_t *omegaIdx, uint8_t *obsFeasible) {
+	refCtx *c = (refCtx *) vc;
+	oneBasis *B;
+	int i;
+	if (b < 0 || b >= c->basis->cnt) return SDGPU_ERR;
+	B = c->basis->vals[b];
+	*ck = B->ck; *weight = B->weight; *phiLength = B->phiLength; *feasFlag = B->feasFlag; *mubBar = B->mubBar;
+	for (i = 0; i <= B->phiLength; i++) sigmaIdx[i] = B->sigmaIdx[i];
+	for (i = 1; i <= B->phiLength; i++) omegaIdx[i] = B->omegaIdx[i];
+	if (obsFeasible)
+		for (i = 0; i < c->omega->cnt; i++) obsFeasible[i] = c->basis->obsFeasible[b] ? c->basis->obsFeasible[b][i] : 2;
 	return 0;
 }
 

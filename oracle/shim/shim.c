@@ -198,13 +198,45 @@ int randInteger(long long *seed, int range) {
 /* ---- solver / driver entry points the compiled reference files name but the oracle never reaches ---- */
 #define UNREACHABLE(name) do { fprintf(stderr, "sdref shim :: %s() needs CPLEX; not available in the oracle build\n", name); abort(); } while (0)
 
-int    getDual(LPptr lp, dVector pi, int length)            { (void) lp; (void) pi; (void) length; UNREACHABLE("getDual"); return 1; }
-int    getPrimal(LPptr lp, dVector x, int length)           { (void) lp; (void) x; (void) length; UNREACHABLE("getPrimal"); return 1; }
-int    getDualSlacks(LPptr lp, dVector dj, int length)      { (void) lp; (void) dj; (void) length; UNREACHABLE("getDualSlacks"); return 1; }
-int    getBasis(LPptr lp, iVector cstat, iVector rstat)     { (void) lp; (void) cstat; (void) rstat; UNREACHABLE("getBasis"); return 1; }
-int    getBasisHead(LPptr lp, iVector head, dVector x)      { (void) lp; (void) head; (void) x; UNREACHABLE("getBasisHead"); return 1; }
-int    getBasisInvRow(LPptr lp, int i, dVector y)           { (void) lp; (void) i; (void) y; UNREACHABLE("getBasisInvRow"); return 1; }
-int    getBasisInvACol(LPptr lp, int i, dVector y)          { (void) lp; (void) i; (void) y; UNREACHABLE("getBasisInvACol"); return 1; }
+/* replay of one recorded solve (sdReplayLP, solver_cplex.h); a NULL LPptr still means "no solver here" */
+#define REPLAY(name) const sdReplayLP *r = (const sdReplayLP *) lp; if (!r) UNREACHABLE(name)
+int getDual(LPptr lp, dVector pi, int length) {
+	int i; REPLAY("getDual");
+	for (i = 0; i < length && i < r->rows; i++) pi[i + 1] = r->pi[i];
+	return 0;
+}
+int getPrimal(LPptr lp, dVector x, int length) {
+	int i; REPLAY("getPrimal");
+	for (i = 0; i < length && i < r->cols; i++) x[i + 1] = r->x[i];
+	return 0;
+}
+int getDualSlacks(LPptr lp, dVector dj, int length) {
+	int i; REPLAY("getDualSlacks");
+	for (i = 0; i < length && i < r->cols; i++) dj[i + 1] = r->dj[i];
+	return 0;
+}
+int getBasis(LPptr lp, iVector cstat, iVector rstat) {
+	int i; REPLAY("getBasis");
+	for (i = 0; i < r->cols; i++) cstat[i + 1] = r->cstat[i];      /* computeMU reads cstat[1..numCols] (stocUpdate.c:372) */
+	for (i = 0; i < r->rows; i++) rstat[i + 1] = r->rstat[i];
+	return 0;
+}
+int getBasisHead(LPptr lp, iVector head, dVector x) {
+	int i; REPLAY("getBasisHead");
+	(void) x;
+	for (i = 0; i < r->basisDim; i++) head[i] = r->head[i];        /* the caller passes basisHead+1 (randCost.c:31) */
+	return 0;
+}
+int getBasisInvRow(LPptr lp, int i, dVector y) {
+	int c; REPLAY("getBasisInvRow");
+	for (c = 0; c < r->rows; c++) y[c] = r->binvRows[(size_t) i * r->rows + c];      /* caller passes phi+1 (randCost.c:47) */
+	return 0;
+}
+int getBasisInvACol(LPptr lp, int i, dVector y) {
+	int c; REPLAY("getBasisInvACol");
+	for (c = 0; c < r->rows; c++) y[c] = r->binvACols[(size_t) i * r->rows + c];     /* caller passes tempPsiRow+1 (randCost.c:79) */
+	return 0;
+}
 double getObjective(LPptr lp, int type)                     { (void) lp; (void) type; UNREACHABLE("getObjective"); return 0.0; }
 int    removeRows(LPptr lp, int begin, int end)             { (void) lp; (void) begin; (void) end; UNREACHABLE("removeRows"); return 1; }
 int    writeProblem(LPptr lp, cString fname)                { (void) lp; (void) fname; UNREACHABLE("writeProblem"); return 1; }

@@ -1,8 +1,8 @@
 /*
  * oracle/shim/solver_cplex.h  --  TEST INFRASTRUCTURE ONLY.
  * Stand-in for spAlgorithms' CPLEX wrapper header.  Only names the reference's hot-path translation
- * units mention; every solver entry point is a stub that aborts if reached (oracle/shim/shim.c): the
- * oracle never solves an LP, it is fed recorded dual vertices.
+ * units mention.  The oracle never solves an LP: the get* entry points replay one recorded solve (sdReplayLP below) when the
+ * LPptr is not NULL and abort otherwise; everything else is a stub that aborts if reached (oracle/shim/shim.c).
  */
 #ifndef SDREF_SHIM_SOLVER_H
 #define SDREF_SHIM_SOLVER_H
@@ -10,6 +10,18 @@
 #include "utils.h"
 
 typedef void *LPptr;
+
+/* Replay "solver" (tests of the host patch): an LPptr of the harness points at ONE recorded solve -- what CPLEX would hand back
+ * after solveProblem() -- and the get* entry points below copy from it.  Arrays are 0-based, as a solver returns them; the
+ * wrappers shift where the reference's call sites expect the un-vendored wrapper to (1-based vectors). */
+typedef struct {
+	int rows, cols, basisDim;
+	const int    *cstat, *rstat;     /* [cols], [rows]: AT_LOWER / BASIC / AT_UPPER / FREE_SUPER                  */
+	const double *x, *dj, *pi;       /* [cols] primal, [cols] reduced costs, [rows] duals                         */
+	const int    *head;              /* [basisDim] basic variable of each row: column j >= 0, or -(row+1) for a slack */
+	const double *binvRows;          /* [basisDim][rows] rows of the basis inverse (only the rows asked for are read) */
+	const double *binvACols;         /* [cols][rows]     B^-1 A_j (the tableau columns)                              */
+} sdReplayLP;
 
 #define ON  1
 #define OFF 0

@@ -20,7 +20,7 @@ REFERENCE_SRC = "/root/reference/twoSD_src"
 
 def build(quiet: bool = True) -> None:
     """(Re)build the checkers: the port always, the reference build only where /root/reference exists."""
-    out = subprocess.run(["make", "-C", ORACLE_DIR, "oracle", "ref"], capture_output=True, text=True)
+    out = subprocess.run(["make", "-C", ORACLE_DIR, "oracle", "ref", "hooks"], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
     if not quiet:
