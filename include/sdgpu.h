@@ -177,6 +177,23 @@ int  sdgpu_check_feasibility_basis(sdgpu_ctx *ctx, int basisIdx, double tol, uin
 int  sdgpu_feas_cuts(sdgpu_ctx *ctx, int obsFirst, int obsLast, int basisFirst, int basisLast, int maxOut,
                      double *alpha /* [maxOut] */, double *beta /* [maxOut][prevCols+1] */);
 
+/* ---- the feasibility-cut pool (cell->fcutsPool) on the device ---------------------------------------------------------------
+ * updtFeasCutPool cuts.c:465-517 INCLUDING the duplicate test of addCut2Pool cuts.c:643-655: the raw cuts of the two loops are
+ * generated in the reference's order and appended to a device-resident pool unless an equal cut (|alpha - alpha'| < tol and every
+ * |beta - beta'| <= tol) is already in it -- first come, first kept, exactly the sequential rule.  fUpdt is cell->fUpdt (in/out:
+ * [0] bases, [1] observations the pool has been updated for).  Returns the pool size.  sdgpu_reset() empties the pool. */
+int  sdgpu_feas_pool_update(sdgpu_ctx *ctx, int *fUpdt /* [2] */, double tol);
+int  sdgpu_feas_pool_size(sdgpu_ctx *ctx);
+int  sdgpu_feas_pool_get(sdgpu_ctx *ctx, int first, int count, double *alpha /* [count] */, double *beta /* [count][prevCols+1] */);
+/* checkFeasCutPool cuts.c:521-567 for the whole pool in one launch.  fAlpha / fBeta: the nFcuts feasibility cuts already in the master
+ * (cell->fcuts).  action[i] for pool cut i: 0 nothing to do; 1 the incumbent violates it (beta.x < alpha) and no equal cut is in the
+ * master: add it (cuts.c:545); 2 the incumbent violates it but an equal cut is in the master (cuts.c:541); 3 the candidate violates it:
+ * add it (cuts.c:556).  *infeasIncumb = 1 iff some action is 1 or 2 (cuts.c:540).  The host calls addCut2Master for actions 1 and 3 in
+ * pool order.  Returns the pool size. */
+int  sdgpu_feas_pool_check(sdgpu_ctx *ctx, int nFcuts, const double *fAlpha, const double *fBeta /* [nFcuts][prevCols+1] */,
+                           const double *incumbX, const double *candidX /* [prevCols+1] */, double tol, int32_t *action /* [pool] */,
+                           int *infeasIncumb);
+
 /* ---- cut formation (cuts.c, stocUpdate.c:142-190) ------------------------------------------------- */
 /* computeIstar stocUpdate.c:142-190 for ONE observation (debug / STOCH_CHECK use; the cut path below
  * never calls it).  Returns the basis index or SDGPU_NONE; *argmax as the reference sets it. */

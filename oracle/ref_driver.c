@@ -20,6 +20,10 @@
 
 configType config;   /* twoSD.c:17 defines it in the real program */
 
+/* checkFeasCutPool (cuts.c:521-567) hands the cuts it wants in the master to addCut2Master: record them instead of calling CPLEX */
+static oneCut **g_addedCuts = NULL;
+static int g_addedCnt = 0, g_addedCap = 0, g_recordAdds = 0;
+
 typedef struct {
 	numType      num;
 	coordType    coord;
@@ -94,7 +98,8 @@ static void dropBases(refCtx *c) {
 int sdref_reset(void *vc) {
 	refCtx *c = (refCtx *) vc;
 	int n;
-	/* setup.c:242-246 */
+	/* setup.c:236,242-246 */
+	if (c->cell && c->cell->fcutsPool) { freeCutsType(c->cell->fcutsPool, true); c->cell->fUpdt[0] = c->cell->fUpdt[1] = 0; }
 	dropBases(c);
 	freeDeltaType(c->delta, c->lambda->cnt, c->omega->cnt, true);
 	for (n = 0; n < c->lambda->cnt; n++) c->delta->vals[n] = NULL;
@@ -409,6 +414,67 @@ int sdref_updt_feas_cut_pool(void *vc, int *fUpdt, double tol, int maxOut, doubl
 	return c->cell->fcutsPool->cnt;
 }
 
+/* same shapes as sdgpu_feas_pool_* (include/sdgpu.h), on the reference's own updtFeasCutPool / addCut2Pool / checkFeasCutPool */
+static void ensureCell(refCtx *c) {
+	if (!c->cell) {
+		c->cell = (cellType *) calloc(1, sizeof(cellType));
+		c->cell->fcutsPool = newCuts(65536);
+	}
+	c->cell->omega = c->omega; c->cell->basis = c->basis; c->cell->sigma = c->sigma; c->cell->delta = c->delta;
+}
+
+int sdref_feas_pool_update(void *vc, int *fUpdt, double tol) {
+	refCtx *c = (refCtx *) vc;
+	ensureCell(c);
+	c->cell->fUpdt[0] = fUpdt[0]; c->cell->fUpdt[1] = fUpdt[1];
+	config.TOLERANCE = tol;
+	updtFeasCutPool(&c->num, &c->coord, c->cell);
+	fUpdt[0] = c->cell->fUpdt[0]; fUpdt[1] = c->cell->fUpdt[1];
+	return c->cell->fcutsPool->cnt;
+}
+
+int sdref_feas_pool_size(void *vc) { refCtx *c = (refCtx *) vc; return c->cell ? c->cell->fcutsPool->cnt : 0; }
+
+int sdref_feas_pool_get(void *vc, int first, int count, double *alpha, double *beta) {
+	refCtx *c = (refCtx *) vc;
+	int i, j, n1 = c->num.prevCols;
+	if (!c->cell || first < 0 || count < 0 || first + count > c->cell->fcutsPool->cnt) return count == 0 ? 0 : SDGPU_ERR;
+	for (i = 0; i < count; i++) {
+		alpha[i] = c->cell->fcutsPool->vals[first + i]->alpha;
+		for (j = 0; j <= n1; j++) beta[(size_t) i * (n1 + 1) + j] = c->cell->fcutsPool->vals[first + i]->beta[j];
+	}
+	return count;
+}
+
+/* action[i]: 1 = the reference added pool cut i to the master (cuts.c:545 or :556), 0 = it did not; the reference does not tell the two
+ * "add" cases apart, nor "violated but already there" from "nothing" other than through infeasIncumb */
+int sdref_feas_pool_check(void *vc, int nFcuts, const double *fAlpha, const double *fBeta, const double *incumbX,
+		const double *candidX, double tol, int32_t *action, int *infeasIncumb) {
+	refCtx *c = (refCtx *) vc;
+	int i, j, n1 = c->num.prevCols;
+	ensureCell(c);
+	c->cell->fcuts = newCuts(nFcuts > 0 ? nFcuts : 1);
+	for (i = 0; i < nFcuts; i++) {
+		c->cell->fcuts->vals[i] = newCut(n1, 0, 1);
+		c->cell->fcuts->vals[i]->alpha = fAlpha[i];
+		for (j = 0; j <= n1; j++) c->cell->fcuts->vals[i]->beta[j] = fBeta[(size_t) i * (n1 + 1) + j];
+		c->cell->fcuts->cnt++;
+	}
+	c->cell->incumbX = (dVector) incumbX; c->cell->candidX = (dVector) candidX; c->cell->infeasIncumb = false;
+	config.TOLERANCE = tol;
+	g_recordAdds = 1; g_addedCnt = 0;
+	checkFeasCutPool(c->cell, n1);
+	g_recordAdds = 0;
+	for (i = 0; i < c->cell->fcutsPool->cnt; i++) {
+		action[i] = 0;
+		for (j = 0; j < g_addedCnt; j++) if (g_addedCuts[j] == c->cell->fcutsPool->vals[i]) action[i] = 1;
+	}
+	if (infeasIncumb) *infeasIncumb = c->cell->infeasIncumb;
+	freeCutsType(c->cell->fcuts, false); c->cell->fcuts = NULL;
+	c->cell->incumbX = c->cell->candidX = NULL;
+	return c->cell->fcutsPool->cnt;
+}
+
 int sdref_compute_istar(void *vc, const double *Xvect, int obs, int numSamples, int pi_eval, int isNew, double *argmax) {
 	refCtx *c = (refCtx *) vc;
 	dVector piCbarX = arr_alloc(c->sigma->cnt + 1, double);
@@ -566,6 +632,12 @@ int solveSubprob(probType *prob, oneProblem *subproblem, dVector Xvect, basisTyp
 		deltaType *delta, int deltaRowLength, omegaType *omega, int omegaIdx, bool *newOmegaFlag, int currentIter, double TOLERANCE,
 		bool *subFeasFlag, bool *newBasisFlag, double *subprobTime, double *argmaxTime) { NOT_IN_ORACLE("solveSubprob"); return 1; }
 int solveQPMaster(numType *num, sparseVector *dBar, cellType *cell, double lb) { NOT_IN_ORACLE("solveQPMaster"); return 1; }
-int addCut2Master(oneProblem *master, oneCut *cut, dVector vectX, int lenX) { NOT_IN_ORACLE("addCut2Master"); return 1; }
+int addCut2Master(oneProblem *master, oneCut *cut, dVector vectX, int lenX) {
+	(void) master; (void) vectX; (void) lenX;
+	if (!g_recordAdds) NOT_IN_ORACLE("addCut2Master");
+	if (g_addedCnt == g_addedCap) { g_addedCap = g_addedCap ? 2 * g_addedCap : 64; g_addedCuts = (oneCut **) realloc(g_addedCuts, (size_t) g_addedCap * sizeof(oneCut *)); }
+	g_addedCuts[g_addedCnt++] = cut;
+	return 0;
+}
 int replaceIncumbent(probType *prob, cellType *cell, double candidEst) { NOT_IN_ORACLE("replaceIncumbent"); return 1; }
 int changeQPproximal(LPptr lp, int numCols, double sigma) { NOT_IN_ORACLE("changeQPproximal"); return 1; }

@@ -55,6 +55,8 @@ typedef struct {
 	/* checkBasisFeasibility inputs (randCost.c:202-258): per basis piDet, phi, gBar, psi values, cstat */
 	int32_t *rvdOmCols; char *senx;
 	double **fPiDet, **fPhi, **fGBar, **fPsi; int32_t **fCstat;
+	/* cell->fcutsPool (twoSD.h:129): feasibility cuts kept by addCut2Pool */
+	int64_t  fpCnt, fpCap;  double *fpAlpha, *fpBeta;
 } oracleCtx;
 
 static char g_err[512];
@@ -131,6 +133,7 @@ int sdo_reset(oracleCtx *c) {
 		c->fPiDet[b] = c->fPhi[b] = c->fGBar[b] = c->fPsi[b] = NULL; c->fCstat[b] = NULL;
 	}
 	c->omegaCnt = c->lambdaCnt = c->sigmaCnt = c->basisCnt = c->termCnt = 0;
+	c->fpCnt = 0;                                          /* freeCutsType(cell->fcutsPool, true) setup.c:236 */
 	return 0;
 }
 
@@ -142,7 +145,7 @@ void sdo_destroy(oracleCtx *c) {
 	free(c->omegaVals); free(c->omegaW); free(c->lambdaVals); free(c->sigmaPib); free(c->sigmaPiC);
 	free(c->sigmaLambda); free(c->sigmaCk); free(c->deltaPib); free(c->deltaPiC);
 	free(c->bCk); free(c->bFeas); free(c->bPhiLen); free(c->bWeight); free(c->bTermStart);
-	free(c->tSigma); free(c->tOmega); free(c->obsFeasible);
+	free(c->tSigma); free(c->tOmega); free(c->obsFeasible); free(c->fpAlpha); free(c->fpBeta);
 	free(c);
 }
 
@@ -511,6 +514,71 @@ int sdo_feas_cuts(oracleCtx *c, int obsFirst, int obsLast, int basisFirst, int b
 			n++;
 		}
 	return n;
+}
+
+/* ---- the feasibility-cut pool: updtFeasCutPool cuts.c:465-517, addCut2Pool(FEASIBILITY) cuts.c:643-655, checkFeasCutPool :521-567 */
+static int sameCut(double aA, const double *aB, double bA, const double *bB, int n1, double tol) {
+	if (!(ABSV(aA - bA) < tol)) return 0;                                                    /* cuts.c:645 */
+	for (int c = 1; c <= n1; c++) if (ABSV(aB[c] - bB[c]) > tol) return 0;                   /* equalVector :646 */
+	return 1;
+}
+
+static int poolAdd(oracleCtx *c, double alpha, const double *beta, double tol) {             /* cuts.c:643-655 */
+	int n1 = c->num.prevCols;
+	for (int64_t i = 0; i < c->fpCnt; i++)
+		if (sameCut(alpha, beta, c->fpAlpha[i], c->fpBeta + (size_t) i * (n1 + 1), n1, tol)) return 0;
+	if (c->fpCnt == c->fpCap) {
+		c->fpCap = c->fpCap ? 2 * c->fpCap : 256;
+		c->fpAlpha = (double *) realloc(c->fpAlpha, (size_t) c->fpCap * sizeof(double));
+		c->fpBeta = (double *) realloc(c->fpBeta, (size_t) c->fpCap * (n1 + 1) * sizeof(double));
+	}
+	c->fpAlpha[c->fpCnt] = alpha;
+	memcpy(c->fpBeta + (size_t) c->fpCnt * (n1 + 1), beta, ((size_t) n1 + 1) * sizeof(double));
+	c->fpCnt++;
+	return 1;
+}
+
+int sdo_feas_pool_update(oracleCtx *c, int *fUpdt, double tol) {
+	int n1 = c->num.prevCols;
+	double a, *b = (double *) calloc((size_t) n1 + 1, sizeof(double));
+	for (int o = fUpdt[1]; o < c->omegaCnt; o++)                                             /* cuts.c:472-490 */
+		for (int i = 0; i < fUpdt[0]; i++)
+			if (!c->bFeas[i] && sdo_feas_cuts(c, o, o + 1, i, i + 1, 1, &a, b) == 1) poolAdd(c, a, b, tol);
+	fUpdt[1] = (int) c->omegaCnt;
+	for (int o = 0; o < c->omegaCnt; o++)                                                    /* cuts.c:494-512 */
+		for (int i = fUpdt[0]; i < c->basisCnt; i++)
+			if (!c->bFeas[i] && sdo_feas_cuts(c, o, o + 1, i, i + 1, 1, &a, b) == 1) poolAdd(c, a, b, tol);
+	fUpdt[0] = (int) c->basisCnt;
+	free(b);
+	return (int) c->fpCnt;
+}
+
+int sdo_feas_pool_size(oracleCtx *c) { return (int) c->fpCnt; }
+
+int sdo_feas_pool_get(oracleCtx *c, int first, int count, double *alpha, double *beta) {
+	int n1 = c->num.prevCols;
+	if (first < 0 || count < 0 || first + count > c->fpCnt) return fail("feas_pool_get: range out of bounds");
+	memcpy(alpha, c->fpAlpha + first, (size_t) count * sizeof(double));
+	memcpy(beta, c->fpBeta + (size_t) first * (n1 + 1), (size_t) count * (n1 + 1) * sizeof(double));
+	return count;
+}
+
+int sdo_feas_pool_check(oracleCtx *c, int nFcuts, const double *fAlpha, const double *fBeta, const double *incumbX,
+		const double *candidX, double tol, int32_t *action, int *infeasIncumb) {
+	int n1 = c->num.prevCols;
+	if (infeasIncumb) *infeasIncumb = 0;
+	for (int64_t idx = 0; idx < c->fpCnt; idx++) {                                           /* cuts.c:526-560 */
+		const double alpha = c->fpAlpha[idx], *beta = c->fpBeta + (size_t) idx * (n1 + 1);
+		int dup = 0;
+		for (int f = 0; f < nFcuts && !dup; f++) dup = sameCut(alpha, beta, fAlpha[f], fBeta + (size_t) f * (n1 + 1), n1, tol);
+		action[idx] = 0;
+		if (dotIdx(beta, incumbX, NULL, n1) < alpha) {
+			if (infeasIncumb) *infeasIncumb = 1;
+			action[idx] = dup ? 2 : 1;
+		}
+		else if (!dup && dotIdx(beta, candidX, NULL, n1) < alpha) action[idx] = 3;
+	}
+	return (int) c->fpCnt;
 }
 
 /* ---- argmax: computeIstar stocUpdate.c:142-190 ---------------------------------------------------------- */

@@ -204,6 +204,8 @@ class Api:
             "check_feasibility_obs": (i, [vp, i, d, c_u8p]), "check_feasibility_basis": (i, [vp, i, d, c_u8p]),
             "feas_cuts": (i, [vp, i, i, i, i, i, c_f64p, c_f64p]),
             "updt_feas_cut_pool": (i, [vp, c_intp, d, i, c_f64p, c_f64p]),
+            "feas_pool_update": (i, [vp, c_intp, d]), "feas_pool_size": (i, [vp]), "feas_pool_get": (i, [vp, i, i, c_f64p, c_f64p]),
+            "feas_pool_check": (i, [vp, i, c_f64p, c_f64p, c_f64p, c_f64p, d, c_i32p, c_intp]),
             "compute_istar": (i, [vp, c_f64p, i, i, i, i, c_f64p]),
             "sd_cut": (i, [vp, c_f64p, i, i, d, C.POINTER(CCut)]),
             "sd_cut_omp": (i, [vp, c_f64p, i, i, d, C.POINTER(CCut), c_intp]),
@@ -485,6 +487,30 @@ class Tables:
         alpha, beta = np.zeros(maxOut), np.zeros((maxOut, self.problem.prevCols + 1))
         n = self._check(self._call("feas_cuts", obsFirst, obsLast, basisFirst, basisLast, maxOut, _pf64(alpha), _pf64(beta)), "feas_cuts")
         return alpha[:n], beta[:n]
+
+    def feas_pool_update(self, fUpdt, tol):
+        """updtFeasCutPool cuts.c:465-517 incl. the duplicate test of addCut2Pool cuts.c:643-655; fUpdt (list of 2) is updated in place"""
+        fu = (C.c_int * 2)(*fUpdt)
+        n = self._check(self._call("feas_pool_update", fu, tol), "feas_pool_update")
+        fUpdt[0], fUpdt[1] = fu[0], fu[1]
+        return n
+
+    def feas_pool(self):
+        n = self._check(self._call("feas_pool_size"), "feas_pool_size")
+        alpha, beta = np.zeros(max(n, 1)), np.zeros((max(n, 1), self.problem.prevCols + 1))
+        if n:
+            self._check(self._call("feas_pool_get", 0, n, _pf64(alpha), _pf64(beta)), "feas_pool_get")
+        return alpha[:n], beta[:n]
+
+    def feas_pool_check(self, fAlpha, fBeta, incumbX, candidX, tol):
+        """checkFeasCutPool cuts.c:521-567: (action per pool cut, infeasIncumb)"""
+        n = self._check(self._call("feas_pool_size"), "feas_pool_size")
+        fa, fb = _f64(fAlpha), _f64(fBeta)
+        ix, cx = _f64(incumbX), _f64(candidX)
+        act, inf = np.zeros(max(n, 1), np.int32), C.c_int(0)
+        self._check(self._call("feas_pool_check", len(fa), _pf64(fa) if len(fa) else None, _pf64(fb) if len(fa) else None, _pf64(ix), _pf64(cx), tol,
+                               _pi32(act), C.byref(inf)), "feas_pool_check")
+        return act[:n], bool(inf.value)
 
     # -- cut formation ----------------------------------------------------------------------------------
     def compute_istar(self, X, obs, numSamples, pi_eval, isNew):

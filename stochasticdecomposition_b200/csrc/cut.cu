@@ -1379,26 +1379,6 @@ __global__ void __launch_bounds__(512) k_reform(ReformArgs a) {
 	for (int i = tid; i <= a.n1; i += blockDim.x) out[1 + i] = beta[i] / (double) a.k;
 }
 
-// raw feasibility cuts (cuts.c:478-486): one thread per (observation, infeasible basis) pair, the scatter into beta done
-// in the reference's order (CCols first, then rvCols) so that coinciding columns add up identically
-__global__ void k_feas_cuts(int nPairs, const int32_t *__restrict__ pairObs, const int32_t *__restrict__ pairBasis,
-		const int32_t *__restrict__ bTermStart, const int32_t *__restrict__ tSigma, const double *__restrict__ sigmaPib,
-		const double *__restrict__ sigmaPiCr, const int32_t *__restrict__ sigmaLam, int n1c, int n1cP, const double *__restrict__ delta,
-		int64_t Dcap, int Q, const int32_t *__restrict__ CCols, const int32_t *__restrict__ rvCols, int n1,
-		double *__restrict__ alpha, double *__restrict__ beta) {
-	const int p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= nPairs) return;
-	const int o = pairObs[p], b = pairBasis[p];
-	const int s = tSigma[bTermStart[b]], l = sigmaLam[s];
-	const size_t rowStride = (size_t) (1 + Q) * SD_TILE_W;
-	const double *cell = delta + (size_t) (o / SD_TILE_W) * Dcap * rowStride + (size_t) l * rowStride + (o % SD_TILE_W);
-	double *bt = beta + (size_t) p * (n1 + 1);
-	for (int i = 0; i <= n1; i++) bt[i] = 0.0;
-	alpha[p] = __dadd_rn(sigmaPib[s], cell[0]);                                                  // cuts.c:481
-	for (int k = 0; k < n1c; k++) bt[CCols[k]] = __dadd_rn(bt[CCols[k]], sigmaPiCr[(size_t) s * n1cP + k]);   // :483-484
-	for (int q = 0; q < Q; q++) bt[rvCols[q]] = __dadd_rn(bt[rvCols[q]], cell[(size_t) (1 + q) * SD_TILE_W]);   // :485-486
-}
-
 // ======================================================================================================
 // host side
 // ======================================================================================================
@@ -2095,34 +2075,4 @@ extern "C" int sdgpu_reform_cut(sdgpu_ctx *c, const int32_t *iStar, int omegaCnt
 	if (!c) return sdgpu_fail("null context");
 	int32_t oc = iStar ? omegaCnt : c->lastOmegaCnt;
 	return sdgpu_reform_cuts_batch(c, 1, iStar, omegaCnt, &oc, 1, observ, k, lbType, lb, alpha, beta);
-}
-
-extern "C" int sdgpu_feas_cuts(sdgpu_ctx *c, int obsFirst, int obsLast, int basisFirst, int basisLast, int maxOut, double *alpha, double *beta) {
-	if (!c || (maxOut > 0 && (!alpha || !beta))) return sdgpu_fail("null argument");
-	if (obsFirst < 0 || obsLast > c->omegaCnt || basisFirst < 0 || basisLast > c->basisCnt || obsFirst > obsLast || basisFirst > basisLast)
-		return sdgpu_fail("feas_cuts: range out of bounds");
-	std::vector<int32_t> po, pb;
-	for (int o = obsFirst; o < obsLast; o++)                       // cuts.c:473-475 loop order
-		for (int b = basisFirst; b < basisLast; b++)
-			if (!c->basis[b].feas) { po.push_back(o); pb.push_back(b); }
-	const int n = (int) std::min<size_t>(po.size(), (size_t) std::max(0, maxOut));
-	if (po.size() > (size_t) std::max(0, maxOut)) return sdgpu_fail("feas_cuts: %zu cuts do not fit maxOut = %d", po.size(), maxOut);
-	if (n == 0) return 0;
-	SD_CUDA(cudaSetDevice(c->device));
-	const size_t n1p = (size_t) c->n1 + 1;
-	const size_t outBytes = (size_t) n * (1 + n1p) * 8;
-	if (sd_scratch_reserve(c, outBytes + (size_t) 2 * n * 4)) return SDGPU_ERR;
-	double *d_o = reinterpret_cast<double *>(c->d_scratch);
-	int32_t *d_p = reinterpret_cast<int32_t *>(c->d_scratch + outBytes);
-	SD_CUDA(cudaMemcpyAsync(d_p, po.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
-	SD_CUDA(cudaMemcpyAsync(d_p + n, pb.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
-	k_feas_cuts<<<sd_blocks(n, 128), 128, 0, c->stream>>>(n, d_p, d_p + n, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaPiCr, c->d_sigmaLam,
-			c->n1c, c->n1cP, c->d_delta, c->caps.maxLambda, c->Q, c->d_CCols, c->d_rvCols, c->n1, d_o, d_o + n);
-	SD_LAUNCH_OK("k_feas_cuts");
-	sd_count_launch(c);
-	SD_CUDA(cudaMemcpyAsync(alpha, d_o, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream));
-	SD_CUDA(cudaMemcpyAsync(beta, d_o + n, (size_t) n * n1p * 8, cudaMemcpyDeviceToHost, c->stream));
-	cudaError_t e = cudaStreamSynchronize(c->stream);
-	if (e != cudaSuccess) return sdgpu_fail("feas_cuts: %s", cudaGetErrorString(e));
-	return n;
 }

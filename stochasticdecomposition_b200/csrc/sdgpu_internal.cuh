@@ -117,6 +117,8 @@ struct sdgpu_ctx {
 	size_t   auxCap = 0;
 	unsigned char *d_scratch = nullptr;                 // growable device scratch of the batched calls (reformCuts, feasibility cuts)
 	size_t   scratchCap = 0;
+	double  *d_fpAlpha = nullptr, *d_fpBeta = nullptr;  // device-resident feasibility-cut pool (cell->fcutsPool): alpha [fpCap], beta [fpCap][n1+1]
+	int64_t  fpCap = 0, fpCnt = 0;
 
 	// cut formation scratch
 	double  *d_x = nullptr;          // [n1+1]

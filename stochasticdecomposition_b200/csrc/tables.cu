@@ -506,6 +506,8 @@ int sd_scratch_reserve(sdgpu_ctx *c, size_t bytes) {
 	if (bytes <= c->scratchCap) return 0;
 	SD_CUDA(cudaStreamSynchronize(c->stream));
 	if (c->d_scratch) cudaFree(c->d_scratch);
+	if (c->d_fpAlpha) cudaFree(c->d_fpAlpha);
+	if (c->d_fpBeta) cudaFree(c->d_fpBeta);
 	c->d_scratch = nullptr; c->scratchCap = 0;
 	size_t cap = std::max<size_t>(bytes * 2, 1 << 20);
 	if (cudaMalloc((void **) &c->d_scratch, cap) != cudaSuccess) return sdgpu_fail("device scratch of %zu bytes failed", cap);
@@ -692,6 +694,8 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	if (c->h_iStar) cudaFreeHost(c->h_iStar);
 	if (c->h_aux) cudaFreeHost(c->h_aux);
 	if (c->d_scratch) cudaFree(c->d_scratch);
+	if (c->d_fpAlpha) cudaFree(c->d_fpAlpha);
+	if (c->d_fpBeta) cudaFree(c->d_fpBeta);
 	if (c->evA) cudaEventDestroy(c->evA);
 	if (c->evB) cudaEventDestroy(c->evB);
 	if (c->evC) cudaEventDestroy(c->evC);
@@ -710,7 +714,7 @@ extern "C" int sdgpu_reset(sdgpu_ctx *c) {
 	  SD_CUDA(cudaMemcpy(c->d_state, &init, sizeof init, cudaMemcpyHostToDevice));
 	  *c->h_state = init; }
 	c->omegaCnt = c->lambdaCnt = c->sigmaCnt = c->basisCnt = c->termCnt = 0;
-	c->maxPhiLen = 0; c->anyInfeasibleBasis = false; c->lastOmegaCnt = 0;
+	c->maxPhiLen = 0; c->anyInfeasibleBasis = false; c->lastOmegaCnt = 0; c->fpCnt = 0;      // (freeCutsType(cell->fcutsPool, true), setup.c:236)
 	c->basis.clear(); c->hostMask.clear();
 	c->hostLam.clear(); c->grpRowCount.clear(); c->grpBasis.clear(); c->grpRow.clear(); c->grpCounted = c->grpDistinct = c->grpSorted = 0;
 	if (c->d_fHas) SD_CUDA(cudaMemset(c->d_fHas, 0, (size_t) c->caps.maxBasis));

@@ -57,3 +57,33 @@ def run(api, use_reference_pool=False, K=40, seed=9):
     if use_reference_pool:
         return sizes, ra[:sizes[-1]].copy(), rb[:sizes[-1]].copy()
     return sizes, np.array(pool.alpha), np.array(pool.beta)
+
+
+def run_device_pool(api, K=60, seed=9):
+    """The whole of updtFeasCutPool / addCut2Pool / checkFeasCutPool behind the C ABI (sdgpu_feas_pool_*): the pool lives in the
+    library.  Returns the pool sizes after every update, the final pool, and the (added-to-master?, infeasIncumb) answers of
+    checkFeasCutPool at several (incumbent, candidate) pairs, with a few pool cuts already "in the master"."""
+    from stochasticdecomposition_b200._abi import Caps
+    from stochasticdecomposition_b200.synthetic import make_problem, make_trace
+    prob = make_problem(61, rows=16, cols=24, n1=7, n1c=5, R=8, Rb=6, Q=3, distinct_rvCols=True)
+    trace = make_trace(prob, K, seed=seed, dual_pool=10, obs_pool=14)
+    n = 2 * K + 2
+    t = api.create(prob, Caps(n, n, n, K + 1, 1))
+    fUpdt, sizes, checks = [0, 0], [], []
+    rng = np.random.default_rng(seed)
+    for it in range(K):
+        k = it + 1
+        oi, onew = t.calc_omega(trace.observ[it], 1e-3)
+        feas = (k % 3 != 0)
+        t.stochastic_updates(oi, onew, trace.duals[it, 0], trace.mubBar[it, 0], k, 1e-3, feas)
+        if not feas or k % 5 == 0:
+            sizes.append(t.feas_pool_update(fUpdt, 1e-3))
+            alpha, beta = t.feas_pool()
+            pick = rng.choice(len(alpha), size=min(3, len(alpha)), replace=False) if len(alpha) else []
+            fA = np.array([alpha[p] + 4e-4 for p in pick])                  # within tolerance of a pool cut: counts as "already in the master"
+            fB = np.array([beta[p] for p in pick]).reshape(len(pick), prob.prevCols + 1)
+            ix, cx = rng.normal(0, 1.5, prob.prevCols + 1), rng.normal(0, 1.5, prob.prevCols + 1)
+            act, inf = t.feas_pool_check(fA, fB, ix, cx, 1e-3)
+            checks.append((np.asarray(act).copy(), inf))
+    alpha, beta = t.feas_pool()
+    return sizes, alpha.copy(), beta.copy(), checks, fUpdt

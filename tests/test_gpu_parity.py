@@ -359,3 +359,51 @@ def test_feasibility_cuts_on_device():
     sg, ag, bg = feas_pool.run(sd.load_library())
     assert sp == sg and sp[-1] > 5
     assert np.array_equal(ap.view(np.int64), ag.view(np.int64)) and np.array_equal(bp.view(np.int64), bg.view(np.int64))
+
+
+def test_feasibility_cut_pool_on_device():
+    """updtFeasCutPool with the duplicate test of addCut2Pool (cuts.c:465-517,643-655) and checkFeasCutPool (cuts.c:521-567) entirely
+    in the library: pool sizes after every update, the pool itself and every action code equal the oracle's"""
+    import feas_pool
+    p = feas_pool.run_device_pool(oracle_loader.oracle())
+    g = feas_pool.run_device_pool(sd.load_library())
+    assert p[0] == g[0] and p[0][-1] > 100 and p[4] == g[4]
+    assert np.array_equal(p[1].view(np.int64), g[1].view(np.int64)) and np.array_equal(p[2].view(np.int64), g[2].view(np.int64))
+    for (ap, ip), (ag, ig) in zip(p[3], g[3]):
+        assert ip == ig and np.array_equal(ap, ag)
+
+
+def test_feasibility_cut_pool_many_raw_cuts():
+    """more raw cuts than one resolution batch (4 096), heavy duplication (a pool of 6 dual rays, near-duplicate observations): the
+    first-come-first-kept rule with a tolerance is not transitive, so the kept set depends on the order -- it must be the oracle's"""
+    from stochasticdecomposition_b200.synthetic import make_problem
+    prob = make_problem(62, rows=14, cols=20, n1=6, n1c=5, R=7, Rb=5, Q=2)
+    rng = np.random.default_rng(4)
+    N, D = 700, 24
+    base = rng.normal(0, 1.0, (40, prob.numRV + 1))
+    obs = base[rng.integers(0, 40, N)] + rng.uniform(-6e-4, 6e-4, (N, prob.numRV + 1))       # clusters about as wide as the tolerance
+    obs[:, 0] = 0.0
+    rays = rng.uniform(-1, 1, (6, prob.rows + 1))
+    pis = rays[rng.integers(0, 6, D)] + rng.uniform(-3e-4, 3e-4, (D, prob.rows + 1))
+    pis[:, 0] = 0.0
+    out = []
+    for api in (oracle_loader.oracle(), sd.load_library()):
+        t = api.create(prob, Caps(D + 4, D + 4, D + 4, N + 4, 1))
+        fUpdt, sizes = [0, 0], []
+        for half in range(2):
+            for o in obs[half * N // 2:(half + 1) * N // 2]:
+                oi, onew = t.calc_omega(o, 1e-7)
+                if onew:
+                    t.calc_delta(True, oi)
+            for d in range(half * D // 2, (half + 1) * D // 2):
+                li, nl, si, ns = t.update_dual(pis[d], 0.0, d + 1, 1e-7)
+                t.basis_append(d + 1, d % 4 == 0, [si])                    # three of four are infeasible rays
+            sizes.append(t.feas_pool_update(fUpdt, 1e-3))
+        a, b = t.feas_pool()
+        act, inf = t.feas_pool_check(a[:5] + 2e-4, b[:5], rng.normal(0, 1, prob.prevCols + 1), rng.normal(0, 1, prob.prevCols + 1), 1e-3)
+        out.append((sizes, a.copy(), b.copy(), act.copy(), inf, t.counts()))
+    (sp, ap, bp, cp, ip, np_), (sg, ag, bg, cg, ig, ng) = out
+    assert np_ == ng and np_["omega"] * 18 > 8192, np_                          # > two batches of raw cuts in the second update
+    assert sp == sg and 40 < sp[-1] < np_["omega"] * 18
+    assert np.array_equal(ap.view(np.int64), ag.view(np.int64)) and np.array_equal(bp.view(np.int64), bg.view(np.int64))
+    assert np.array_equal(cp, cg) and ip == ig

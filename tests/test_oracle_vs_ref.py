@@ -166,6 +166,24 @@ def test_feasibility_cut_pool_matches_reference():
     assert np.array_equal(ar.view(np.int64), ap.view(np.int64)) and np.array_equal(br.view(np.int64), bp.view(np.int64))
 
 
+def test_feasibility_cut_pool_behind_the_abi_matches_reference():
+    """sdgpu_feas_pool_update / _check (the port's restatement) against the reference's own updtFeasCutPool + addCut2Pool
+    (cuts.c:465-517,643-655) and checkFeasCutPool (cuts.c:521-567; the cuts it hands to addCut2Master are recorded)"""
+    import feas_pool
+    r = feas_pool.run_device_pool(oracle_loader.reference())
+    p = feas_pool.run_device_pool(oracle_loader.oracle())
+    assert r[0] == p[0] and r[0][-1] > 100 and r[4] == p[4]
+    assert np.array_equal(r[1].view(np.int64), p[1].view(np.int64)) and np.array_equal(r[2].view(np.int64), p[2].view(np.int64))
+    seen = set()
+    for (ar, ir), (ap, ip) in zip(r[3], p[3]):
+        assert ir == ip
+        assert np.array_equal(ar, np.isin(ap, [1, 3]).astype(np.int32))       # the reference only shows which cuts it adds to the master
+        seen |= set(ap.tolist())
+    assert seen == {0, 1, 2, 3}
+    s2, a2, b2 = feas_pool.run(oracle_loader.oracle(), K=60)                   # the host-side pool of the older API gives the same pool
+    assert s2 == p[0] and np.array_equal(a2, p[1]) and np.array_equal(b2, p[2])
+
+
 def test_omp_flavour_same_istar():
     prob = make_problem(31, rows=30, cols=40, n1=12, n1c=9, R=11, Rb=8, Q=2)
     K = 40
