@@ -8,6 +8,7 @@
 // earlier raw cuts survived.  The O(n^2 n1) comparisons are done in parallel (raw x pool, and the lower triangle raw x raw as a bit
 // matrix); only the O(n) resolution of "kept" walks the cuts in order, in one warp.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "sdgpu_internal.cuh"

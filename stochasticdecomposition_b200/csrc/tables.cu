@@ -506,8 +506,6 @@ int sd_scratch_reserve(sdgpu_ctx *c, size_t bytes) {
 	if (bytes <= c->scratchCap) return 0;
 	SD_CUDA(cudaStreamSynchronize(c->stream));
 	if (c->d_scratch) cudaFree(c->d_scratch);
-	if (c->d_fpAlpha) cudaFree(c->d_fpAlpha);
-	if (c->d_fpBeta) cudaFree(c->d_fpBeta);
 	c->d_scratch = nullptr; c->scratchCap = 0;
 	size_t cap = std::max<size_t>(bytes * 2, 1 << 20);
 	if (cudaMalloc((void **) &c->d_scratch, cap) != cudaSuccess) return sdgpu_fail("device scratch of %zu bytes failed", cap);

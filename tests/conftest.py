@@ -12,6 +12,7 @@ if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: long LP-driven lock-step runs (tens of seconds each; deselect with -m 'gpu and not slow')")
 
 
 def _has_gpu() -> bool:

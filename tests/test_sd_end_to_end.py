@@ -41,6 +41,22 @@ def test_reference_and_port_agree_over_a_whole_run(shape, K):
     _lockstep([oracle_loader.reference(), oracle_loader.oracle()], shape, K, rtol=0.0)
 
 
+@pytest.mark.skipif(not oracle_loader.have_reference(), reason="reference build unavailable")
+@pytest.mark.parametrize("shape,K", [("ssn", 160), ("storm_rc", 40)])
+def test_reference_and_port_agree_through_reset(shape, K):
+    """the shapes of the long GPU lock-step runs (tests/test_sd_long.py), here reference build vs port, bit for bit, over two
+    replications separated by cleanCellType (setup.c:242-246)"""
+    slp = make_slp(shape)
+    prob = slp.problem()
+    tabs = Lockstep([a.create(prob, _caps(slp, K)) for a in (oracle_loader.reference(), oracle_loader.oracle())], rtol=0.0)
+    for rep in range(2):
+        if rep:
+            tabs.reset()
+            assert tabs.counts() == {"omega": 0, "lambda": 0, "sigma": 0, "basis": 0}
+        SDHost(slp, tabs, seed=3 + 7 * rep).run(K)
+    assert tabs.checked >= 2 * K
+
+
 def test_sd_converges_on_pgp2_shape():
     """sanity of the harness itself: candidate and incumbent estimates approach each other"""
     st, host = _lockstep([oracle_loader.oracle()], "pgp2", 300, rtol=0.0)

@@ -137,6 +137,7 @@ SHAPES = {
     "ssn": dict(n1=89, rows=175, core_cols=356, R=86, levels=5, density=0.05),
     "storm": dict(n1=121, rows=528, core_cols=203, R=118, levels=5, density=0.02),
     "randcost_small": dict(n1=8, rows=14, core_cols=24, R=8, levels=3, density=0.3, Q=2, rvd=3),   # storm-style random cost, small enough for tests
+    "storm_rc": dict(n1=121, rows=528, core_cols=203, R=118, levels=5, density=0.02, rvd=4),        # BASELINE config 4: storm's shape with random cost coefficients
 }
 
 
@@ -223,11 +224,19 @@ def basis_info(sub: "Subproblem", wd: np.ndarray, pi: np.ndarray):
         piDet[1:] -= ph[1:] * wd[om[n] - 1]
     basic_cost = np.array([slp.d[c] if c >= 0 else 0.0 for c in head])
     gBar = np.zeros(cols + 1); psi = np.zeros((cols, len(phis)))
-    for i in range(cols):                                           # randCost.c:78-89
-        colv = h.getReducedColumn(i)[1]
-        gBar[i + 1] = slp.d[i] - float(np.dot(colv, basic_cost))
-        for n, p in enumerate(heads):
-            psi[i, n] = colv[p]
+    if cols <= 256:
+        for i in range(cols):                                       # randCost.c:78-89, one tableau column B^-1 A_i at a time as the reference asks the solver
+            colv = h.getReducedColumn(i)[1]
+            gBar[i + 1] = slp.d[i] - float(np.dot(colv, basic_cost))
+            for n, p in enumerate(heads):
+                psi[i, n] = colv[p]
+    else:
+        # the same quantities without 1 259 solver calls per basis (storm shape): (B^-1 A_i) . c_B = A_i . (B^-T c_B) = A_i . piDet, and the
+        # tableau entry (B^-1 A_i)[p_n] = (row p_n of B^-1) . A_i = phi_n . A_i -- two matrix products.  Equal in exact arithmetic; every
+        # table backend of a lock-step run is fed the same numbers either way.
+        gBar[1:] = slp.d - slp.W.T @ piDet[1:]
+        for n, ph in enumerate(phis):
+            psi[:, n] = slp.W.T @ ph[1:]
     return dict(key=key, phi=phis, omegaIdx=om, piDet=piDet, gBar=gBar, psi=psi, cstat=np.concatenate([[0], cstat]).astype(np.int32))
 
 
@@ -360,6 +369,11 @@ class Lockstep:
 
     def calc_omega(self, observ, tol):
         return self._same([t.calc_omega(observ, tol) for t in self.b], "calc_omega")
+
+    def reset(self):
+        """cleanCellType (setup.c:242-246) on every backend"""
+        for t in self.b:
+            t.reset()
 
     def stochastic_updates(self, *a, **kw):
         return self._same([t.stochastic_updates(*a, **kw) for t in self.b], "stochastic_updates")
