@@ -130,6 +130,11 @@ int  sdgpu_calc_delta_block(sdgpu_ctx *ctx, int64_t l0, int64_t l1, int64_t o0, 
  * (stocUpdate.c:78-85 / :90-97).  Outputs may be NULL. */
 int  sdgpu_update_dual(sdgpu_ctx *ctx, const double *pi, double mubBar, int currentIter, double tol,
                        int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag);
+/* the same with the delta column of a NEW observation (calcDelta case I, stocUpdate.c:24-25) folded into the launch that scans lambda:
+ * newOmegaIdx = the index sdgpu_calc_omega just returned with *newOmegaFlag set, or -1 when the observation was not new (then this
+ * is sdgpu_update_dual).  One launch for {column, lambda, sigma}, one programmatically dependent launch for the delta row. */
+int  sdgpu_update_dual_col(sdgpu_ctx *ctx, int newOmegaIdx, const double *pi, double mubBar, int currentIter, double tol,
+                           int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag);
 /* bulk load of n dual vectors (rows of rows+1 doubles).  tol >= 0: the same find-or-append chain as
  * sdgpu_update_dual, vector after vector, without host round trips in between.  tol < 0: synthetic loader,
  * no dedup scan -- vector i becomes lambda row and sigma row (count + i) and NO delta row is computed

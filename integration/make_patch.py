@@ -90,10 +90,15 @@ def apply(dst):
     sub(p, "	int 	cnt, lambdaIdx;\n	bool	newSigmaFlag, newLambdaFlag, retainBasis;\n",
         "	int 	cnt, idx, lambdaIdx, newSigmaFlag, newLambdaFlag, isNew = 1;\n	bool	retainBasis;\n	unsigned char *flags;\n")
     sub(p, "		calcDelta(prob->num, prob->coord, lambda, delta, deltaRowLength, omega, newOmegaFlag, omegaIdx);\n",
-        "		if ( sdgpu_calc_delta(gpu, 1, omegaIdx) ) {\n"
-        "			errMsg(\"algorithm\", \"stochasticUpdates\", sdgpu_last_error(), 0);\n"
-        "			return -1;\n"
-        "		}\n")
+        "		/* (the new column of delta is computed on the device by the launch that scans lambda for the first dual below, or on its\n"
+        "		 * own if the basis turns out to be an old one) */\n")
+    sub(p, "				(*newBasisFlag) = false;\n#if defined (STOCH_CHECK)\n",
+        "				(*newBasisFlag) = false;\n"
+        "				if ( newOmegaFlag && sdgpu_calc_delta(gpu, 1, omegaIdx) ) {\n"
+        "					errMsg(\"algorithm\", \"stochasticUpdates\", sdgpu_last_error(), 0);\n"
+        "					return -1;\n"
+        "				}\n"
+        "#if defined (STOCH_CHECK)\n")
     sub(p, "		for ( cnt = 0; cnt < basis->cnt; cnt++ )\n"
            "			basis->obsFeasible[cnt][omegaIdx] = checkBasisFeasibility(basis->vals[cnt], dOmega, prob->sp->senx, prob->num->cols, prob->num->rows, TOLERANCE);\n",
         "		for ( cnt = 0; cnt < basis->cnt; cnt++ )\n"
@@ -107,9 +112,11 @@ def apply(dst):
         "		}\n")
     between(p, "	/* Elements of deterministic component of dual solution corresponding to rows with random elements in them */\n",
             "	retainBasis = newSigmaFlag;\n",
-            "	/* calcLambda + calcSigma + calcDelta(row) for the deterministic component of the dual solution: one device round trip */\n"
+            "	/* calcDelta(column, if the observation is new) + calcLambda + calcSigma + calcDelta(row) for the deterministic component of the\n"
+            "	 * dual solution: one device round trip */\n"
             "	B->sigmaIdx = (iVector) mem_realloc(B->sigmaIdx, (B->phiLength+1)*sizeof(int));\n"
-            "	if ( sdgpu_update_dual(gpu, B->piDet, B->mubBar, currentIter, TOLERANCE, &lambdaIdx, &newLambdaFlag, &B->sigmaIdx[0], &newSigmaFlag) ) {\n"
+            "	if ( sdgpu_update_dual_col(gpu, newOmegaFlag ? omegaIdx : -1, B->piDet, B->mubBar, currentIter, TOLERANCE, &lambdaIdx, &newLambdaFlag,\n"
+            "			&B->sigmaIdx[0], &newSigmaFlag) ) {\n"
             "		errMsg(\"algorithm\", \"stochasticUpdates\", sdgpu_last_error(), 0);\n"
             "		return -1;\n"
             "	}\n\n"

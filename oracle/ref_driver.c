@@ -175,6 +175,12 @@ int sdref_update_dual(void *vc, const double *pi, double mubBar, int currentIter
 	return 0;
 }
 
+int sdref_update_dual_col(void *vc, int newOmegaIdx, const double *pi, double mubBar, int currentIter, double tol,
+		int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag) {
+	if (newOmegaIdx >= 0) sdref_calc_delta(vc, 1, newOmegaIdx);                 /* stocUpdate.c:24-25 */
+	return sdref_update_dual(vc, pi, mubBar, currentIter, tol, lambdaIdx, newLambdaFlag, sigmaIdx, newSigmaFlag);
+}
+
 /* Bulk loader for the timing harness (bench.py): every table entry is still produced by the reference's own
  * calcLambda / calcSigma / calcDelta; only the loop over NEW lambda rows of calcDelta case II (rows are
  * independent, stocUpdate.c:230-254) is spread over OpenMP threads so that building a timing sample does not

@@ -344,6 +344,13 @@ int sdo_update_dual(oracleCtx *c, const double *pi, double mubBar, int currentIt
 	return 0;
 }
 
+/* stocUpdate.c:24-25 followed by :78-85 (the entry point the CUDA library serves with one launch) */
+int sdo_update_dual_col(oracleCtx *c, int newOmegaIdx, const double *pi, double mubBar, int currentIter, double tol,
+		int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag) {
+	if (newOmegaIdx >= 0) { int r = sdo_calc_delta(c, 1, newOmegaIdx); if (r != 0) return r; }
+	return sdo_update_dual(c, pi, mubBar, currentIter, tol, lambdaIdx, newLambdaFlag, sigmaIdx, newSigmaFlag);
+}
+
 int sdo_update_dual_bulk(oracleCtx *c, int64_t n, const double *pis, const double *mubBar, const int32_t *iters,
 		double tol, int32_t *lambdaIdx, int32_t *sigmaIdx) {
 	for (int64_t i = 0; i < n; i++) {

@@ -14,6 +14,7 @@
 #define sdgpu_calc_omega                  sdo_calc_omega
 #define sdgpu_calc_delta                  sdo_calc_delta
 #define sdgpu_update_dual                 sdo_update_dual
+#define sdgpu_update_dual_col             sdo_update_dual_col
 #define sdgpu_basis_find_or_append        sdo_basis_find_or_append
 #define sdgpu_basis_set_obs_feasible_col  sdo_basis_set_obs_feasible_col
 #define sdgpu_basis_set_obs_feasible_row  sdo_basis_set_obs_feasible_row

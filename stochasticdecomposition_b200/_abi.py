@@ -193,6 +193,7 @@ class Api:
             "get_delta_block": (i, [vp, i64, i64, i64, i64, i, c_f64p]),
             "bulk_load": (i, [vp, i, c_f64p, c_i32p, i, c_f64p, c_f64p, c_i32p, d, c_i32p, c_i32p]),
             "update_dual": (i, [vp, c_f64p, d, i, d, c_intp, c_intp, c_intp, c_intp]),
+            "update_dual_col": (i, [vp, i, c_f64p, d, i, d, c_intp, c_intp, c_intp, c_intp]),
             "update_dual_bulk": (i, [vp, i64, c_f64p, c_f64p, c_i32p, d, c_i32p, c_i32p]),
             "basis_append": (i, [vp, i, i, i, c_i32p, c_i32p]),
             "basis_append_bulk": (i, [vp, i64, c_i32p, c_i32p, c_i32p]),
@@ -420,6 +421,18 @@ class Tables:
                                C.byref(si), C.byref(ns)), "update_dual")
         return li.value, bool(nl.value), si.value, bool(ns.value)
 
+    def update_dual_col(self, newOmegaIdx, pi, mubBar, currentIter, tol):
+        """the delta column of a new observation (index, or -1) + calcLambda + calcSigma + delta row in one device round trip"""
+        if not self.api.has("update_dual_col"):                       # a checker without the fused entry point: the two calls it stands for
+            if newOmegaIdx >= 0:
+                self.calc_delta(True, newOmegaIdx)
+            return self.update_dual(pi, mubBar, currentIter, tol)
+        p = _f64(pi)
+        li, nl, si, ns = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self._call("update_dual_col", int(newOmegaIdx), _pf64(p), mubBar, currentIter, tol, C.byref(li), C.byref(nl),
+                               C.byref(si), C.byref(ns)), "update_dual_col")
+        return li.value, bool(nl.value), si.value, bool(ns.value)
+
     def update_dual_bulk(self, pis, mubBar=None, iters=None, tol=1e-3):
         p = _f64(pis)
         n = p.shape[0]
@@ -637,9 +650,7 @@ class Tables:
                            phi=(), phiOmegaIdx=()):
         """stocUpdate.c:14-133 with the solver outputs (piDet, mubBar, phi columns) passed in.
         Returns (basisIdx, newBasisFlag).  The basis-code shortcut (:39-53) is the caller's."""
-        if newOmegaFlag:
-            self.calc_delta(True, omegaIdx)                                   # :24-25
-        li, nl, s0, ns = self.update_dual(piDet, mubBar, currentIter, tol)    # :78-85
+        li, nl, s0, ns = self.update_dual_col(omegaIdx if newOmegaFlag else -1, piDet, mubBar, currentIter, tol)   # :24-25, :78-85
         sig, retain = [s0], ns                                                # :87
         for col in phi:                                                       # :88-99
             li, nl, sk, ns = self.update_dual(col, 0.0, currentIter, tol)

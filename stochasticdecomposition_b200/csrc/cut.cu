@@ -59,6 +59,27 @@ __device__ __forceinline__ double sd_block_sum(double v, double *s_red) {
 	return t;
 }
 
+// four block sums at once: each value goes through exactly the tree of sd_block_sum (so the results have the same bits), but the
+// four share one pair of barriers.  s_red holds 4 x 32 doubles.  Results valid in thread 0.
+__device__ __forceinline__ void sd_block_sum4(double (&v)[4], double *s_red) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+	for (int u = 0; u < 4; u++) v[u] = sd_warp_sum(v[u]);
+	__syncthreads();
+	if (lane == 0) {
+#pragma unroll
+		for (int u = 0; u < 4; u++) s_red[u * 32 + warp] = v[u];
+	}
+	__syncthreads();
+	if (warp == 0) {
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			double t = lane < nw ? s_red[u * 32 + lane] : 0.0;
+			v[u] = sd_warp_sum(t);
+		}
+	}
+}
+
 // sum_k col[k*stride] * s_x[k], left to right from 0.0 with separate multiply and add (vXv, cuts.c:106); the loads of a
 // batch of 32 are issued together (past the end: the last element again, not added) so the chain of dependent adds does not
 // also serialise the memory latency -- three round trips for the 89 columns of ssn instead of twelve
@@ -88,6 +109,7 @@ __global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, doubl
 		const int32_t *__restrict__ tOmega, double *__restrict__ termA, double *__restrict__ termC, int32_t *__restrict__ termRow,
 		int32_t *__restrict__ termMeta, int32_t *__restrict__ termBasis) {
 	extern __shared__ double s_x[];
+	sd_pdl_launch_dependents();              // the sweep may be scheduled now; its CTAs wait in sd_pdl_wait() until this grid has finished
 	for (int k = threadIdx.x; k < n1c; k += blockDim.x) s_x[k] = xDevIn ? xDevIn[CCols[k]] : xp.v[CCols[k]];
 	if (blockIdx.x == 0 && !xDevIn)
 		for (int i = threadIdx.x; i <= n1; i += blockDim.x) xDevOut[i] = xp.v[i];
@@ -128,6 +150,7 @@ struct SweepArgs {
 	const uint8_t *mask; int64_t Bcap;
 	const double *x; const int32_t *rvCOmCols;
 	double *partV; int32_t *partI; int64_t NP;
+	int rev;                        // load-based sweep: walk the chunk's bases in descending order (see k_sweep_ldg)
 };
 
 #define SW_BATCH 256    // basis descriptors staged per shared-memory refill
@@ -156,7 +179,13 @@ __device__ __forceinline__ void sd_basis_descriptor(const SweepPrepArgs &pa, con
 	rw = make_int2(pa.sigmaLam[sg], win);
 }
 
-template <bool HAS_Q, bool HAS_MASK, bool FUSED>
+// REV: the chunk's bases are walked in DESCENDING order.  The library alternates the direction from cut to cut: a delta table
+// somewhat larger than the 126 MB L2 (real problems late in a run: 5 000 x 5 000 doubles = 200 MB) is then read back to front right
+// after it was read front to back, so the part read last -- still in L2 -- is read first.  Descending order keeps the reference's
+// tie rule with '>=' instead of '>': among equal scores the one met LAST, i.e. the lowest basis index, stays (stocUpdate.c:178
+// keeps the first one met in ascending order -- the same basis).  A score of exactly -DBL_MAX can then sit in a partial maximum;
+// the merge kernel's strict '>' against its -DBL_MAX start drops it, as the reference's loop would.
+template <bool HAS_Q, bool HAS_MASK, bool FUSED, bool REV>
 __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typename std::conditional<FUSED, SweepPrepArgs, int>::type pa_) {
 	const SweepPrepArgs &pa = *reinterpret_cast<const SweepPrepArgs *>(&pa_);      // only dereferenced when FUSED
 	__shared__ double2 s_ac[SW_BATCH];       // (sigma.pib, piCbarX)
@@ -165,20 +194,24 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typ
 	extern __shared__ double s_xc[];         // FUSED: x[CCols[k]]
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	if (FUSED) for (int k = tid; k < pa.n1c; k += blockDim.x) s_xc[k] = pa.xp.v[pa.CCols[k]];
-	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize), nTot = b1 - b0;
 	const size_t rowStride = (size_t) (1 + a.Q) * SD_TILE_W;
 	const double *tileBase = a.delta + (size_t) tile * a.Dcap * rowStride + 2 * tid;
+	sd_pdl_wait();                           // descriptors and x come from k_cut_prep
+	sd_pdl_launch_dependents();              // the merge kernel may be scheduled; it waits for this grid to finish
 	if (HAS_Q) {
 		for (int j = tid; j < a.Q; j += blockDim.x) s_xq[j] = a.x[a.rvCOmCols[j]];
 	}
 	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
 	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+#define SD_BASIS_AT(i) (REV ? (b1 - 1 - (i)) : (b0 + (i)))                  // i-th basis of the walk
+#define SD_BETTER(sc, best) (REV ? ((sc) >= (best)) : ((sc) > (best)))
 
-	for (int base = b0; base < b1; base += SW_BATCH) {
+	for (int off = 0; off < nTot; off += SW_BATCH) {
 		__syncthreads();
 		{
-			int b = base + tid;
-			bool ok = b < b1;
+			const bool ok = off + tid < nTot;
+			const int b = SD_BASIS_AT(off + tid);
 			if (!FUSED) {
 				s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
 				s_rw[tid] = ok ? make_int2(a.descRow[b], a.descWin[b]) : make_int2(0, 0);
@@ -187,7 +220,7 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typ
 			else { s_ac[tid] = make_double2(0.0, 0.0); s_rw[tid] = make_int2(0, 0); }
 		}
 		__syncthreads();
-		const int n = min(SW_BATCH, b1 - base);
+		const int n = min(SW_BATCH, nTot - off);
 		for (int j = 0; j < n; j += SW_UNROLL) {
 			double2 d[SW_UNROLL];
 #pragma unroll
@@ -198,7 +231,7 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typ
 				const int win = s_rw[j + u].y;
 				if (win == 0) continue;
 				const double2 ac = s_ac[j + u];
-				const int b = base + j + u;
+				const int b = SD_BASIS_AT(off + j + u);
 				// ((sigma.pib + delta.pib) - piCbarX)   stocUpdate.c:174
 				double s0 = __dsub_rn(__dadd_rn(ac.x, d[u].x), ac.y);
 				double s1 = __dsub_rn(__dadd_rn(ac.x, d[u].y), ac.y);
@@ -219,16 +252,18 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typ
 					f0 = m.x != 0; f1 = m.y != 0;
 				}
 				if (win == 1) {
-					if (f0 && s0 > oV0) { oV0 = s0; oI0 = b; }
-					if (f1 && s1 > oV1) { oV1 = s1; oI1 = b; }
+					if (f0 && SD_BETTER(s0, oV0)) { oV0 = s0; oI0 = b; }
+					if (f1 && SD_BETTER(s1, oV1)) { oV1 = s1; oI1 = b; }
 				}
 				else {
-					if (f0 && s0 > nV0) { nV0 = s0; nI0 = b; }
-					if (f1 && s1 > nV1) { nV1 = s1; nI1 = b; }
+					if (f0 && SD_BETTER(s0, nV0)) { nV0 = s0; nI0 = b; }
+					if (f1 && SD_BETTER(s1, nV1)) { nV1 = s1; nI1 = b; }
 				}
 			}
 		}
 	}
+#undef SD_BASIS_AT
+#undef SD_BETTER
 	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
 	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
 	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
@@ -278,6 +313,8 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_recompute(SweepRcArg
 	}
 	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
 	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
+	sd_pdl_wait();                           // descriptors come from k_cut_prep (the observation values above are table data)
+	sd_pdl_launch_dependents();
 	for (int base = b0; base < b1; base += SW_BATCH) {
 		__syncthreads();
 		{
@@ -386,6 +423,8 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) k_sweep_tma(SweepArgs a
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
+	sd_pdl_wait();                           // the ring is set up; descriptors come from k_cut_prep
+	sd_pdl_launch_dependents();
 
 	if (tid >= TMA_CONSUMERS) {
 		// ---------------- producer warp: one lane feeds the ring -------------------------------------------------
@@ -490,6 +529,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
+	sd_pdl_wait();
+	sd_pdl_launch_dependents();
 
 	if (tid >= TMA_CONSUMERS) {
 		// ---------------- producer warp: lane r looks after entry r of the stage; only group leaders copy ----------------
@@ -586,6 +627,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_q(SweepArgs a, int
 		for (int s = 0; s < stages; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	sd_pdl_wait();                           // x and the descriptors come from k_cut_prep
+	sd_pdl_launch_dependents();
 	for (int q = tid; q < a.Q; q += blockDim.x) s_xq[q] = a.x[a.rvCOmCols[q]];
 	__syncthreads();
 
@@ -675,6 +718,8 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general(SweepGenArgs
 	__shared__ double s_xq[64];
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
+	sd_pdl_wait();
+	sd_pdl_launch_dependents();
 	for (int j = tid; j < a.Q; j += blockDim.x) s_xq[j] = a.x[a.rvCOmCols[j]];
 	__syncthreads();
 	double bestV[2][2] = {{-DBL_MAX, -DBL_MAX}, {-DBL_MAX, -DBL_MAX}};
@@ -758,6 +803,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_gen(SweepTGArgs a)
 		sd_mbar_init(costBar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	sd_pdl_wait();
+	sd_pdl_launch_dependents();
 	for (int q = tid; q < a.Q; q += blockDim.x) s_xq[q] = a.x[a.rvCOmCols[q]];
 	__syncthreads();
 
@@ -962,7 +1009,8 @@ __device__ __forceinline__ void sd_cut_exchange_and_store(double *s_cut, int pee
 		partial[c] = s_cut[c];
 		if (fuseNormalise) hostRes[c] = (c <= n1) ? s_cut[c] / numSamples : s_cut[c];
 	}
-	if (fuseNormalise) __threadfence_system();
+	// no system fence here: the host reads hostRes only after it has waited for this kernel, and kernel completion makes its writes
+	// to mapped host memory visible (a fence would only make the last block wait for the PCIe round trip: ~3.5 us per cut)
 }
 
 // a rank with nothing to sweep (no local observation yet) still has to take part in the exchange
@@ -981,12 +1029,13 @@ __global__ void k_cut_exchange(MergeArgs a) {
 __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	__shared__ int s_istar[SD_TILE_W];
 	__shared__ int s_w[SD_TILE_W];
-	__shared__ double s_red[32];
+	__shared__ double s_red[4 * 32];
 	__shared__ double s_mv[2][MG_THREADS];
 	__shared__ int s_mi[2][MG_THREADS];
 	extern __shared__ double s_dyn[];        // [groups][n1c] partial sums of the sigma.piC part
 	const int W = a.mW, L = MG_THREADS / W;
 	const int sub = blockIdx.x, tid = threadIdx.x;
+	sd_pdl_wait();                           // the per-chunk maxima come from the sweep
 	const int ol = tid & (W - 1), lane = tid / W;
 	const int64_t o = (int64_t) sub * W + ol;
 	const bool valid = o < a.omegaCnt;
@@ -1047,28 +1096,35 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	SD_PHASE(1);
 	if (lane == 0) { s_istar[ol] = valid ? istar : -1; s_w[ol] = wgt; }
 	double *out = a.tilePart + (size_t) sub * a.P;
-	double r;
-	r = sd_block_sum(tAlpha, s_red); if (tid == 0) out[0] = r;
-	r = sd_block_sum(tOld, s_red);   if (tid == 0) out[1] = r;
-	r = sd_block_sum(tAll, s_red);   if (tid == 0) out[2] = r;
-	r = sd_block_sum(tMiss, s_red);  if (tid == 0) out[3] = r;
+	{
+		double v4[4] = {tAlpha, tOld, tAll, tMiss};
+		sd_block_sum4(v4, s_red);            // the four sums through one pair of barriers; same tree per value as sd_block_sum
+		if (tid == 0) { out[0] = v4[0]; out[1] = v4[1]; out[2] = v4[2]; out[3] = v4[3]; }
+	}
 	SD_PHASE(2);
 
-	// delta.piC part of beta: one block sum per random T element   cuts.c:156-157 / :166-167
-	for (int q = 0; q < a.Q; q++) {
-		double v = 0.0;
+	// delta.piC part of beta: one block sum per random T element, four elements per pass   cuts.c:156-157 / :166-167
+	for (int q0 = 0; q0 < a.Q; q0 += 4) {
+		double v4[4] = {0.0, 0.0, 0.0, 0.0};
 		if (owner && istar >= 0) {
-			if (!a.randCost)
-				v = __dmul_rn(tileBase[(size_t) a.sigmaLam[istar] * rowStride + (size_t) (1 + q) * SD_TILE_W], (double) wgt);
-			else
-				for (int t = a.bTermStart[istar]; t < a.bTermStart[istar + 1]; t++) {
-					int s = a.tSigma[t], l = a.sigmaLam[s];
-					double m = (t == a.bTermStart[istar]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
-					v = __dadd_rn(v, __dmul_rn(__dmul_rn((double) wgt, m), tileBase[(size_t) l * rowStride + (size_t) (1 + q) * SD_TILE_W]));
-				}
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int q = q0 + u;
+				if (q >= a.Q) break;
+				double v = 0.0;
+				if (!a.randCost)
+					v = __dmul_rn(tileBase[(size_t) a.sigmaLam[istar] * rowStride + (size_t) (1 + q) * SD_TILE_W], (double) wgt);
+				else
+					for (int t = a.bTermStart[istar]; t < a.bTermStart[istar + 1]; t++) {
+						int s = a.tSigma[t], l = a.sigmaLam[s];
+						double m = (t == a.bTermStart[istar]) ? 1.0 : a.omega[(size_t) (a.rvOffset2 + a.tOmega[t] - 1) * a.NP + o];
+						v = __dadd_rn(v, __dmul_rn(__dmul_rn((double) wgt, m), tileBase[(size_t) l * rowStride + (size_t) (1 + q) * SD_TILE_W]));
+					}
+				v4[u] = v;
+			}
 		}
-		r = sd_block_sum(v, s_red);
-		if (tid == 0) out[4 + a.n1c + q] = r;
+		sd_block_sum4(v4, s_red);
+		if (tid == 0) for (int u = 0; u < 4 && q0 + u < a.Q; u++) out[4 + a.n1c + q0 + u] = v4[u];
 	}
 
 	// sigma.piC part of beta: thread (group g, column k) walks the observations of its group in order   cuts.c:154-155 / :164-165
@@ -1463,27 +1519,27 @@ extern "C" int sdgpu_plan_sweep_grid(int smCount, int64_t observations, int64_t 
 }
 
 template <int ROWS, int STAGES, int CTAS>
-static int sd_launch_tma_cfg(sdgpu_ctx *c, dim3 grid, const SweepArgs &a, int slot) {
+static int sd_launch_tma_cfg(sdgpu_ctx *c, dim3 grid, const SweepArgs &a, int slot, bool pdl) {
 	const size_t smem = (size_t) STAGES * ROWS * TMA_ROW_BYTES + 2 * STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int));
 	if (!c->tmaAttrSet[slot]) {             // the attribute is per device: remember it per context, not per process
 		SD_CUDA(cudaFuncSetAttribute(k_sweep_tma<ROWS, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		c->tmaAttrSet[slot] = true;
 	}
-	k_sweep_tma<ROWS, STAGES, CTAS><<<grid, TMA_THREADS, smem, c->stream>>>(a);
+	SD_CUDA(sd_launch(k_sweep_tma<ROWS, STAGES, CTAS>, grid, dim3(TMA_THREADS), smem, c->stream, pdl, a));
 	return 0;
 }
 
-static int sd_launch_tma(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
+static int sd_launch_tma(sdgpu_ctx *c, dim3 grid, const SweepArgs &a, bool pdl) {
 	static int cfg = -1;                      // SDGPU_TMA_CFG = experiment knob (tools/tma_check.py); unset = the measured best
 	if (cfg < 0) { const char *e = getenv("SDGPU_TMA_CFG"); cfg = e ? atoi(e) : 0; }
 	switch (cfg) {
 	// measured on B200, 65 536 x 131 072 (profiles/r01_tma_cfg_sweep.jsonl): <8,2,3> 6.87 TB/s, <8,3,2> 6.73, <4,4,3> 6.67,
 	// <4,3,4> 6.62, <8,4,1> 5.71; the LDG variant 6.4-6.5
-	case 1: return sd_launch_tma_cfg<8, 3, 2>(c, grid, a, 1);
-	case 2: return sd_launch_tma_cfg<4, 4, 3>(c, grid, a, 2);
-	case 3: return sd_launch_tma_cfg<8, 4, 1>(c, grid, a, 3);
-	case 4: return sd_launch_tma_cfg<4, 3, 4>(c, grid, a, 4);
-	default: return sd_launch_tma_cfg<8, 2, 3>(c, grid, a, 0);
+	case 1: return sd_launch_tma_cfg<8, 3, 2>(c, grid, a, 1, pdl);
+	case 2: return sd_launch_tma_cfg<4, 4, 3>(c, grid, a, 2, pdl);
+	case 3: return sd_launch_tma_cfg<8, 4, 1>(c, grid, a, 3, pdl);
+	case 4: return sd_launch_tma_cfg<4, 3, 4>(c, grid, a, 4, pdl);
+	default: return sd_launch_tma_cfg<8, 2, 3>(c, grid, a, 0, pdl);
 	}
 }
 
@@ -1493,7 +1549,7 @@ static size_t sd_tma_q_smem(int planes, int rps, int stages) {
 	return (size_t) stages * rps * planes * TMA_ROW_BYTES + 8 * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int)) + 64 * sizeof(double);
 }
 
-static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
+static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a, bool pdl) {
 	const int planes = 1 + c->Q;
 	static int envRps = -1, envStages = -1;
 	if (envRps < 0) { const char *e = getenv("SDGPU_Q_RPS"); envRps = e ? atoi(e) : 0; e = getenv("SDGPU_Q_STAGES"); envStages = e ? atoi(e) : 0; }
@@ -1513,7 +1569,7 @@ static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a) {
 	const size_t smem = sd_tma_q_smem(planes, rps, stages);
 	if (smem + 1024 > smemPerSM) return sdgpu_fail("sd_cut: ring of %zu bytes does not fit shared memory", smem);
 	if (smem > c->tmaQAttr) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaQAttr = smem; }
-	k_sweep_tma_q<<<grid, TMA_THREADS, smem, c->stream>>>(a, rps, stages);
+	SD_CUDA(sd_launch(k_sweep_tma_q, grid, dim3(TMA_THREADS), smem, c->stream, pdl, a, rps, stages));
 	return 0;
 }
 
@@ -1689,6 +1745,8 @@ static SweepPrepArgs sd_fused_prep_args(sdgpu_ctx *c, const double *Xvect, int n
 
 static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const double *Xvect, int numSamples, int pi_eval_flag) {
 	const dim3 grid((unsigned) tiles, (unsigned) p.nChunks);
+	const bool pdl = c->pdl && !c->timing;         // (event records between the kernels would break the programmatic edge anyway)
+#define SD_SWEEP_GO(kernel, block, smem, ...) SD_CUDA(sd_launch(kernel, grid, dim3(block), smem, c->stream, pdl, __VA_ARGS__))
 	const size_t xs = (size_t) std::max(1, c->n1c) * 8;          // dynamic shared memory of the fused-prologue instantiations
 	switch (p.kind) {
 	case SD_SW_TMA_GEN: {
@@ -1702,11 +1760,11 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 		g.partV = c->d_partV; g.partI = c->d_partI; g.rps = p.genRps; g.stages = p.genStages;
 		const size_t smem = sd_tma_gen_smem(c, p.genRps, p.genStages);
 		if (smem > c->tmaGenAttr) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaGenAttr = smem; }
-		k_sweep_tma_gen<<<grid, TMA_THREADS, smem, c->stream>>>(g);
+		SD_SWEEP_GO(k_sweep_tma_gen, TMA_THREADS, smem, g);
 		return 0;
 	}
 	case SD_SW_GENERAL:
-		k_sweep_general<<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(sd_gen_args(c, p.chunkSize, p.nChunks));
+		SD_SWEEP_GO(k_sweep_general, SD_SWEEP_THREADS, 0, sd_gen_args(c, p.chunkSize, p.nChunks));
 		return 0;
 	case SD_SW_RECOMPUTE: {
 		SweepRcArgs r;
@@ -1715,8 +1773,8 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 		r.basisCnt = (int) c->basisCnt; r.chunkSize = p.chunkSize; r.nChunks = p.nChunks; r.partV = c->d_partV; r.partI = c->d_partI;
 		SweepPrepArgs pa;
 		if (p.fusedPrep) pa = sd_fused_prep_args(c, Xvect, numSamples, pi_eval_flag);
-#define SD_RC_LAUNCH(RBV) do { if (p.fusedPrep) k_sweep_recompute<RBV, true><<<grid, SD_SWEEP_THREADS, xs, c->stream>>>(r, pa); \
-		else k_sweep_recompute<RBV, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(r, 0); } while (0)
+#define SD_RC_LAUNCH(RBV) do { if (p.fusedPrep) SD_SWEEP_GO((k_sweep_recompute<RBV, true>), SD_SWEEP_THREADS, xs, r, pa); \
+		else SD_SWEEP_GO((k_sweep_recompute<RBV, false>), SD_SWEEP_THREADS, 0, r, 0); } while (0)
 		switch (c->Rb) {
 		case 1: SD_RC_LAUNCH(1); break;
 		case 2: SD_RC_LAUNCH(2); break;
@@ -1737,7 +1795,7 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 		g.basisCnt = (int) c->basisCnt; g.chunkSize = p.chunkSize; g.nChunks = p.nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
 		const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + 2 * sizeof(int));
 		if (!c->tmaAttrSet[7]) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaAttrSet[7] = true; }
-		k_sweep_tma_grp<<<grid, TMA_THREADS, smem, c->stream>>>(g);
+		SD_SWEEP_GO(k_sweep_tma_grp, TMA_THREADS, smem, g);
 		return 0;
 	}
 	default: break;
@@ -1748,14 +1806,22 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 	a.basisCnt = (int) c->basisCnt; a.chunkSize = p.chunkSize; a.nChunks = p.nChunks;
 	a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
 	a.partV = c->d_partV; a.partI = c->d_partI; a.NP = c->NP;
-	if (p.kind == SD_SW_TMA) return sd_launch_tma(c, grid, a);
-	if (p.kind == SD_SW_TMA_Q) return sd_launch_tma_q(c, grid, a);
+	a.rev = 0;
+	if (p.kind == SD_SW_TMA) return sd_launch_tma(c, grid, a, pdl);
+	if (p.kind == SD_SW_TMA_Q) return sd_launch_tma_q(c, grid, a, pdl);
+	// the load-based sweep alternates its direction from cut to cut (L2 re-use on tables a little larger than L2, see k_sweep_ldg)
+	const bool rev = c->altDir && (c->sweepFlip ^= 1) == 0;
+	a.rev = rev ? 1 : 0;
 	const bool hasMask = c->rvd > 0;
-	if (c->Q > 0 && hasMask) k_sweep_ldg<true, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-	else if (c->Q > 0)       k_sweep_ldg<true, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-	else if (hasMask)        k_sweep_ldg<false, true, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-	else if (!p.fusedPrep)   k_sweep_ldg<false, false, false><<<grid, SD_SWEEP_THREADS, 0, c->stream>>>(a, 0);
-	else                     k_sweep_ldg<false, false, true><<<grid, SD_SWEEP_THREADS, xs, c->stream>>>(a, sd_fused_prep_args(c, Xvect, numSamples, pi_eval_flag));
+#define SD_LDG_GO(HQ, HM, FU, smem, second) do { if (rev) SD_SWEEP_GO((k_sweep_ldg<HQ, HM, FU, true>), SD_SWEEP_THREADS, smem, a, second); \
+		else SD_SWEEP_GO((k_sweep_ldg<HQ, HM, FU, false>), SD_SWEEP_THREADS, smem, a, second); } while (0)
+	if (c->Q > 0 && hasMask) SD_LDG_GO(true, true, false, 0, 0);
+	else if (c->Q > 0)       SD_LDG_GO(true, false, false, 0, 0);
+	else if (hasMask)        SD_LDG_GO(false, true, false, 0, 0);
+	else if (!p.fusedPrep)   SD_LDG_GO(false, false, false, 0, 0);
+	else { const SweepPrepArgs pa = sd_fused_prep_args(c, Xvect, numSamples, pi_eval_flag); SD_LDG_GO(false, false, true, xs, pa); }
+#undef SD_LDG_GO
+#undef SD_SWEEP_GO
 	return 0;
 }
 
@@ -1818,8 +1884,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		const size_t dyn = (size_t) std::max(std::max(1, groups * c->n1c), (groupsP + 1) * P + c->n1 + 4) * 8;
 		// static: s_istar, s_w (2 x 2 KiB), s_red, s_mv (8 KiB), s_mi (4 KiB)
 		if (sd_smem_optin(c, k_cut_merge, SD_SMEM_MERGE, 17 * 1024, dyn, "k_cut_merge")) return SDGPU_ERR;
-		k_cut_merge<<<(N + mW - 1) / mW, MG_THREADS, dyn, c->stream>>>(m);
-		SD_LAUNCH_OK("k_cut_merge");
+		SD_CUDA(sd_launch(k_cut_merge, dim3((unsigned) ((N + mW - 1) / mW)), dim3(MG_THREADS), dyn, c->stream, c->pdl && !c->timing, m));
 		sd_count_launch(c);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evE, c->stream));
 	}

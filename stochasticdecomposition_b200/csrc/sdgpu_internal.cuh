@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -146,6 +147,9 @@ struct sdgpu_ctx {
 	bool     tmaAttrSet[8] = {false, false, false, false, false, false, false, false};   // per context (= per device): opt-in shared memory sizes
 	size_t   tmaQAttr = 0;
 	bool     cutFused = false;       // the last merge block already normalised the cut into h_cutRes
+	bool     pdl = true;             // chain the kernels of a cut with programmatic dependent launch (SDGPU_PDL=0 turns it off)
+	bool     altDir = true;          // the load-based sweep alternates its row direction from cut to cut (SDGPU_ALTDIR=0 turns it off):
+	int      sweepFlip = 0;          //   a table a little larger than the 126 MB L2 then finds its most recently read part still cached
 
 	// host mirrors (bookkeeping only; no table arithmetic happens on the host)
 	int64_t omegaCnt = 0, lambdaCnt = 0, sigmaCnt = 0, basisCnt = 0, termCnt = 0;
@@ -210,6 +214,25 @@ __host__ __device__ static inline size_t sd_mask_off(int64_t Bcap, int64_t b, in
 }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): the kernels of one cut (prologue -> sweep -> merge) are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so kernel N+1 is scheduled while kernel N still runs and its CTAs block in
+// sd_pdl_wait() until kernel N has completed and flushed -- the launch latency and the prologue of N+1 overlap the tail of N.
+// Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void sd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void sd_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KA, class... A>
+static inline cudaError_t sd_launch(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, A &&...args) {
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
+
 // The block that draws the last ticket of a launch (1-D grid) gets `true`; the ticket is reset for the next launch.
 __device__ __forceinline__ bool sd_is_last_block(unsigned int *ticket) {
 	__shared__ bool s_last;

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <climits>
 #include <algorithm>
 
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restri
 	__shared__ double s_buf[DC_BATCH][DC_THREADS];
 	extern __shared__ double s_lam[];            // [Rb] the lambda entry each random RHS row meets (0.0 where it meets none), then [R] the row itself
 	double *s_row = s_lam + Rb;
+	sd_pdl_wait();                               // (launched as the programmatic dependent of the find-or-append kernel)
 	int l = forcedRow >= 0 ? forcedRow : (st->newLambda ? st->lambdaIdx : -1);
 	if (l < 0) return;
 	for (int j = threadIdx.x; j < Rb; j += blockDim.x) { const int p = bLamPos[j]; s_lam[j] = p >= 0 ? lambda[(size_t) p * LP + l] : 0.0; }
@@ -286,6 +288,142 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_col(const double *__restri
 	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
 	out[0] = s;
 	sd_delta_cell_T(Rb, Q, cLamPos, cListStart, cList, [&](int p) { return lambda[(size_t) p * LP + l]; }, [&](int j) { return s_om[j]; }, out, SD_TILE_W);
+}
+
+// ---- one launch for stocUpdate.c:24-25 + :78-81: the delta column of a new observation (blocks [nbScan, gridDim.x)) next to the
+// lambda scan (blocks [0, nbScan)); the block that draws the last ticket commits lambda (:280-283), forms calcSigma's candidate
+// (:293-296), scans sigma by itself (:299-310 -- a pib compare per row, the piC compare only where pib matches), commits sigma
+// (:312-318) and publishes the state.  The delta ROW of a new lambda follows as a second, programmatically dependent launch.
+// Same arithmetic per element as k_lambda_fused / k_sigma_fused / k_delta_col, hence the same bits.
+#define UF_THREADS 256
+#define UF_COLB    16      // column role: operands a thread keeps in flight
+struct UpdArgs {
+	const double *pi; int rows; const int32_t *rvRows; int R; double *lambda; int64_t LP, lambdaCap; double tol;
+	const int32_t *bCol; const double *bVal; int bCnt; double mubBar;
+	const int32_t *cbStart, *cbRow; const double *cbVal; int n1c, n1cP, cbStage;
+	double *vecDev;
+	double *sigPib, *sigPiCk, *sigPiCr; int32_t *sigLam, *sigCk; int64_t SP, sigmaCap; int iter;
+	int nbScan, colObs, lambdaCntHost;
+	const double *omega; int64_t NP; int numRV, Rb, Q; const int32_t *bLamPos, *cLamPos, *cListStart, *cList; double *delta; int64_t Dcap;
+	SdDevState *st, *hst;
+};
+
+__global__ void __launch_bounds__(UF_THREADS) k_update_fused(UpdArgs a) {
+	extern __shared__ double s_dyn[];
+	__shared__ int s_found;
+	sd_pdl_launch_dependents();                               // the delta-row kernel may be scheduled; it waits for this grid
+	const int tid = threadIdx.x;
+	if ((int) blockIdx.x >= a.nbScan) {
+		// ------------- delta column (calcDelta case I, stocUpdate.c:206-229): one thread per stored lambda row -------------------
+		double *s_om = s_dyn;                                 // [numRV] the observation
+		int32_t *s_pos = reinterpret_cast<int32_t *>(s_om + a.numRV);                 // [Rb]
+		double *s_buf = reinterpret_cast<double *>(s_pos + ((a.Rb + 1) & ~1));        // [UF_COLB][UF_THREADS]
+		const int o = a.colObs;
+		for (int j = tid; j < a.numRV; j += blockDim.x) s_om[j] = a.omega[(size_t) j * a.NP + o];
+		for (int j = tid; j < a.Rb; j += blockDim.x) s_pos[j] = a.bLamPos[j];
+		__syncthreads();
+		const int64_t l = (int64_t) (blockIdx.x - a.nbScan) * blockDim.x + tid;
+		if (l < a.lambdaCntHost) {                            // rows stored BEFORE this call (a row appended by it gets its whole delta row next)
+			double sum = 0.0;                                 // vXvSparse :218, index order
+			for (int j = 0; j < a.Rb; j += UF_COLB) {
+				const int n = min(UF_COLB, a.Rb - j);
+				for (int u = 0; u < n; u++) { const int p = s_pos[j + u]; if (p >= 0) sd_cp_async8(&s_buf[u * UF_THREADS + tid], a.lambda + (size_t) p * a.LP + l); }
+				sd_cp_async_wait_all();
+				for (int u = 0; u < n; u++) sum = __dadd_rn(sum, __dmul_rn(s_om[j + u], s_pos[j + u] >= 0 ? s_buf[u * UF_THREADS + tid] : 0.0));
+			}
+			double *out = a.delta + sd_delta_off(a.Dcap, a.Q, l, 0, o);
+			out[0] = sum;
+			sd_delta_cell_T(a.Rb, a.Q, a.cLamPos, a.cListStart, a.cList, [&](int p) { return a.lambda[(size_t) p * a.LP + l]; }, [&](int j) { return s_om[j]; }, out, SD_TILE_W);
+		}
+	}
+	else {
+		// ------------- lambda scan (calcLambda, stocUpdate.c:269-277): one thread per stored row -----------------------------------
+		double *s_cand = s_dyn, *s_pi = s_dyn + a.R;
+		for (int i = tid; i <= a.rows; i += blockDim.x) s_pi[i] = a.pi[i];              // one trip to the (possibly host-mapped) vector
+		__syncthreads();
+		if (blockIdx.x == 0) for (int i = tid; i <= a.rows; i += blockDim.x) a.vecDev[i] = s_pi[i];     // for the committing block, whichever it is
+		for (int i = tid; i < a.R; i += blockDim.x) s_cand[i] = s_pi[a.rvRows[i]];      // reduceVector :269
+		__syncthreads();
+		const int r = blockIdx.x * blockDim.x + tid;
+		if (r < a.lambdaCntHost) {
+			bool same = true;
+			for (int i = 0; i < a.R; i++)
+				if (sd_abs(s_cand[i] - a.lambda[(size_t) i * a.LP + r]) > a.tol) { same = false; break; }
+			if (same) atomicMin(&a.st->foundLambda, r);
+		}
+	}
+	if (!sd_is_last_block(&a.st->ticket)) return;
+
+	// ------------- commit (one block; every other block's writes are visible after the ticket) ---------------------------------------
+	double *s_cand = s_dyn, *s_pi = s_cand + a.R, *s_prod = s_pi + a.rows + 1, *s_cprod = s_prod + a.bCnt, *s_candC = s_cprod + a.cbStage;
+	for (int i = tid; i <= a.rows; i += blockDim.x) s_pi[i] = __ldcg(a.vecDev + i);
+	if (tid == 0) s_found = INT_MAX;
+	__syncthreads();
+	for (int i = tid; i < a.R; i += blockDim.x) s_cand[i] = s_pi[a.rvRows[i]];
+	__syncthreads();
+	const int cnt = a.lambdaCntHost;
+	const int found = *(volatile int *) &a.st->foundLambda;
+	int idx = found, isNew = 0;
+	if (found == INT_MAX) {                                                             // :280-283
+		if (cnt >= a.lambdaCap) { idx = -1; if (tid == 0) a.st->overflow = 1; }
+		else {
+			for (int i = tid; i < a.R; i += blockDim.x) a.lambda[(size_t) i * a.LP + cnt] = s_cand[i];
+			idx = cnt; isNew = 1;
+		}
+	}
+	// calcSigma's candidate (:293-296): products in parallel, sums left to right per sum (see k_lambda_fused)
+	for (int e = tid; e < a.bCnt; e += blockDim.x) s_prod[e] = __dmul_rn(a.bVal[e], s_pi[a.bCol[e]]);
+	const int nnz = a.cbStart[a.n1c];
+	const bool staged = nnz <= a.cbStage;
+	if (staged) for (int e = tid; e < nnz; e += blockDim.x) s_cprod[e] = __dmul_rn(s_pi[a.cbRow[e]], a.cbVal[e]);
+	__syncthreads();
+	for (int k = tid; k < a.n1c; k += blockDim.x) {
+		double t = 0.0;
+		if (staged) for (int e = a.cbStart[k]; e < a.cbStart[k + 1]; e++) t = __dadd_rn(t, s_cprod[e]);
+		else for (int e = a.cbStart[k]; e < a.cbStart[k + 1]; e++) t = __dadd_rn(t, __dmul_rn(s_pi[a.cbRow[e]], a.cbVal[e]));
+		s_candC[k] = t;
+	}
+	__shared__ double s_pibBar;
+	if (tid == 0) {
+		double sum = 0.0;                                                               // vXvSparse :293
+		for (int e = 0; e < a.bCnt; e++) sum = __dadd_rn(sum, s_prod[e]);
+		s_pibBar = __dadd_rn(sum, a.mubBar);
+	}
+	__syncthreads();
+	const double pibBar = s_pibBar;
+	const int scnt = a.st->sigmaCnt;
+	if (!isNew && idx >= 0) {                                                           // :299-310
+		for (int sg = tid; sg < scnt; sg += blockDim.x) {
+			if (!(sd_abs(pibBar - a.sigPib[sg]) <= a.tol)) continue;
+			bool same = true;
+			for (int k = 0; k < a.n1c; k++)
+				if (sd_abs(s_candC[k] - a.sigPiCk[(size_t) k * a.SP + sg]) > a.tol) { same = false; break; }
+			if (same && a.sigLam[sg] == idx) atomicMin(&s_found, sg);
+		}
+	}
+	__syncthreads();
+	const int sfound = s_found;
+	int sidx = sfound, sNew = 0;
+	if (sfound == INT_MAX) {                                                            // :312-318
+		if (scnt >= a.sigmaCap || idx < 0) { sidx = -1; if (tid == 0) a.st->overflow = 1; }
+		else {
+			for (int k = tid; k < a.n1c; k += blockDim.x) {
+				a.sigPiCk[(size_t) k * a.SP + scnt] = s_candC[k];
+				a.sigPiCr[(size_t) scnt * a.n1cP + k] = s_candC[k];
+			}
+			sidx = scnt; sNew = 1;
+		}
+	}
+	__syncthreads();
+	if (tid == 0) {
+		SdDevState *st = a.st;
+		st->pibBar = pibBar;
+		st->lambdaIdx = idx; st->newLambda = isNew; st->foundLambda = INT_MAX;
+		if (isNew) st->lambdaCnt = cnt + 1;
+		if (sNew) { a.sigPib[scnt] = pibBar; a.sigLam[scnt] = idx; a.sigCk[scnt] = a.iter; st->sigmaCnt = scnt + 1; }
+		st->sigmaIdx = sidx; st->newSigma = sNew; st->foundSigma = INT_MAX;
+		sd_publish(st, a.hst);
+	}
 }
 
 // calcDelta for a whole block of (dual, observation) pairs -- the bulk loader of synthetic sweeps.  A CTA owns
@@ -564,6 +702,7 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 
 	sdgpu_ctx *c = new sdgpu_ctx();
 	c->device = device; c->num = nm; c->caps = *caps;
+	{ const char *e = getenv("SDGPU_PDL"); if (e) c->pdl = atoi(e) != 0; e = getenv("SDGPU_ALTDIR"); if (e) c->altDir = atoi(e) != 0; }   // experiment knobs
 	if (c->caps.maxTerms < 1) c->caps.maxTerms = 1;
 	c->n1 = nm.prevCols; c->n1c = nm.cntCcols; c->n1cP = std::max(1, nm.cntCcols); c->R = nm.rvRowCnt; c->Rb = nm.rvbOmCnt;
 	c->Q = nm.rvCOmCnt; c->rvd = nm.rvdOmCnt; c->numRV = nm.numRV; c->rows = nm.rows; c->cols = nm.cols;
@@ -902,20 +1041,76 @@ extern "C" int sdgpu_calc_delta(sdgpu_ctx *c, int newOmegaFlag, int elemIdx) {
 	return 0;
 }
 
-extern "C" int sdgpu_update_dual(sdgpu_ctx *c, const double *pi, double mubBar, int currentIter, double tol,
+// the fused form: {delta column || lambda scan -> commit lambda, sigma scan + commit} in one launch, the delta row as its programmatic
+// dependent.  Used while the sigma table is small enough for one block to scan (every real problem: <= 7 501 rows, setup.c:139).
+static bool sd_fused_update_ok(sdgpu_ctx *c) {
+	static int env = -1;                                  // SDGPU_FUSED_UPDATE=0: experiment knob, the three-launch chain
+	if (env < 0) { const char *e = getenv("SDGPU_FUSED_UPDATE"); env = e ? atoi(e) : 1; }
+	return env != 0 && c->sigmaCnt <= 16384 && c->lambdaCnt <= ((int64_t) 1 << 22);
+}
+
+static int sd_launch_update_fused(sdgpu_ctx *c, const double *d_pi, double mubBar, int iter, double tol, int colObs) {
+	UpdArgs a;
+	const int cbStage = std::min(c->cbNnz, 2048);
+	a.pi = d_pi; a.rows = c->rows; a.rvRows = c->d_rvRows; a.R = c->R; a.lambda = c->d_lambda; a.LP = c->LP; a.lambdaCap = c->caps.maxLambda; a.tol = tol;
+	a.bCol = c->d_bBarCol; a.bVal = c->d_bBarVal; a.bCnt = c->bBarCnt; a.mubBar = mubBar;
+	a.cbStart = c->d_cbStart; a.cbRow = c->d_cbRow; a.cbVal = c->d_cbVal; a.n1c = c->n1c; a.n1cP = c->n1cP; a.cbStage = std::max(1, cbStage);
+	a.vecDev = c->d_vecIn;
+	a.sigPib = c->d_sigmaPib; a.sigPiCk = c->d_sigmaPiCk; a.sigPiCr = c->d_sigmaPiCr; a.sigLam = c->d_sigmaLam; a.sigCk = c->d_sigmaCk;
+	a.SP = c->SP; a.sigmaCap = c->caps.maxSigma; a.iter = iter;
+	a.nbScan = sd_blocks(c->lambdaCnt, UF_THREADS);
+	const int nbCol = (colObs >= 0 && c->lambdaCnt > 0) ? sd_blocks(c->lambdaCnt, UF_THREADS) : 0;
+	a.colObs = colObs; a.lambdaCntHost = (int) c->lambdaCnt;
+	a.omega = c->d_omega; a.NP = c->NP; a.numRV = c->numRV; a.Rb = c->Rb; a.Q = c->Q; a.bLamPos = c->d_bLamPos; a.cLamPos = c->d_cLamPos;
+	a.cListStart = c->d_cListStart; a.cList = c->d_cList; a.delta = c->d_delta; a.Dcap = c->caps.maxLambda;
+	a.st = c->d_state; a.hst = c->d_hstate;
+	const size_t commitD = (size_t) std::max(1, c->R) + c->rows + 1 + std::max(1, c->bBarCnt) + std::max(1, cbStage) + std::max(1, c->n1c);
+	const size_t colD = (size_t) c->numRV + (size_t) ((c->Rb + 1) / 2 + 1) + (size_t) UF_COLB * UF_THREADS;
+	const size_t smem = std::max(commitD, colD) * 8;
+	if (sd_smem_optin(c, k_update_fused, SD_SMEM_UPD1, 64, smem, "k_update_fused")) return SDGPU_ERR;
+	k_update_fused<<<a.nbScan + nbCol, UF_THREADS, smem, c->stream>>>(a);
+	SD_LAUNCH_OK("k_update_fused");
+	sd_count_launch(c);
+	if (c->omegaCnt > 0) {                                 // :84-85, a no-op kernel unless the lambda was new
+		const size_t rs = (size_t) std::max(1, c->R + c->Rb) * 8;
+		if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, rs, "k_delta_row")) return SDGPU_ERR;
+		SD_CUDA(sd_launch(k_delta_row, dim3((unsigned) sd_blocks(c->omegaCnt, DC_THREADS)), dim3(DC_THREADS), rs, c->stream, c->pdl,
+				(const double *) c->d_lambda, c->LP, c->R, (const double *) c->d_omega, c->NP, c->Rb, c->Q, (const int32_t *) c->d_bLamPos, (const int32_t *) c->d_cLamPos,
+				(const int32_t *) c->d_cListStart, (const int32_t *) c->d_cList, c->d_delta, (int64_t) c->caps.maxLambda, (const SdDevState *) c->d_state, -1));
+		sd_count_launch(c);
+	}
+	return 0;
+}
+
+// stocUpdate.c:24-25 (the delta column of a new observation, newOmegaIdx >= 0) and :78-85 (calcLambda, calcSigma, delta row) in one
+// device round trip
+extern "C" int sdgpu_update_dual_col(sdgpu_ctx *c, int newOmegaIdx, const double *pi, double mubBar, int currentIter, double tol,
 		int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag) {
 	if (!c || !pi) return sdgpu_fail("null argument");
+	if (newOmegaIdx >= c->omegaCnt) return sdgpu_fail("update_dual_col: observation %d out of range", newOmegaIdx);
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
-	if (sd_launch_lambda(c, sd_staged_source(c, c->rows + 1, c->lambdaCnt), mubBar, tol, c->lambdaCnt, false)) return SDGPU_ERR;   // stocUpdate.c:78 (+ staging of :293-296)
-	if (sd_launch_sigma(c, currentIter, tol, c->sigmaCnt)) return SDGPU_ERR;                     // :81
-	if (sd_launch_delta_row(c, -1, c->omegaCnt)) return SDGPU_ERR;                               // :84-85 (kernel no-op unless the lambda was new)
+	const double *src = sd_staged_source(c, c->rows + 1, c->lambdaCnt);
+	if (sd_fused_update_ok(c)) {
+		if (sd_launch_update_fused(c, src, mubBar, currentIter, tol, newOmegaIdx >= 0 ? newOmegaIdx : -1)) return SDGPU_ERR;
+	}
+	else {
+		if (newOmegaIdx >= 0 && sd_launch_delta_col(c, newOmegaIdx, c->lambdaCnt)) return SDGPU_ERR;
+		if (sd_launch_lambda(c, src, mubBar, tol, c->lambdaCnt, false)) return SDGPU_ERR;   // stocUpdate.c:78 (+ staging of :293-296)
+		if (sd_launch_sigma(c, currentIter, tol, c->sigmaCnt)) return SDGPU_ERR;                     // :81
+		if (sd_launch_delta_row(c, -1, c->omegaCnt)) return SDGPU_ERR;                               // :84-85 (kernel no-op unless the lambda was new)
+	}
 	if (sd_sync_state(c)) return SDGPU_ERR;
 	if (lambdaIdx) *lambdaIdx = c->h_state->lambdaIdx;
 	if (newLambdaFlag) *newLambdaFlag = c->h_state->newLambda;
 	if (sigmaIdx) *sigmaIdx = c->h_state->sigmaIdx;
 	if (newSigmaFlag) *newSigmaFlag = c->h_state->newSigma;
 	return 0;
+}
+
+extern "C" int sdgpu_update_dual(sdgpu_ctx *c, const double *pi, double mubBar, int currentIter, double tol,
+		int *lambdaIdx, int *newLambdaFlag, int *sigmaIdx, int *newSigmaFlag) {
+	return sdgpu_update_dual_col(c, -1, pi, mubBar, currentIter, tol, lambdaIdx, newLambdaFlag, sigmaIdx, newSigmaFlag);
 }
 
 extern "C" int sdgpu_update_dual_bulk(sdgpu_ctx *c, int64_t n, const double *pis, const double *mubBar, const int32_t *iters,
