@@ -318,6 +318,10 @@ int  sdgpu_plan_sweep_grid(int smCount, int64_t observations, int64_t bases, int
  * shape and these table sizes under sdgpu_set_sweep_variant(variant), and whether the cut skips the separate prologue launch */
 int  sdgpu_plan_sweep_kind(int rvCOmCnt, int rvdOmCnt, int rvbOmCnt, int maxPhiLength, int costColumns, int n1, int n1c,
                            int64_t bases, int64_t terms, int64_t distinctLambdaRows, int64_t observations, int variant, int *fusedPrologue);
+/* micro-benchmark of the FP64 pipe for the instruction mix this library issues: separately rounded DMUL + DADD pairs (counted as two
+ * operations per pair; the library never fuses them) and, for comparison, DFMA flops.  Best of `reps` launches.
+ * The roofline denominator of the FP64-bound kernels (recompute sweep, bulk delta build). */
+int  sdgpu_fp64_peak(int device, int reps, double *mulAddOpsPerSec, double *fmaFlopsPerSec);
 /* run subsequent work on an existing CUDA stream (cudaStream_t) instead of the context's own */
 int  sdgpu_set_stream(sdgpu_ctx *ctx, void *cudaStream);
 

@@ -234,6 +234,7 @@ class Api:
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
             "get_stats": (i, [vp, C.POINTER(CStats)]),
             "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]), "set_collective": (i, [vp, i]),
+            "fp64_peak": (i, [i, i, c_f64p, c_f64p]),
             "plan_sweep_grid": (i, [i, i64, i64, i, c_intp, c_intp, c_intp]),
             "plan_sweep_kind": (i, [i, i, i, i, i, i, i, i64, i64, i64, i64, i, c_intp]),
         }
@@ -258,6 +259,13 @@ class Api:
         if k < 0:
             raise SdError(self.error())
         return k, bool(fused.value)
+
+    def fp64_peak(self, device: int = 0, reps: int = 5):
+        """(separately rounded DMUL+DADD operations / s, DFMA flops / s) of the device's FP64 pipe"""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        if self._fn("fp64_peak")(device, reps, C.byref(a), C.byref(b)) != 0:
+            raise SdError(self.error())
+        return a.value, b.value
 
     def error(self) -> str:
         fn = self._fn("last_error")

@@ -148,7 +148,9 @@ struct sdgpu_ctx {
 	size_t   tmaQAttr = 0;
 	bool     cutFused = false;       // the last merge block already normalised the cut into h_cutRes
 	bool     pdl = true;             // chain the kernels of a cut with programmatic dependent launch (SDGPU_PDL=0 turns it off)
+	bool     fusedUpdate = true;     // {delta column || lambda scan -> sigma} in one launch (SDGPU_FUSED_UPDATE=0: the three-launch chain)
 	bool     altDir = true;          // the load-based sweep alternates its row direction from cut to cut (SDGPU_ALTDIR=0 turns it off):
+	int      forceChunks = 0;        // SDGPU_CHUNKS at create: forces the basis-chunk count of the sweep grid (experiment knob)
 	int      sweepFlip = 0;          //   a table a little larger than the 126 MB L2 then finds its most recently read part still cached
 
 	// host mirrors (bookkeeping only; no table arithmetic happens on the host)

@@ -36,6 +36,17 @@ __device__ __forceinline__ void sd_cp_async8(double *smemDst, const double *gmem
 __device__ __forceinline__ void sd_cp_async_wait_all() {
 	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void sd_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` (0 or 1) committed groups of this thread are still in flight
+__device__ __forceinline__ void sd_cp_async_wait(bool onePending) {
+	if (onePending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+	else asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// A small host vector (observation, dual vector) travelling as a KERNEL PARAMETER: no DMA, and no zero-copy read over PCIe by every
+// block either (~2 us per kernel at real-problem sizes).  Longer vectors go through the mapped staging buffer / one DMA copy.
+#define SD_VEC_PARAM_MAX 640
+struct SdVecParam { double v[SD_VEC_PARAM_MAX]; };
 
 // DBL_ABS of the reference: (x) > 0 ? (x) : -(x); a NaN difference therefore never counts as a mismatch
 __device__ __forceinline__ double sd_abs(double x) { return x > 0.0 ? x : -x; }
@@ -48,8 +59,7 @@ __device__ __forceinline__ double sd_abs(double x) { return x > 0.0 ? x : -x; }
 // Every block scans its rows; the block that draws the last ticket commits the result and publishes the device
 // state into mapped pinned host memory, so the host only has to wait for the stream.
 __device__ __forceinline__ void sd_publish(const SdDevState *st, SdDevState *host) {
-	*host = *st;
-	__threadfence_system();
+	*host = *st;           // mapped pinned memory; the host reads it after it has waited for the stream, which makes the write visible
 }
 
 // calcLambda (stocUpdate.c:264-284) in one launch, followed in the same launch by the staging part of calcSigma
@@ -146,10 +156,10 @@ __global__ void k_sigma_fused(double *__restrict__ pib, double *__restrict__ piC
 }
 
 // calcOmega (stocUpdate.c:326-348) in one launch.  mode 0: find, then bump or append; 1: find only; 2: append only
-__global__ void k_omega_fused(const double *__restrict__ observ, int numRV, double *__restrict__ omega, int32_t *__restrict__ w, int64_t NP,
+__global__ void k_omega_fused(const double *__restrict__ observ, SdVecParam vp, int numRV, double *__restrict__ omega, int32_t *__restrict__ w, int64_t NP,
 		int64_t cap, double tol, int mode, int weight, SdDevState *st, SdDevState *hst) {
 	extern __shared__ double s_cand[];
-	for (int j = threadIdx.x; j < numRV; j += blockDim.x) s_cand[j] = observ[1 + j];
+	for (int j = threadIdx.x; j < numRV; j += blockDim.x) s_cand[j] = observ ? observ[1 + j] : vp.v[1 + j];
 	__syncthreads();
 	const int cnt = st->omegaCnt;
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,11 +262,20 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restri
 	int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (o >= st->omegaCnt) return;
 	double s = 0.0;                                                                        // vXvSparse :244, index order
-	for (int j = 0; j < Rb; j += DC_BATCH) {
-		const int n = min(DC_BATCH, Rb - j);
-		for (int u = 0; u < n; u++) sd_cp_async8(&s_buf[u][threadIdx.x], omega + (size_t) (j + u) * NP + o);
-		sd_cp_async_wait_all();
-		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_buf[u][threadIdx.x], s_lam[j + u]));
+	// two half-batches alternate: the loads of group g+1 are in flight while the (sequential) adds of group g run
+	constexpr int H = DC_BATCH / 2;
+	const int G = (Rb + H - 1) / H;
+	auto issue = [&](int g) {
+		const int j0 = g * H, n = min(H, Rb - j0);
+		for (int u = 0; u < n; u++) sd_cp_async8(&s_buf[(g & 1) * H + u][threadIdx.x], omega + (size_t) (j0 + u) * NP + o);
+		sd_cp_async_commit();
+	};
+	if (G > 0) issue(0);
+	for (int g = 0; g < G; g++) {
+		if (g + 1 < G) issue(g + 1);
+		sd_cp_async_wait(g + 1 < G);
+		const int j0 = g * H, n = min(H, Rb - j0);
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_buf[(g & 1) * H + u][threadIdx.x], s_lam[j0 + u]));
 	}
 	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
 	out[0] = s;
@@ -279,11 +298,20 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_col(const double *__restri
 	int64_t l = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (l >= st->lambdaCnt) return;
 	double s = 0.0;                                                                        // vXvSparse :218, index order
-	for (int j = 0; j < Rb; j += DC_BATCH) {
-		const int n = min(DC_BATCH, Rb - j);
-		for (int u = 0; u < n; u++) { const int p = s_pos[j + u]; if (p >= 0) sd_cp_async8(&s_buf[u][threadIdx.x], lambda + (size_t) p * LP + l); }
-		sd_cp_async_wait_all();
-		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_om[j + u], s_pos[j + u] >= 0 ? s_buf[u][threadIdx.x] : 0.0));
+	// two half-batches alternate: the loads of group g+1 are in flight while the (sequential) adds of group g run
+	constexpr int H = DC_BATCH / 2;
+	const int G = (Rb + H - 1) / H;
+	auto issue = [&](int g) {
+		const int j0 = g * H, n = min(H, Rb - j0);
+		for (int u = 0; u < n; u++) { const int p = s_pos[j0 + u]; if (p >= 0) sd_cp_async8(&s_buf[(g & 1) * H + u][threadIdx.x], lambda + (size_t) p * LP + l); }
+		sd_cp_async_commit();
+	};
+	if (G > 0) issue(0);
+	for (int g = 0; g < G; g++) {
+		if (g + 1 < G) issue(g + 1);
+		sd_cp_async_wait(g + 1 < G);
+		const int j0 = g * H, n = min(H, Rb - j0);
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_om[j0 + u], s_pos[j0 + u] >= 0 ? s_buf[(g & 1) * H + u][threadIdx.x] : 0.0));
 	}
 	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
 	out[0] = s;
@@ -308,7 +336,7 @@ struct UpdArgs {
 	SdDevState *st, *hst;
 };
 
-__global__ void __launch_bounds__(UF_THREADS) k_update_fused(UpdArgs a) {
+__global__ void __launch_bounds__(UF_THREADS) k_update_fused(UpdArgs a, SdVecParam vp) {
 	extern __shared__ double s_dyn[];
 	__shared__ int s_found;
 	sd_pdl_launch_dependents();                               // the delta-row kernel may be scheduled; it waits for this grid
@@ -324,12 +352,20 @@ __global__ void __launch_bounds__(UF_THREADS) k_update_fused(UpdArgs a) {
 		__syncthreads();
 		const int64_t l = (int64_t) (blockIdx.x - a.nbScan) * blockDim.x + tid;
 		if (l < a.lambdaCntHost) {                            // rows stored BEFORE this call (a row appended by it gets its whole delta row next)
-			double sum = 0.0;                                 // vXvSparse :218, index order
-			for (int j = 0; j < a.Rb; j += UF_COLB) {
-				const int n = min(UF_COLB, a.Rb - j);
-				for (int u = 0; u < n; u++) { const int p = s_pos[j + u]; if (p >= 0) sd_cp_async8(&s_buf[u * UF_THREADS + tid], a.lambda + (size_t) p * a.LP + l); }
-				sd_cp_async_wait_all();
-				for (int u = 0; u < n; u++) sum = __dadd_rn(sum, __dmul_rn(s_om[j + u], s_pos[j + u] >= 0 ? s_buf[u * UF_THREADS + tid] : 0.0));
+			double sum = 0.0;                                 // vXvSparse :218, index order; two half-batches alternate (see k_delta_col)
+			constexpr int H = UF_COLB / 2;
+			const int G = (a.Rb + H - 1) / H;
+			auto issue = [&](int g) {
+				const int j0 = g * H, n = min(H, a.Rb - j0);
+				for (int u = 0; u < n; u++) { const int p = s_pos[j0 + u]; if (p >= 0) sd_cp_async8(&s_buf[((g & 1) * H + u) * UF_THREADS + tid], a.lambda + (size_t) p * a.LP + l); }
+				sd_cp_async_commit();
+			};
+			if (G > 0) issue(0);
+			for (int g = 0; g < G; g++) {
+				if (g + 1 < G) issue(g + 1);
+				sd_cp_async_wait(g + 1 < G);
+				const int j0 = g * H, n = min(H, a.Rb - j0);
+				for (int u = 0; u < n; u++) sum = __dadd_rn(sum, __dmul_rn(s_om[j0 + u], s_pos[j0 + u] >= 0 ? s_buf[((g & 1) * H + u) * UF_THREADS + tid] : 0.0));
 			}
 			double *out = a.delta + sd_delta_off(a.Dcap, a.Q, l, 0, o);
 			out[0] = sum;
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(UF_THREADS) k_update_fused(UpdArgs a) {
 	else {
 		// ------------- lambda scan (calcLambda, stocUpdate.c:269-277): one thread per stored row -----------------------------------
 		double *s_cand = s_dyn, *s_pi = s_dyn + a.R;
-		for (int i = tid; i <= a.rows; i += blockDim.x) s_pi[i] = a.pi[i];              // one trip to the (possibly host-mapped) vector
+		for (int i = tid; i <= a.rows; i += blockDim.x) s_pi[i] = a.pi ? a.pi[i] : vp.v[i];        // kernel parameter, or one trip to the staged vector
 		__syncthreads();
 		if (blockIdx.x == 0) for (int i = tid; i <= a.rows; i += blockDim.x) a.vecDev[i] = s_pi[i];     // for the committing block, whichever it is
 		for (int i = tid; i < a.R; i += blockDim.x) s_cand[i] = s_pi[a.rvRows[i]];      // reduceVector :269
@@ -702,7 +738,10 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 
 	sdgpu_ctx *c = new sdgpu_ctx();
 	c->device = device; c->num = nm; c->caps = *caps;
-	{ const char *e = getenv("SDGPU_PDL"); if (e) c->pdl = atoi(e) != 0; e = getenv("SDGPU_ALTDIR"); if (e) c->altDir = atoi(e) != 0; }   // experiment knobs
+	{ const char *e = getenv("SDGPU_PDL"); if (e) c->pdl = atoi(e) != 0; e = getenv("SDGPU_ALTDIR"); if (e) c->altDir = atoi(e) != 0;
+	  e = getenv("SDGPU_FUSED_UPDATE"); if (e) c->fusedUpdate = atoi(e) != 0;
+	  e = getenv("SDGPU_CHUNKS"); if (e) c->forceChunks = atoi(e);
+	  e = getenv("SDGPU_SWEEP_VARIANT"); if (e && atoi(e) >= 0 && atoi(e) <= 4) c->sweepVariant = atoi(e); }   // experiment knobs, read per context
 	if (c->caps.maxTerms < 1) c->caps.maxTerms = 1;
 	c->n1 = nm.prevCols; c->n1c = nm.cntCcols; c->n1cP = std::max(1, nm.cntCcols); c->R = nm.rvRowCnt; c->Rb = nm.rvbOmCnt;
 	c->Q = nm.rvCOmCnt; c->rvd = nm.rvdOmCnt; c->numRV = nm.numRV; c->rows = nm.rows; c->cols = nm.cols;
@@ -886,10 +925,13 @@ extern "C" int sdgpu_get_stats(sdgpu_ctx *c, sdgpu_stats *out) {
 
 // ---- omega -------------------------------------------------------------------------------------------------
 static int sd_launch_omega(sdgpu_ctx *c, const double *observ, double tol, int mode, int weight) {
-	if (sd_stage_vec(c, observ, c->numRV + 1)) return SDGPU_ERR;
+	if (c->numRV + 1 > SD_VEC_PARAM_MAX && sd_stage_vec(c, observ, c->numRV + 1)) return SDGPU_ERR;
 	const int blocks = mode == 2 ? 1 : sd_blocks(c->omegaCnt, 256);
 	if (sd_smem_optin(c, k_omega_fused, SD_SMEM_OMEGA, 64, (size_t) std::max(1, c->numRV) * 8, "k_omega_fused")) return SDGPU_ERR;
-	k_omega_fused<<<blocks, 256, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(sd_staged_source(c, c->numRV + 1, mode == 2 ? 0 : c->omegaCnt), c->numRV, c->d_omega, c->d_omegaW, c->NP,
+	SdVecParam vp;
+	const bool asParam = c->numRV + 1 <= SD_VEC_PARAM_MAX;
+	if (asParam) memcpy(vp.v, observ, ((size_t) c->numRV + 1) * sizeof(double));
+	k_omega_fused<<<blocks, 256, (size_t) std::max(1, c->numRV) * 8, c->stream>>>(asParam ? nullptr : sd_staged_source(c, c->numRV + 1, mode == 2 ? 0 : c->omegaCnt), vp, c->numRV, c->d_omega, c->d_omegaW, c->NP,
 			c->caps.maxOmega, tol, mode, weight, c->d_state, c->d_hstate);
 	SD_LAUNCH_OK("k_omega_fused");
 	sd_count_launch(c);
@@ -1044,13 +1086,15 @@ extern "C" int sdgpu_calc_delta(sdgpu_ctx *c, int newOmegaFlag, int elemIdx) {
 // the fused form: {delta column || lambda scan -> commit lambda, sigma scan + commit} in one launch, the delta row as its programmatic
 // dependent.  Used while the sigma table is small enough for one block to scan (every real problem: <= 7 501 rows, setup.c:139).
 static bool sd_fused_update_ok(sdgpu_ctx *c) {
-	static int env = -1;                                  // SDGPU_FUSED_UPDATE=0: experiment knob, the three-launch chain
-	if (env < 0) { const char *e = getenv("SDGPU_FUSED_UPDATE"); env = e ? atoi(e) : 1; }
-	return env != 0 && c->sigmaCnt <= 16384 && c->lambdaCnt <= ((int64_t) 1 << 22);
+	return c->fusedUpdate && c->sigmaCnt <= 16384 && c->lambdaCnt <= ((int64_t) 1 << 22);
 }
 
-static int sd_launch_update_fused(sdgpu_ctx *c, const double *d_pi, double mubBar, int iter, double tol, int colObs) {
+static int sd_launch_update_fused(sdgpu_ctx *c, const double *hostPi, double mubBar, int iter, double tol, int colObs) {
 	UpdArgs a;
+	SdVecParam vp;
+	const double *d_pi = nullptr;
+	if (c->rows + 1 <= SD_VEC_PARAM_MAX) memcpy(vp.v, hostPi, ((size_t) c->rows + 1) * sizeof(double));
+	else { if (sd_stage_vec(c, hostPi, c->rows + 1)) return SDGPU_ERR; d_pi = sd_staged_source(c, c->rows + 1, c->lambdaCnt); }
 	const int cbStage = std::min(c->cbNnz, 2048);
 	a.pi = d_pi; a.rows = c->rows; a.rvRows = c->d_rvRows; a.R = c->R; a.lambda = c->d_lambda; a.LP = c->LP; a.lambdaCap = c->caps.maxLambda; a.tol = tol;
 	a.bCol = c->d_bBarCol; a.bVal = c->d_bBarVal; a.bCnt = c->bBarCnt; a.mubBar = mubBar;
@@ -1068,7 +1112,7 @@ static int sd_launch_update_fused(sdgpu_ctx *c, const double *d_pi, double mubBa
 	const size_t colD = (size_t) c->numRV + (size_t) ((c->Rb + 1) / 2 + 1) + (size_t) UF_COLB * UF_THREADS;
 	const size_t smem = std::max(commitD, colD) * 8;
 	if (sd_smem_optin(c, k_update_fused, SD_SMEM_UPD1, 64, smem, "k_update_fused")) return SDGPU_ERR;
-	k_update_fused<<<a.nbScan + nbCol, UF_THREADS, smem, c->stream>>>(a);
+	k_update_fused<<<a.nbScan + nbCol, UF_THREADS, smem, c->stream>>>(a, vp);
 	SD_LAUNCH_OK("k_update_fused");
 	sd_count_launch(c);
 	if (c->omegaCnt > 0) {                                 // :84-85, a no-op kernel unless the lambda was new
@@ -1089,12 +1133,12 @@ extern "C" int sdgpu_update_dual_col(sdgpu_ctx *c, int newOmegaIdx, const double
 	if (!c || !pi) return sdgpu_fail("null argument");
 	if (newOmegaIdx >= c->omegaCnt) return sdgpu_fail("update_dual_col: observation %d out of range", newOmegaIdx);
 	SD_CUDA(cudaSetDevice(c->device));
-	if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
-	const double *src = sd_staged_source(c, c->rows + 1, c->lambdaCnt);
 	if (sd_fused_update_ok(c)) {
-		if (sd_launch_update_fused(c, src, mubBar, currentIter, tol, newOmegaIdx >= 0 ? newOmegaIdx : -1)) return SDGPU_ERR;
+		if (sd_launch_update_fused(c, pi, mubBar, currentIter, tol, newOmegaIdx >= 0 ? newOmegaIdx : -1)) return SDGPU_ERR;
 	}
 	else {
+		if (sd_stage_vec(c, pi, c->rows + 1)) return SDGPU_ERR;
+		const double *src = sd_staged_source(c, c->rows + 1, c->lambdaCnt);
 		if (newOmegaIdx >= 0 && sd_launch_delta_col(c, newOmegaIdx, c->lambdaCnt)) return SDGPU_ERR;
 		if (sd_launch_lambda(c, src, mubBar, tol, c->lambdaCnt, false)) return SDGPU_ERR;   // stocUpdate.c:78 (+ staging of :293-296)
 		if (sd_launch_sigma(c, currentIter, tol, c->sigmaCnt)) return SDGPU_ERR;                     // :81

@@ -387,6 +387,7 @@ def test_feasibility_cut_pool_many_raw_cuts():
     pis = rays[rng.integers(0, 6, D)] + rng.uniform(-3e-4, 3e-4, (D, prob.rows + 1))
     pis[:, 0] = 0.0
     out = []
+    ix, cx = rng.normal(0, 1, prob.prevCols + 1), rng.normal(0, 1, prob.prevCols + 1)
     for api in (oracle_loader.oracle(), sd.load_library()):
         t = api.create(prob, Caps(D + 4, D + 4, D + 4, N + 4, 1))
         fUpdt, sizes = [0, 0], []
@@ -400,10 +401,54 @@ def test_feasibility_cut_pool_many_raw_cuts():
                 t.basis_append(d + 1, d % 4 == 0, [si])                    # three of four are infeasible rays
             sizes.append(t.feas_pool_update(fUpdt, 1e-3))
         a, b = t.feas_pool()
-        act, inf = t.feas_pool_check(a[:5] + 2e-4, b[:5], rng.normal(0, 1, prob.prevCols + 1), rng.normal(0, 1, prob.prevCols + 1), 1e-3)
+        act, inf = t.feas_pool_check(a[:5] + 2e-4, b[:5], ix, cx, 1e-3)
         out.append((sizes, a.copy(), b.copy(), act.copy(), inf, t.counts()))
     (sp, ap, bp, cp, ip, np_), (sg, ag, bg, cg, ig, ng) = out
     assert np_ == ng and np_["omega"] * 18 > 8192, np_                          # > two batches of raw cuts in the second update
     assert sp == sg and 40 < sp[-1] < np_["omega"] * 18
     assert np.array_equal(ap.view(np.int64), ag.view(np.int64)) and np.array_equal(bp.view(np.int64), bg.view(np.int64))
     assert np.array_equal(cp, cg) and ip == ig
+
+
+@pytest.mark.parametrize("name", ["pgp2_dedup", "T_random", "random_cost_pool_ties"])
+def test_latency_features_do_not_change_a_bit(name, monkeypatch):
+    """Programmatic dependent launch, the alternating sweep direction and the fused update launch (delta column || lambda scan -> sigma
+    in the committing block) are pure scheduling: with all of them off and with all of them on, every table entry, every index and
+    every cut must have the same bits."""
+    pk, K, dpool, opool, phi_len, rk = CASES[name]
+    prob = make_problem(1000 + len(name), **pk)
+    trace = make_trace(prob, K, seed=77 + K, dual_pool=dpool, obs_pool=opool, phi_len=phi_len)
+    caps = roomy_caps(K, phi_len)
+    runs = []
+    for on in ("0", "1"):
+        for knob in ("SDGPU_PDL", "SDGPU_ALTDIR", "SDGPU_FUSED_UPDATE"):
+            monkeypatch.setenv(knob, on)
+        runs.append(replay(sd.load_library(), prob, trace, caps, **rk))
+    off, on = runs
+    assert_records_match(off, on, exact_cut=True)
+    assert_tables_identical(off.tables, on.tables)
+
+
+def test_multi_tile_both_sweep_directions():
+    """the load-based sweep alternates its direction from cut to cut (descending order keeps the lowest index with '>='): consecutive
+    cuts at the same x must be bit-identical, with duplicated duals (exact ties) in every chunk, and equal the oracle's iStar"""
+    D, N = 900, 1300
+    prob = make_problem(5, rows=30, cols=40, n1=12, n1c=9, R=11, Rb=9, Q=0)
+    rng = np.random.default_rng(2)
+    pis = rng.uniform(-1, 1, (D, prob.rows + 1)); pis[:, 0] = 0
+    for d in rng.choice(np.arange(1, D), size=D // 10, replace=False):
+        pis[d] = pis[rng.integers(0, d)]
+    obs = rng.normal(0, 1, (N, prob.numRV + 1)); obs[:, 0] = 0
+    w = (1 + rng.poisson(0.3, N)).astype(np.int32)
+    iters = np.ceil((np.arange(D) + 1) * (int(w.sum()) / D)).astype(np.int32)
+    x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
+    t, li, si = _bulk_tables(sd.load_library(), prob, pis, None, iters, obs, w, Caps(D + 2, D + 2, D + 2, N + 3, 1))
+    t.set_sweep_variant(1)
+    cuts = [t.sd_cut(x, int(w.sum()), pe, 0.0) for pe in (1, 1, 1, 0, 0)]
+    for c in cuts[1:3]:
+        assert np.array_equal(c.iStar, cuts[0].iStar) and c.alpha == cuts[0].alpha and np.array_equal(c.beta, cuts[0].beta)
+    assert np.array_equal(cuts[4].iStar, cuts[3].iStar) and cuts[4].alpha == cuts[3].alpha
+    port, _, _ = _bulk_tables(oracle_loader.oracle(), prob, pis, None, iters, obs, w, Caps(D + 2, D + 2, D + 2, N + 3, 1))
+    for pe, c in ((1, cuts[0]), (0, cuts[3])):
+        pc = port.sd_cut(x, int(w.sum()), pe, 0.0)
+        assert np.array_equal(pc.iStar, c.iStar)

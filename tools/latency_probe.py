@@ -20,13 +20,14 @@ import stochasticdecomposition_b200 as sd
 from stochasticdecomposition_b200._abi import CCut, _pf64, _pi32
 
 
-def probe(D, N, rv, n1, pdl, alt, fused, reps=40):
+def probe(D, N, rv, n1, pdl, alt, fused, l2keep=0, chunks=0, reps=40):
     os.environ["SDGPU_PDL"], os.environ["SDGPU_ALTDIR"], os.environ["SDGPU_FUSED_UPDATE"] = str(pdl), str(alt), str(fused)
+    os.environ["SDGPU_CHUNKS"] = str(chunks)
     api = sd.load_library()
     prob, pis, obsv, weights, xs = bench.make_workload(D, N, rv, n1, 0, reps + 8)
     k = int(weights.sum())
     t = bench.load_tables(api, prob, pis, obsv, weights, D, N, k, reps + 8)
-    out = {"D": D, "N": N, "rv": rv, "n1": n1, "pdl": pdl, "altdir": alt, "fused_update": fused}
+    out = {"D": D, "N": N, "rv": rv, "n1": n1, "pdl": pdl, "altdir": alt, "fused_update": fused, "chunks": chunks}
     beta = np.zeros(prob.prevCols + 1); istar = np.zeros(N + reps + 16, np.int32)
     cut = CCut(0.0, _pf64(beta), _pi32(istar), 0, 0, 0.0, 0.0)
     fn, ctx = api._fn("sd_cut"), t.ctx
@@ -87,11 +88,11 @@ if __name__ == "__main__":
     shapes = [(1000, 1000, 86, 89), (5000, 5000, 86, 89), (7500, 5000, 118, 121)]
     if "--quick" in sys.argv:
         shapes = shapes[1:2]
-    combos = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (1, 1, 1)]
+    combos = [(0, 0, 0, 0, 0), (1, 0, 0, 0, 0), (0, 1, 0, 0, 0), (1, 1, 0, 0, 0), (1, 1, 1, 0, 0)]
     for D, N, rv, n1 in shapes:
         base = None
-        for pdl, alt, fused in combos:
-            r = probe(D, N, rv, n1, pdl, alt, fused)
+        for pdl, alt, fused, l2keep, chunks in combos:
+            r = probe(D, N, rv, n1, pdl, alt, fused, l2keep, chunks)
             sig, counts = r.pop("_sig"), r.pop("_counts")
             if base is None:
                 base = (sig, counts)
