@@ -100,65 +100,41 @@ __device__ __forceinline__ double sd_dot_strided(const double *__restrict__ col,
 // own sigma row with the same left-to-right sum, hence the same bits.
 struct SdXParam { double v[256]; };
 
-#define PREP_WARPS 8      // warps (= bases) per CTA of k_cut_prep
-
-// sigma.piC[s] . x[CCols] by ONE WARP: the lanes fetch the row of the row-major copy of sigma.piC in one coalesced trip and form the
-// products (each product is rounded on its own in the reference too), lane 0 adds them up left to right from 0.0 -- vXv's order and
-// bits (cuts.c:106) -- and the sum is broadcast.  One memory round trip per dot instead of three strided ones per thread.
-__device__ __forceinline__ double sd_warp_dot(const double *__restrict__ row, const double *s_x, double *s_prod, int n) {
-	const int lane = threadIdx.x & 31;
-	for (int k = lane; k < n; k += 32) s_prod[k] = __dmul_rn(row[k], s_x[k]);
-	__syncwarp();
-	double acc = 0.0;
-	if (lane == 0) for (int k = 0; k < n; k++) acc = __dadd_rn(acc, s_prod[k]);
-	acc = __shfl_sync(0xffffffffu, acc, 0);
-	__syncwarp();
-	return acc;
-}
-
-__global__ void __launch_bounds__(32 * PREP_WARPS) k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, double *__restrict__ xDevOut, int n1,
-		const double *__restrict__ piCr, int n1c, int n1cP, const int32_t *__restrict__ CCols, int sigmaCnt, double *__restrict__ piCbarXAll,
+__global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, double *__restrict__ xDevOut, int n1,
+		const double *__restrict__ piCk, int64_t SP, int n1c, const int32_t *__restrict__ CCols, int sigmaCnt, double *__restrict__ piCbarXAll,
 		const int32_t *__restrict__ bCk, const int32_t *__restrict__ bFeas, const int32_t *__restrict__ bTermStart,
 		const int32_t *__restrict__ tSigma, const double *__restrict__ sigmaPib, const int32_t *__restrict__ sigmaLam,
 		int basisCnt, int split, int cutoff,
 		double *__restrict__ descA, double *__restrict__ descC, int32_t *__restrict__ descRow, int32_t *__restrict__ descWin,
 		const int32_t *__restrict__ tOmega, double *__restrict__ termA, double *__restrict__ termC, int32_t *__restrict__ termRow,
 		int32_t *__restrict__ termMeta, int32_t *__restrict__ termBasis) {
-	extern __shared__ double s_x[];              // [n1c] x[CCols[k]], then [PREP_WARPS][n1c] products
+	extern __shared__ double s_x[];
 	sd_pdl_launch_dependents();              // the sweep may be scheduled now; its CTAs wait in sd_pdl_wait() until this grid has finished
 	for (int k = threadIdx.x; k < n1c; k += blockDim.x) s_x[k] = xDevIn ? xDevIn[CCols[k]] : xp.v[CCols[k]];
 	if (blockIdx.x == 0 && !xDevIn)
 		for (int i = threadIdx.x; i <= n1; i += blockDim.x) xDevOut[i] = xp.v[i];
 	__syncthreads();
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	double *s_prod = s_x + n1c + (size_t) warp * n1c;
-	const int i = blockIdx.x * PREP_WARPS + warp;
-	if (piCbarXAll && i < sigmaCnt) {
-		const double v = sd_warp_dot(piCr + (size_t) i * n1cP, s_x, s_prod, n1c);
-		if (lane == 0) piCbarXAll[i] = v;
-	}
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (piCbarXAll && i < sigmaCnt) piCbarXAll[i] = sd_dot_strided(piCk + i, (size_t) SP, s_x, n1c);
 	if (i < basisCnt) {
-		const int ts = bTermStart[i], te = bTermStart[i + 1];
-		const int s = tSigma[ts];
-		const double acc = sd_warp_dot(piCr + (size_t) s * n1cP, s_x, s_prod, n1c);
+		const int s = tSigma[bTermStart[i]];
+		const double acc = sd_dot_strided(piCk + s, (size_t) SP, s_x, n1c);
 		const int ck = bCk[i];
 		int win = 0;
 		if (bFeas[i]) {
 			if (ck <= cutoff) win = (ck > -INT_MAX) ? 1 : 0;
 			else win = split ? 2 : 0;
 		}
-		if (lane == 0) { descA[i] = sigmaPib[s]; descC[i] = acc; descRow[i] = sigmaLam[s]; descWin[i] = win; }
+		descA[i] = sigmaPib[s]; descC[i] = acc; descRow[i] = sigmaLam[s]; descWin[i] = win;
 		if (termA) {                                      // term-linear form for the random-cost sweep: one descriptor per (basis, term)
+			const int ts = bTermStart[i], te = bTermStart[i + 1];
 			for (int t = ts; t < te; t++) {
 				const int st = tSigma[t];
-				const double c = (t == ts) ? acc : sd_warp_dot(piCr + (size_t) st * n1cP, s_x, s_prod, n1c);
-				if (lane == 0) {
-					termA[t] = sigmaPib[st];
-					termC[t] = c;
-					termRow[t] = sigmaLam[st];
-					termMeta[t] = win | (t == te - 1 ? 4 : 0) | ((t == ts ? 0 : tOmega[t]) << 8);
-					termBasis[t] = i;
-				}
+				termA[t] = sigmaPib[st];
+				termC[t] = (t == ts) ? acc : sd_dot_strided(piCk + st, (size_t) SP, s_x, n1c);
+				termRow[t] = sigmaLam[st];
+				termMeta[t] = win | (t == te - 1 ? 4 : 0) | ((t == ts ? 0 : tOmega[t]) << 8);
+				termBasis[t] = i;
 			}
 		}
 	}
@@ -1476,9 +1452,8 @@ static int sd_launch_prep(sdgpu_ctx *c, const double *X, int cutoff, int split, 
 		xDevIn = c->d_x;
 	}
 	const int64_t n = std::max<int64_t>(std::max<int64_t>(c->basisCnt, wantAllPiCbarX ? c->sigmaCnt : 0), 1);
-	const size_t prepSmem = (size_t) std::max(1, c->n1c) * (1 + PREP_WARPS) * 8;
-	if (sd_smem_optin(c, k_cut_prep, SD_SMEM_PREP, 0, prepSmem, "k_cut_prep")) return SDGPU_ERR;
-	k_cut_prep<<<sd_blocks(n, PREP_WARPS), 32 * PREP_WARPS, prepSmem, c->stream>>>(xp, xDevIn, c->d_x, c->n1, c->d_sigmaPiCr, c->n1c, c->n1cP,
+	if (sd_smem_optin(c, k_cut_prep, SD_SMEM_PREP, 0, (size_t) std::max(1, c->n1c) * 8, "k_cut_prep")) return SDGPU_ERR;
+	k_cut_prep<<<sd_blocks(n, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(xp, xDevIn, c->d_x, c->n1, c->d_sigmaPiCk, c->SP, c->n1c,
 			c->d_CCols, (int) c->sigmaCnt, wantAllPiCbarX ? c->d_piCbarX : nullptr, c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma,
 			c->d_sigmaPib, c->d_sigmaLam, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin,
 			c->d_tOmega, wantTerms ? c->d_termA : nullptr, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis);
