@@ -457,7 +457,13 @@ def gpu_arm(args):
         return ms_step, launches, {k: float(np.mean(v)) for k, v in split.items()}
 
     # ---- value: K cuts over resident tables ------------------------------------------------------------------------
-    sampler = ClockSampler(local)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    phys = local
+    try:                                                       # nvidia-smi counts physical GPUs, CUDA counts the visible ones
+        phys = int(vis.split(",")[local]) if vis else local
+    except (ValueError, IndexError):
+        phys = local
+    sampler = ClockSampler(phys)
     sampler.start()                                            # nvidia-smi takes a while to come up (longer with 8 GPUs): start it before the warm-up,
     for s in range(args.warmup):                               # count only the samples taken inside the timed regions
         one_cut(s, cut_dev)

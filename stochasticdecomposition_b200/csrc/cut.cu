@@ -1490,6 +1490,14 @@ static void sd_pick_chunks_for(int smCount, int tiles, int64_t basisCnt, int max
 	const double slots = (double) smCount * 3;
 	int64_t cmax = std::min<int64_t>(maxChunks, std::max<int64_t>(1, (basisCnt + 31) / 32));   // at least four load batches per chunk
 	cmax = std::min<int64_t>(cmax, std::max<int64_t>(1, (int64_t) ceil(32.0 * slots / tiles)));
+	// with many observation tiles and few bases, short chunks cost twice: every CTA pays its start-up for few rows, and the per-chunk
+	// partial maxima (24 bytes per chunk and observation, written by the sweep, read by the merge) grow with the chunk count.  Measured at
+	// 8 192 x 131 072 (profiles/r02_chunk_probe.jsonl): 55 chunks of 149 rows 1 310 us per cut, 10-19 chunks (430-820 rows) 1 260-1 267 us.
+	// So: at least ~600 rows per chunk as long as that still leaves two and a half waves of CTAs.
+	{
+		const int64_t cRows = std::max<int64_t>(1, basisCnt / 600);
+		if ((double) tiles * (double) cRows >= 2.5 * slots) cmax = std::min(cmax, cRows);
+	}
 	int64_t want = cmax;
 	for (int64_t cc = cmax; cc >= std::max<int64_t>(1, cmax / 2); cc--) {
 		const double w = tiles * (double) cc / slots;

@@ -87,6 +87,10 @@ def test_sweep_grid_plan_is_wave_aware():
     # the two cases that motivated the rule: 256 tiles must not get 7 chunks (4.04 waves); 10 tiles get one full wave, not 1.44
     assert api.plan_sweep_grid(148, 131072, 65536, 64)[2] != 7
     assert api.plan_sweep_grid(148, 5000, 5000, 64)[2] == 44
+    # round 2: many tiles, few bases (one GPU's share of the strong-scaling table): chunks of >= ~600 rows, not 55 chunks of 149 rows
+    t, cs, nc = api.plan_sweep_grid(148, 131072, 8192, 64)
+    assert 8 <= nc <= 13 and cs >= 600, (cs, nc)
+    assert api.plan_sweep_grid(148, 131072, 65536, 64)[2] >= 50                  # the bench table keeps its ~55 chunks of ~1 200 rows
 
 
 def test_sweep_family_plan():
