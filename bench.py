@@ -315,10 +315,15 @@ def multi_gpu_parity(api, rank, world, local, dist, duals=2048, obs_per_rank=409
     sh.total_obs = N
     whole = build(obsv, weights) if rank == 0 else None
     attach_library_nccl(api, sh.t, rank, world, dist)
-    sh.attach_peer_exchange()                    # both exchanges attached; sdgpu_set_collective picks one per cut
     rec = {"ranks": world, "duals": duals, "observations": N, "cuts_checked": 0, "max_rel_err": 0.0, "tolerance": 1e-9}
+    modes = [("nccl", 1), ("peer", 2)]
+    try:
+        sh.attach_peer_exchange()                # both exchanges attached; sdgpu_set_collective picks one per cut
+    except Exception as exc:                     # (raised on every rank or on none) no CUDA IPC between these processes: NCCL only
+        rec["peer"] = f"unavailable: {exc}"
+        modes = modes[:1]
     ok_all = True
-    for name, mode in (("nccl", 1), ("peer", 2)):
+    for name, mode in modes:
         sh.t.set_collective(mode)
         ok = True
         for variant in (0, 1):                   # automatic (bulk-copy ring at this size) and the load-based sweep
@@ -407,9 +412,15 @@ def gpu_arm(args):
         # record times both side by side)
         from stochasticdecomposition_b200.sharding import ShardedTables
         attach_library_nccl(api, t, rank, world, dist)
-        ShardedTables(t, rank, world).attach_peer_exchange()
+        have_peer = True
+        try:
+            ShardedTables(t, rank, world).attach_peer_exchange()
+        except Exception:                                     # consistent across ranks (see attach_peer_exchange)
+            have_peer = False
         chosen = args.collective if args.collective != "auto" else ("peer" if world >= 4 else "nccl")
         collectives = ["nccl", "peer"] if (strong or args.both_collectives) else [chosen]
+        if not have_peer:
+            collectives = ["nccl"]
         t.set_collective({"nccl": 1, "peer": 2}[collectives[0]])
 
     stream = torch.cuda.Stream()

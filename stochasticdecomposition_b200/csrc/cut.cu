@@ -147,7 +147,7 @@ struct SweepArgs {
 	const double *delta; int64_t Dcap; int Q;
 	const double *descA, *descC; const int32_t *descRow, *descWin;
 	int basisCnt, chunkSize, nChunks;
-	const uint8_t *mask; int64_t Bcap;
+	const uint32_t *mask; int64_t Bcap;     // bit-packed obsFeasible: [tile][Bcap][SD_MASK_WORDS]
 	const double *x; const int32_t *rvCOmCols;
 	double *partV; int32_t *partI; int64_t NP;
 	int rev;                        // load-based sweep: walk the chunk's bases in descending order (see k_sweep_ldg)
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typ
 				}
 				bool f0 = true, f1 = true;
 				if (HAS_MASK) {
-					uchar2 m = *reinterpret_cast<const uchar2 *>(a.mask + ((size_t) tile * a.Bcap + b) * SD_TILE_W + 2 * tid);
-					f0 = m.x != 0; f1 = m.y != 0;
+					const unsigned mw = a.mask[((size_t) tile * a.Bcap + b) * SD_MASK_WORDS + (tid >> 4)] >> ((2 * tid) & 31);   // 16 threads share a word
+					f0 = (mw & 1u) != 0; f1 = (mw & 2u) != 0;
 				}
 				if (win == 1) {
 					if (f0 && SD_BETTER(s0, oV0)) { oV0 = s0; oI0 = b; }
@@ -709,7 +709,7 @@ struct SweepGenArgs {
 	const double *sigmaPib, *piCbarX; const int32_t *sigmaLam;
 	const double *omega; int64_t NP; int rvOffset2;
 	int basisCnt, chunkSize, nChunks;
-	const uint8_t *mask; int64_t Bcap;
+	const uint32_t *mask; int64_t Bcap;     // bit-packed obsFeasible: [tile][Bcap][SD_MASK_WORDS]
 	const double *x; const int32_t *rvCOmCols;
 	double *partV; int32_t *partI;
 };
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general(SweepGenArgs
 		for (int h = 0; h < 2; h++) {
 			const int w = 2 * tid + h;
 			const size_t o = (size_t) tile * SD_TILE_W + w;
-			if (a.mask && !a.mask[((size_t) tile * a.Bcap + b) * SD_TILE_W + w]) continue;
+			if (a.mask && !((a.mask[((size_t) tile * a.Bcap + b) * SD_MASK_WORDS + (w >> 5)] >> (w & 31)) & 1u)) continue;
 			double arg = 0.0;
 			for (int t = ts; t < te; t++) {
 				const int s = a.tSigma[t], l = a.sigmaLam[s];
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general(SweepGenArgs
 // Term-linear TMA sweep for random-cost problems (rvdOmCnt > 0): multi-term bases (stocUpdate.c:165-176) and the obsFeasible
 // mask (:163).  k_cut_prep has flattened the bases of the chunk into a list of terms (sigma.pib, piCbarX, lambda row, multiplier
 // column, window, "last term of its basis").  The producer warp feeds a two-stage ring with one bulk copy per term -- the 1+Q
-// planes of that term's delta row for this tile -- plus, at a basis' last term, the 512 mask bytes of that basis; lane r of the
+// planes of that term's delta row for this tile -- plus, at a basis' last term, the 512 mask bits (64 bytes) of that basis; lane r of the
 // warp looks after term r of the stage, so the descriptor reads and the copies of a stage go out together.  The cost columns of
 // omega for this tile (the multipliers m_c) are copied once per CTA and stay resident in shared memory.  Consumers therefore
 // touch only shared memory: LDS.128 of the delta pair, LDS.128 of the multiplier pair, LDS.U16 of the mask pair, and the score
@@ -771,7 +771,7 @@ struct SweepTGArgs {
 	const double *termA, *termC; const int32_t *termRow, *termMeta, *termBasis, *bTermStart;
 	const double *omegaCost; int64_t NP; int nCost;       // omega rows rvOffset[2].. (cost coefficients), nCost of them
 	int basisCnt, chunkSize, nChunks;
-	const uint8_t *mask; int64_t Bcap;
+	const uint32_t *mask; int64_t Bcap;     // bit-packed obsFeasible: [tile][Bcap][SD_MASK_WORDS]
 	const double *x; const int32_t *rvCOmCols;
 	double *partV; int32_t *partI;
 	int rps, stages;                                      // terms per ring stage (1, 2, 4 or 8) and ring depth (2..4)
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_gen(SweepTGArgs a)
 	const int planes = 1 + a.Q, rps = a.rps, stages = a.stages;
 	const size_t rowDoubles = (size_t) planes * SD_TILE_W;
 	const uint32_t rowBytes = (uint32_t) (rowDoubles * 8);
-	const size_t slotBytes = (size_t) rowBytes + SD_TILE_W;                                // delta planes, then the mask bytes of the basis
+	const size_t slotBytes = (size_t) rowBytes + SD_MASK_WORDS * 4;                        // delta planes, then the 512 mask bits of the basis
 	const size_t stageBytes = (size_t) rps * slotBytes;
 	unsigned char *cost = smem_raw;                                                      // [nCost][512] doubles
 	unsigned char *ring = smem_raw + (size_t) a.nCost * TMA_ROW_BYTES;
@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_gen(SweepTGArgs a)
 			if (lane < rps && t < T1) { meta = a.termMeta[t]; row = a.termRow[t]; basis = a.termBasis[t]; }
 			const bool live = (meta & 3) != 0;
 			const bool wantMask = live && (meta & 4) && a.mask != nullptr;
-			uint32_t bytes = live ? rowBytes + (wantMask ? SD_TILE_W : 0) : 0;
+			uint32_t bytes = live ? rowBytes + (wantMask ? SD_MASK_WORDS * 4 : 0) : 0;
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
 			sd_mbar_wait(&empty[s], ph ^ 1);
@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_gen(SweepTGArgs a)
 			if (live) {
 				unsigned char *slot = ring + (size_t) s * stageBytes + (size_t) lane * slotBytes;
 				sd_bulk_g2s(slot, tileBase + (size_t) row * rowDoubles, rowBytes, &full[s]);
-				if (wantMask) sd_bulk_g2s(slot + rowBytes, a.mask + ((size_t) tile * a.Bcap + basis) * SD_TILE_W, SD_TILE_W, &full[s]);
+				if (wantMask) sd_bulk_g2s(slot + rowBytes, a.mask + ((size_t) tile * a.Bcap + basis) * SD_MASK_WORDS, SD_MASK_WORDS * 4, &full[s]);
 			}
 			if (++s == stages) { s = 0; ph ^= 1; }
 		}
@@ -884,8 +884,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_gen(SweepTGArgs a)
 			if (meta & 4) {                                                                // the basis is complete: stocUpdate.c:163,178-181
 				bool f0 = true, f1 = true;
 				if (a.mask) {
-					const uchar2 mk = reinterpret_cast<const uchar2 *>(slot + rowBytes)[tid];
-					f0 = mk.x != 0; f1 = mk.y != 0;
+					const unsigned mw = reinterpret_cast<const unsigned *>(slot + rowBytes)[tid >> 4] >> ((2 * tid) & 31);
+					f0 = (mw & 1u) != 0; f1 = (mw & 2u) != 0;
 				}
 				const int b = s_basis[j];
 				if ((meta & 3) == 1) {
@@ -1247,7 +1247,7 @@ __global__ void k_istar_one(SweepGenArgs a, int obs, int isNew, double *outV, in
 		const int win = a.descWin[b];
 		if (win == 0) continue;
 		if ((isNew && win != 2) || (!isNew && win != 1)) continue;
-		if (a.mask && !a.mask[((size_t) tile * a.Bcap + b) * SD_TILE_W + w]) continue;
+		if (a.mask && !((a.mask[((size_t) tile * a.Bcap + b) * SD_MASK_WORDS + (w >> 5)] >> (w & 31)) & 1u)) continue;
 		double arg = 0.0;
 		const int ts = a.bTermStart[b], te = a.bTermStart[b + 1];
 		for (int t = ts; t < te; t++) {
@@ -1582,7 +1582,7 @@ static int sd_launch_tma_q(sdgpu_ctx *c, dim3 grid, const SweepArgs &a, bool pdl
 // shared memory of k_sweep_tma_gen for a ring of `stages` x `rps` term slots
 static size_t sd_tma_gen_smem(const sdgpu_ctx *c, int rps, int stages) {
 	const int nCost = c->numRV - c->rvOffset[2];
-	return (size_t) nCost * TMA_ROW_BYTES + (size_t) stages * rps * ((size_t) (1 + c->Q) * TMA_ROW_BYTES + SD_TILE_W) + 10 * sizeof(uint64_t) +
+	return (size_t) nCost * TMA_ROW_BYTES + (size_t) stages * rps * ((size_t) (1 + c->Q) * TMA_ROW_BYTES + SD_MASK_WORDS * 4) + 10 * sizeof(uint64_t) +
 	       SW_BATCH * (sizeof(double2) + 2 * sizeof(int)) + 64 * sizeof(double);
 }
 
@@ -1593,7 +1593,7 @@ static size_t sd_tma_gen_smem(const sdgpu_ctx *c, int rps, int stages) {
 static bool sd_tma_gen_shape(const sdgpu_ctx *c, int *rps, int *stages) {
 	static int envRps = -1, envStages = -1;
 	if (envRps < 0) { const char *e = getenv("SDGPU_GEN_RPS"); envRps = e ? atoi(e) : 0; e = getenv("SDGPU_GEN_STAGES"); envStages = e ? atoi(e) : 0; }
-	const size_t smemPerSM = (size_t) 227 << 10, slot = (size_t) (1 + c->Q) * TMA_ROW_BYTES + SD_TILE_W;
+	const size_t smemPerSM = (size_t) 227 << 10, slot = (size_t) (1 + c->Q) * TMA_ROW_BYTES + SD_MASK_WORDS * 4;
 	if (envRps > 0 || envStages > 0) {
 		int r = envRps > 0 ? envRps : 4, st = envStages > 0 ? envStages : 2;
 		if ((r == 1 || r == 2 || r == 4 || r == 8) && st >= 2 && st <= 4 && sd_tma_gen_smem(c, r, st) + 1024 <= smemPerSM) { *rps = r; *stages = st; return true; }
@@ -1858,7 +1858,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		sd_count_launch(c);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evD, c->stream));
 		// algorithmic bytes of the sweep: delta stream + per-observation weight and iStar + per-basis descriptors
-		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * sweepRows * (int64_t) N + (c->rvd > 0 ? c->basisCnt * (int64_t) N : 0) + (int64_t) N * 8 + c->basisCnt * 16;
+		c->stats.last_sweep_bytes = (int64_t) 8 * (1 + c->Q) * sweepRows * (int64_t) N + (c->rvd > 0 ? c->basisCnt * (int64_t) N / 8 : 0) + (int64_t) N * 8 + c->basisCnt * 16;
 
 		MergeArgs m;
 		m.partV = c->d_partV; m.partI = c->d_partI; m.nChunks = nChunks; m.NP = c->NP; m.lex = lexMerge ? 1 : 0;

@@ -10,7 +10,7 @@
 //            all duals are back to back, so the sweep of one CTA is a single contiguous HBM stream, a new
 //            dual (row append) writes nTiles contiguous W*8-byte segments, and a new observation (column
 //            append) writes D strided doubles.
-//   mask     tiled [nTiles][Bcap][W] bytes, only when rvdOmCnt > 0 (obsFeasible, stoc.h:95)
+//   mask     tiled [nTiles][Bcap][W/32] 32-bit words, one BIT per (basis, observation), only when rvdOmCnt > 0 (obsFeasible, stoc.h:95)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -85,7 +85,7 @@ struct sdgpu_ctx {
 	double  *d_sigmaPib = nullptr, *d_sigmaPiCk = nullptr, *d_sigmaPiCr = nullptr;
 	int32_t *d_sigmaLam = nullptr, *d_sigmaCk = nullptr;
 	double  *d_delta = nullptr;
-	uint8_t *d_mask = nullptr;
+	uint32_t *d_mask = nullptr;      // bit-packed obsFeasible: [tile][Bcap][SD_MASK_WORDS]
 	int32_t *d_bCk = nullptr, *d_bFeas = nullptr, *d_bPhiLen = nullptr, *d_bTermStart = nullptr;
 	int32_t *d_tSigma = nullptr, *d_tOmega = nullptr;
 	SdDevState *d_state = nullptr;
@@ -158,7 +158,7 @@ struct sdgpu_ctx {
 	int     maxPhiLen = 0;
 	bool    anyInfeasibleBasis = false;
 	std::vector<SdHostBasis> basis;
-	std::vector<std::vector<uint8_t>> hostMask;   // [b][NP] only when rvd > 0
+	std::vector<std::vector<uint32_t>> hostMask;  // [b][NP / 32] bit-packed mirror of the basis' mask row (empty for infeasible bases), only when rvd > 0
 	// bases grouped by lambda row for the grouped sweep (several sigmas / bases on one lambda): host bookkeeping, device copies of the order
 	std::vector<int32_t> hostLam;                 // sigma -> lambda row (mirror of d_sigmaLam, refreshed on demand)
 	std::vector<int32_t> grpRowCount;             // bases per lambda row (single-term bases only)
@@ -210,9 +210,17 @@ __host__ __device__ static inline size_t sd_delta_off(int64_t Dcap, int Q, int64
 	int64_t t = o / SD_TILE_W, w = o % SD_TILE_W;
 	return (((size_t) t * Dcap + l) * (size_t) (1 + Q) + q) * SD_TILE_W + w;
 }
-__host__ __device__ static inline size_t sd_mask_off(int64_t Bcap, int64_t b, int64_t o) {
+// the mask word holding (basis b, observation o); the bit inside it is o % 32
+#define SD_MASK_WORDS (SD_TILE_W / 32)
+__host__ __device__ static inline size_t sd_mask_word(int64_t Bcap, int64_t b, int64_t o) {
 	int64_t t = o / SD_TILE_W, w = o % SD_TILE_W;
-	return ((size_t) t * Bcap + b) * SD_TILE_W + w;
+	return ((size_t) t * Bcap + b) * SD_MASK_WORDS + w / 32;
+}
+// host mirror of the mask (the basis de-duplication of stocUpdate.c:104 reads obsFeasible[b][omegaIdx] on the host)
+static inline bool sd_hm_get(const sdgpu_ctx *c, int64_t b, int64_t o) { return (c->hostMask[b][o >> 5] >> (o & 31)) & 1u; }
+static inline void sd_hm_set(sdgpu_ctx *c, int64_t b, int64_t o, bool v) {
+	uint32_t &w = c->hostMask[b][o >> 5];
+	w = v ? (w | (1u << (o & 31))) : (w & ~(1u << (o & 31)));
 }
 
 #ifdef __CUDACC__

@@ -243,16 +243,22 @@ __device__ __forceinline__ void sd_delta_cell_T(int Rb, int Q, const int32_t *__
 }
 
 #define DC_THREADS 128     // threads per CTA of the row / column kernels
-#define DC_BATCH   32      // operands a thread keeps in flight (DC_BATCH x DC_THREADS x 8 bytes of shared memory)
+#define DC_GROUP   16      // operands per cp.async group; ng groups (2 for small tables, 4 for large ones) rotate through shared memory, so
+                           // ng - 1 groups are in flight while the (sequential) adds of the oldest one run
+#define DC_SMEM(ng) ((size_t) (ng) * DC_GROUP * DC_THREADS * 8)
+__device__ __forceinline__ void sd_cp_async_wait_ng(int ng) {          // the oldest of ng committed groups has landed
+	if (ng >= 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+	else asm volatile("cp.async.wait_group 1;" ::: "memory");
+}
 
 // calcDelta case II stocUpdate.c:230-254: a new dual -> one delta row, one thread per observation (coalesced
 // reads of omega, contiguous W-segment writes).  The lambda row sits in shared memory.
 __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restrict__ lambda, int64_t LP, int R, const double *__restrict__ omega, int64_t NP,
 		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
-		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedRow) {
-	__shared__ double s_buf[DC_BATCH][DC_THREADS];
-	extern __shared__ double s_lam[];            // [Rb] the lambda entry each random RHS row meets (0.0 where it meets none), then [R] the row itself
-	double *s_row = s_lam + Rb;
+		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedRow, int ng) {
+	extern __shared__ double s_lam[];            // [Rb] the lambda entry each random RHS row meets (0.0 where it meets none), then [R] the row itself,
+	double *s_row = s_lam + Rb;                  // then [ng][DC_GROUP][DC_THREADS] operand groups
+	double *s_buf = s_row + R;
 	sd_pdl_wait();                               // (launched as the programmatic dependent of the find-or-append kernel)
 	int l = forcedRow >= 0 ? forcedRow : (st->newLambda ? st->lambdaIdx : -1);
 	if (l < 0) return;
@@ -262,20 +268,19 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restri
 	int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (o >= st->omegaCnt) return;
 	double s = 0.0;                                                                        // vXvSparse :244, index order
-	// two half-batches alternate: the loads of group g+1 are in flight while the (sequential) adds of group g run
-	constexpr int H = DC_BATCH / 2;
+	constexpr int H = DC_GROUP;
 	const int G = (Rb + H - 1) / H;
-	auto issue = [&](int g) {
-		const int j0 = g * H, n = min(H, Rb - j0);
-		for (int u = 0; u < n; u++) sd_cp_async8(&s_buf[(g & 1) * H + u][threadIdx.x], omega + (size_t) (j0 + u) * NP + o);
+	auto issue = [&](int g) {                    // (an empty group past the end keeps the group count uniform)
+		const int j0 = g * H, n = g < G ? min(H, Rb - j0) : 0;
+		for (int u = 0; u < n; u++) sd_cp_async8(&s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x], omega + (size_t) (j0 + u) * NP + o);
 		sd_cp_async_commit();
 	};
-	if (G > 0) issue(0);
+	for (int g = 0; g < ng - 1; g++) issue(g);
 	for (int g = 0; g < G; g++) {
-		if (g + 1 < G) issue(g + 1);
-		sd_cp_async_wait(g + 1 < G);
+		issue(g + ng - 1);
+		sd_cp_async_wait_ng(ng);
 		const int j0 = g * H, n = min(H, Rb - j0);
-		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_buf[(g & 1) * H + u][threadIdx.x], s_lam[j0 + u]));
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x], s_lam[j0 + u]));
 	}
 	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
 	out[0] = s;
@@ -286,10 +291,10 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restri
 // reads of lambda, strided 8-byte writes).  The observation sits in shared memory.
 __global__ void __launch_bounds__(DC_THREADS) k_delta_col(const double *__restrict__ lambda, int64_t LP, const double *__restrict__ omega, int64_t NP, int numRV,
 		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
-		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedCol) {
-	__shared__ double s_buf[DC_BATCH][DC_THREADS];
-	extern __shared__ double s_om[];             // [numRV] the observation, then [Rb] ints: position of each random RHS row inside a lambda
-	int32_t *s_pos = reinterpret_cast<int32_t *>(s_om + numRV);
+		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedCol, int ng) {
+	extern __shared__ double s_om[];             // [numRV] the observation, then [Rb] ints: position of each random RHS row inside a lambda,
+	int32_t *s_pos = reinterpret_cast<int32_t *>(s_om + numRV);                    // then [ng][DC_GROUP][DC_THREADS] operand groups
+	double *s_buf = reinterpret_cast<double *>(s_pos + ((Rb + 1) & ~1));
 	int o = forcedCol >= 0 ? forcedCol : (st->newOmega ? st->omegaIdx : -1);
 	if (o < 0) return;
 	for (int j = threadIdx.x; j < numRV; j += blockDim.x) s_om[j] = omega[(size_t) j * NP + o];
@@ -298,20 +303,19 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_col(const double *__restri
 	int64_t l = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (l >= st->lambdaCnt) return;
 	double s = 0.0;                                                                        // vXvSparse :218, index order
-	// two half-batches alternate: the loads of group g+1 are in flight while the (sequential) adds of group g run
-	constexpr int H = DC_BATCH / 2;
+	constexpr int H = DC_GROUP;
 	const int G = (Rb + H - 1) / H;
-	auto issue = [&](int g) {
-		const int j0 = g * H, n = min(H, Rb - j0);
-		for (int u = 0; u < n; u++) { const int p = s_pos[j0 + u]; if (p >= 0) sd_cp_async8(&s_buf[(g & 1) * H + u][threadIdx.x], lambda + (size_t) p * LP + l); }
+	auto issue = [&](int g) {                    // (an empty group past the end keeps the group count uniform)
+		const int j0 = g * H, n = g < G ? min(H, Rb - j0) : 0;
+		for (int u = 0; u < n; u++) { const int p = s_pos[j0 + u]; if (p >= 0) sd_cp_async8(&s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x], lambda + (size_t) p * LP + l); }
 		sd_cp_async_commit();
 	};
-	if (G > 0) issue(0);
+	for (int g = 0; g < ng - 1; g++) issue(g);
 	for (int g = 0; g < G; g++) {
-		if (g + 1 < G) issue(g + 1);
-		sd_cp_async_wait(g + 1 < G);
+		issue(g + ng - 1);
+		sd_cp_async_wait_ng(ng);
 		const int j0 = g * H, n = min(H, Rb - j0);
-		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_om[j0 + u], s_pos[j0 + u] >= 0 ? s_buf[(g & 1) * H + u][threadIdx.x] : 0.0));
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_om[j0 + u], s_pos[j0 + u] >= 0 ? s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x] : 0.0));
 	}
 	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
 	out[0] = s;
@@ -577,16 +581,32 @@ __global__ void k_record_pair(const SdDevState *st, int32_t *lamOut, int32_t *si
 
 __global__ void k_omega_bump(int32_t *w, int idx, int by) { w[idx] += by; }
 
-__global__ void k_mask_fill_row(uint8_t *mask, int64_t Bcap, int64_t b, int64_t NP, const uint8_t *flags, int64_t n, int fillAll) {
-	int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	if (o >= NP) return;
-	if (fillAll) mask[sd_mask_off(Bcap, b, o)] = 1;
-	else if (o < n) mask[sd_mask_off(Bcap, b, o)] = flags[o] != 0;
+// the mask is bit-packed: one thread per 32-bit word of the basis' row (observations 32 j .. 32 j + 31); flags beyond n keep their bits
+__global__ void k_mask_fill_row(uint32_t *mask, int64_t Bcap, int64_t b, int64_t NP, const uint8_t *flags, int64_t n, int fillAll) {
+	const int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, o0 = j * 32;
+	if (o0 >= NP) return;
+	uint32_t *w = mask + sd_mask_word(Bcap, b, o0);
+	if (fillAll) { *w = 0xffffffffu; return; }
+	if (o0 >= n) return;
+	uint32_t v = *w;
+	for (int i = 0; i < 32 && o0 + i < n; i++) v = flags[o0 + i] ? (v | (1u << i)) : (v & ~(1u << i));
+	*w = v;
 }
 
-__global__ void k_mask_fill_col(uint8_t *mask, int64_t Bcap, int64_t o, const uint8_t *flags, const int32_t *feas, int64_t nb) {
+// one observation, every feasible basis: thread b owns the word of (b, o) (no other thread of this launch touches it)
+__global__ void k_mask_fill_col(uint32_t *mask, int64_t Bcap, int64_t o, const uint8_t *flags, const int32_t *feas, int64_t nb) {
 	int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	if (b < nb && feas[b]) mask[sd_mask_off(Bcap, b, o)] = flags[b] != 0;
+	if (b < nb && feas[b]) {
+		uint32_t *w = mask + sd_mask_word(Bcap, b, o);
+		const uint32_t bit = 1u << (o & 31);
+		*w = flags[b] ? (*w | bit) : (*w & ~bit);
+	}
+}
+
+__global__ void k_mask_set_bit(uint32_t *mask, int64_t Bcap, int64_t b, int64_t o, int v) {
+	uint32_t *w = mask + sd_mask_word(Bcap, b, o);
+	const uint32_t bit = 1u << (o & 31);
+	*w = v ? (*w | bit) : (*w & ~bit);
 }
 
 // checkBasisFeasibility randCost.c:202-258 for one (basis, observation) pair, evaluated by a whole CTA: every row's
@@ -597,7 +617,7 @@ struct FeasArgs {
 	const int32_t *rvdOmCols; const char *senx; int rows, cols;
 	const int32_t *bPhiLen, *bTermStart, *bFeas, *tOmega;
 	const double *piDet, *phi, *gBar, *psi; const int8_t *cstat; const uint8_t *has;
-	double tol; uint8_t *mask; int64_t Bcap; uint8_t *flags;
+	double tol; uint32_t *mask; int64_t Bcap; uint8_t *flags;
 };
 
 __device__ __forceinline__ bool sd_pair_violates(const FeasArgs &a, int b, const double *s_val) {
@@ -631,7 +651,12 @@ __global__ void k_feas_obs(FeasArgs a, int obs) {
 	for (int j = threadIdx.x; j < a.rvd; j += blockDim.x) s_val[j] = a.omega[(size_t) (a.rvOffset2 + j) * a.NP + obs];
 	__syncthreads();
 	const int bad = __syncthreads_or(sd_pair_violates(a, b, s_val));
-	if (threadIdx.x == 0) { a.flags[b] = !bad; a.mask[sd_mask_off(a.Bcap, b, obs)] = !bad; }
+	if (threadIdx.x == 0) {                                  // this CTA is the only writer of the word of (b, obs) in this launch
+		a.flags[b] = !bad;
+		uint32_t *w = a.mask + sd_mask_word(a.Bcap, b, obs);
+		const uint32_t bit = 1u << (obs & 31);
+		*w = bad ? (*w & ~bit) : (*w | bit);
+	}
 }
 
 // a new basis against every stored observation (stocUpdate.c:123-126): one CTA per observation
@@ -641,7 +666,12 @@ __global__ void k_feas_basis(FeasArgs a, int b) {
 	for (int j = threadIdx.x; j < a.rvd; j += blockDim.x) s_val[j] = a.omega[(size_t) (a.rvOffset2 + j) * a.NP + obs];
 	__syncthreads();
 	const int bad = __syncthreads_or(sd_pair_violates(a, b, s_val));
-	if (threadIdx.x == 0) { a.flags[obs] = !bad; a.mask[sd_mask_off(a.Bcap, b, obs)] = !bad; }
+	if (threadIdx.x == 0) {                                  // 32 CTAs share a mask word: atomic bit update
+		a.flags[obs] = !bad;
+		uint32_t *w = a.mask + sd_mask_word(a.Bcap, b, obs);
+		const uint32_t bit = 1u << (obs & 31);
+		if (bad) atomicAnd(w, ~bit); else atomicOr(w, bit);
+	}
 }
 
 // ======================================================================================================
@@ -797,7 +827,7 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	SD_TRY(sd_alloc(&c->d_sigmaPiCr, (size_t) c->SP * c->n1cP));
 	SD_TRY(sd_alloc(&c->d_sigmaLam, (size_t) c->SP)); SD_TRY(sd_alloc(&c->d_sigmaCk, (size_t) c->SP));
 	SD_TRY(sd_alloc(&c->d_delta, (size_t) c->nTiles * caps->maxLambda * (1 + c->Q) * SD_TILE_W));
-	if (c->rvd > 0) SD_TRY(sd_alloc(&c->d_mask, (size_t) c->nTiles * caps->maxBasis * SD_TILE_W));
+	if (c->rvd > 0) SD_TRY(sd_alloc(&c->d_mask, (size_t) c->nTiles * caps->maxBasis * SD_MASK_WORDS));
 	SD_TRY(sd_alloc(&c->d_bCk, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bFeas, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bPhiLen, (size_t) c->BP));
 	SD_TRY(sd_alloc(&c->d_bTermStart, (size_t) c->BP + 1)); SD_TRY(sd_alloc(&c->d_tSigma, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_tOmega, (size_t) c->termCap));
 	SD_TRY(sd_alloc(&c->d_state, 1));
@@ -1020,11 +1050,17 @@ static int sd_launch_sigma(sdgpu_ctx *c, int iter, double tol, int64_t sigmaUppe
 	return 0;
 }
 
+// operand groups in flight per thread of the row / column kernels: large tables are bandwidth business (four groups, 64 KiB per CTA), small
+// ones are over before a deeper pipeline fills (two groups, 32 KiB)
+static inline int sd_dc_groups(int64_t cells) { return cells >= 16384 ? 4 : 2; }
+
 static int sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
 	if (omegaUpper <= 0) return 0;
-	if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->R + c->Rb) * 8, "k_delta_row")) return SDGPU_ERR;
-	k_delta_row<<<sd_blocks(omegaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->R + c->Rb) * 8, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
-			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow);
+	const int ng = sd_dc_groups(omegaUpper);
+	const size_t smem = (size_t) (c->R + c->Rb) * 8 + DC_SMEM(ng);
+	if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, 0, smem, "k_delta_row")) return SDGPU_ERR;
+	k_delta_row<<<sd_blocks(omegaUpper, DC_THREADS), DC_THREADS, smem, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow, ng);
 	SD_LAUNCH_OK("k_delta_row");
 	sd_count_launch(c);
 	return 0;
@@ -1032,9 +1068,11 @@ static int sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) 
 
 static int sd_launch_delta_col(sdgpu_ctx *c, int forcedCol, int64_t lambdaUpper) {
 	if (lambdaUpper <= 0) return 0;
-	if (sd_smem_optin(c, k_delta_col, SD_SMEM_DELTA_COL, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, "k_delta_col")) return SDGPU_ERR;
-	k_delta_col<<<sd_blocks(lambdaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
-			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol);
+	const int ng = sd_dc_groups(lambdaUpper);
+	const size_t smem = (size_t) c->numRV * 8 + (size_t) ((c->Rb + 1) & ~1) * 4 + DC_SMEM(ng);
+	if (sd_smem_optin(c, k_delta_col, SD_SMEM_DELTA_COL, 0, smem, "k_delta_col")) return SDGPU_ERR;
+	k_delta_col<<<sd_blocks(lambdaUpper, DC_THREADS), DC_THREADS, smem, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol, ng);
 	SD_LAUNCH_OK("k_delta_col");
 	sd_count_launch(c);
 	return 0;
@@ -1116,11 +1154,12 @@ static int sd_launch_update_fused(sdgpu_ctx *c, const double *hostPi, double mub
 	SD_LAUNCH_OK("k_update_fused");
 	sd_count_launch(c);
 	if (c->omegaCnt > 0) {                                 // :84-85, a no-op kernel unless the lambda was new
-		const size_t rs = (size_t) std::max(1, c->R + c->Rb) * 8;
-		if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, rs, "k_delta_row")) return SDGPU_ERR;
+		const int ng = sd_dc_groups(c->omegaCnt);
+		const size_t rs = (size_t) (c->R + c->Rb) * 8 + DC_SMEM(ng);
+		if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, 0, rs, "k_delta_row")) return SDGPU_ERR;
 		SD_CUDA(sd_launch(k_delta_row, dim3((unsigned) sd_blocks(c->omegaCnt, DC_THREADS)), dim3(DC_THREADS), rs, c->stream, c->pdl,
 				(const double *) c->d_lambda, c->LP, c->R, (const double *) c->d_omega, c->NP, c->Rb, c->Q, (const int32_t *) c->d_bLamPos, (const int32_t *) c->d_cLamPos,
-				(const int32_t *) c->d_cListStart, (const int32_t *) c->d_cList, c->d_delta, (int64_t) c->caps.maxLambda, (const SdDevState *) c->d_state, -1));
+				(const int32_t *) c->d_cListStart, (const int32_t *) c->d_cList, c->d_delta, (int64_t) c->caps.maxLambda, (const SdDevState *) c->d_state, -1, ng));
 		sd_count_launch(c);
 	}
 	return 0;
@@ -1280,9 +1319,9 @@ extern "C" int sdgpu_basis_append(sdgpu_ctx *c, int ck, int feasFlag, int phiLen
 		SD_CUDA(cudaStreamSynchronize(c->stream));
 	}
 	if (c->rvd > 0) {
-		c->hostMask.emplace_back(hb.feas ? std::vector<uint8_t>((size_t) c->NP, 1) : std::vector<uint8_t>());
+		c->hostMask.emplace_back(hb.feas ? std::vector<uint32_t>((size_t) c->NP / 32, 0xffffffffu) : std::vector<uint32_t>());
 		if (hb.feas) {
-			k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, b, c->NP, nullptr, 0, 1);
+			k_mask_fill_row<<<sd_blocks(c->NP / 32, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, b, c->NP, nullptr, 0, 1);
 			sd_count_launch(c);
 		}
 	}
@@ -1317,8 +1356,8 @@ extern "C" int sdgpu_basis_append_bulk(sdgpu_ctx *c, int64_t n, const int32_t *c
 		hb.sigmaIdx.assign(1, sigmaIdx[i]); hb.omegaIdx.assign(1, 0);
 		if (!hb.feas) c->anyInfeasibleBasis = true;
 		if (c->rvd > 0) {
-			c->hostMask.emplace_back(hb.feas ? std::vector<uint8_t>((size_t) c->NP, 1) : std::vector<uint8_t>());
-			if (hb.feas) { k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, b0 + i, c->NP, nullptr, 0, 1); sd_count_launch(c); }
+			c->hostMask.emplace_back(hb.feas ? std::vector<uint32_t>((size_t) c->NP / 32, 0xffffffffu) : std::vector<uint32_t>());
+			if (hb.feas) { k_mask_fill_row<<<sd_blocks(c->NP / 32, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, b0 + i, c->NP, nullptr, 0, 1); sd_count_launch(c); }
 		}
 		c->basis.push_back(std::move(hb));
 	}
@@ -1335,7 +1374,7 @@ extern "C" int sdgpu_basis_find_or_append(sdgpu_ctx *c, int retainBasis, int obs
 		if (obsIdx < 0 || obsIdx >= c->omegaCnt) return sdgpu_fail("basis_find_or_append: observation %d out of range", obsIdx);
 		for (int64_t b = 0; b < c->basisCnt; b++) {
 			const SdHostBasis &hb = c->basis[b];
-			bool feasAtObs = hb.feas && (c->rvd == 0 || c->hostMask[b][obsIdx]);
+			bool feasAtObs = hb.feas && (c->rvd == 0 || sd_hm_get(c, b, obsIdx));
 			if (hb.phiLen == phiLength && feasAtObs && std::equal(hb.sigmaIdx.begin(), hb.sigmaIdx.end(), sigmaIdx)) {
 				c->basis[b].weight++;
 				if (newBasisFlag) *newBasisFlag = 0;
@@ -1353,10 +1392,10 @@ extern "C" int sdgpu_basis_set_obs_feasible_row(sdgpu_ctx *c, int basisIdx, cons
 	SD_CUDA(cudaSetDevice(c->device));
 	if (sd_aux_reserve(c, (size_t) std::max<int64_t>(1, c->omegaCnt))) return SDGPU_ERR;
 	memcpy(c->h_aux, flags, (size_t) c->omegaCnt);                       // the kernel reads the flags through the mapped alias
-	k_mask_fill_row<<<sd_blocks(c->NP, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, basisIdx, c->NP, c->d_aux, c->omegaCnt, 0);
+	k_mask_fill_row<<<sd_blocks(c->NP / 32, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, basisIdx, c->NP, c->d_aux, c->omegaCnt, 0);
 	sd_count_launch(c);
 	SD_CUDA(cudaStreamSynchronize(c->stream));
-	for (int64_t o = 0; o < c->omegaCnt; o++) c->hostMask[basisIdx][o] = flags[o] != 0;
+	for (int64_t o = 0; o < c->omegaCnt; o++) sd_hm_set(c, basisIdx, o, flags[o] != 0);
 	return 0;
 }
 
@@ -1370,7 +1409,7 @@ extern "C" int sdgpu_basis_set_obs_feasible_col(sdgpu_ctx *c, int obsIdx, const 
 	k_mask_fill_col<<<sd_blocks(c->basisCnt, 256), 256, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, obsIdx, c->d_aux, c->d_bFeas, c->basisCnt);
 	sd_count_launch(c);
 	SD_CUDA(cudaStreamSynchronize(c->stream));
-	for (int64_t b = 0; b < c->basisCnt; b++) if (c->basis[b].feas) c->hostMask[b][obsIdx] = flags[b] != 0;
+	for (int64_t b = 0; b < c->basisCnt; b++) if (c->basis[b].feas) sd_hm_set(c, b, obsIdx, flags[b] != 0);
 	return 0;
 }
 
@@ -1380,10 +1419,11 @@ extern "C" int sdgpu_basis_set_obs_feasible(sdgpu_ctx *c, int basisIdx, int obsI
 	if (obsIdx < 0 || obsIdx >= c->caps.maxOmega) return sdgpu_fail("set_obs_feasible: bad observation %d", obsIdx);
 	if (c->rvd == 0) return 0;
 	SD_CUDA(cudaSetDevice(c->device));
-	uint8_t v = flag != 0;
-	SD_CUDA(cudaMemcpyAsync(c->d_mask + sd_mask_off(c->caps.maxBasis, basisIdx, obsIdx), &v, 1, cudaMemcpyHostToDevice, c->stream));
+	k_mask_set_bit<<<1, 1, 0, c->stream>>>(c->d_mask, c->caps.maxBasis, basisIdx, obsIdx, flag != 0);
+	SD_LAUNCH_OK("k_mask_set_bit");
+	sd_count_launch(c);
 	SD_CUDA(cudaStreamSynchronize(c->stream));
-	c->hostMask[basisIdx][obsIdx] = v;
+	sd_hm_set(c, basisIdx, obsIdx, flag != 0);
 	return 0;
 }
 
@@ -1523,8 +1563,8 @@ extern "C" int sdgpu_check_feasibility_obs(sdgpu_ctx *c, int obsIdx, double tol,
 	SD_CUDA(cudaMemcpyAsync(f.data(), c->d_fFlags, f.size(), cudaMemcpyDeviceToHost, c->stream));
 	SD_CUDA(cudaStreamSynchronize(c->stream));
 	for (int64_t b = 0; b < c->basisCnt; b++) {
-		if (f[b] == 2) { f[b] = c->basis[b].feas ? c->hostMask[b][obsIdx] : 0; continue; }   // untouched: keep what the mask holds
-		c->hostMask[b][obsIdx] = f[b];
+		if (f[b] == 2) { f[b] = c->basis[b].feas ? (uint8_t) sd_hm_get(c, b, obsIdx) : 0; continue; }   // untouched: keep what the mask holds
+		sd_hm_set(c, b, obsIdx, f[b] != 0);
 	}
 	if (flagsOut) memcpy(flagsOut, f.data(), f.size());
 	return 0;
@@ -1541,7 +1581,7 @@ extern "C" int sdgpu_check_feasibility_basis(sdgpu_ctx *c, int basisIdx, double 
 	std::vector<uint8_t> f((size_t) c->omegaCnt);
 	SD_CUDA(cudaMemcpyAsync(f.data(), c->d_fFlags, f.size(), cudaMemcpyDeviceToHost, c->stream));
 	SD_CUDA(cudaStreamSynchronize(c->stream));
-	for (int64_t o = 0; o < c->omegaCnt; o++) c->hostMask[basisIdx][o] = f[o];
+	for (int64_t o = 0; o < c->omegaCnt; o++) sd_hm_set(c, basisIdx, o, f[o] != 0);
 	if (flagsOut) memcpy(flagsOut, f.data(), f.size());
 	return 0;
 }

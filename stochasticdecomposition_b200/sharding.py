@@ -81,17 +81,22 @@ class ShardedTables:
         dist = self._dist()
         api = self.t.api
         raw = (C.c_char * 64)()
+        err = ""
         if api._fn("peer_export")(self.t.ctx, self.world, raw) != 0:
-            raise SdError("peer_export: " + api.error())
+            err = "peer_export: " + api.error()
         dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
         mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone().to(dev)
         allh = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allh, mine, group=self.group)
-        blob = b"".join(h.cpu().numpy().tobytes() for h in allh)
-        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
-        if api._fn("peer_attach")(self.t.ctx, self.world, self.rank, buf) != 0:
-            raise SdError("peer_attach: " + api.error())
-        dist.barrier(group=self.group)
+        dist.all_gather(allh, mine, group=self.group)             # every rank takes part, whether or not its own export worked
+        if not err:
+            blob = b"".join(h.cpu().numpy().tobytes() for h in allh)
+            buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+            if api._fn("peer_attach")(self.t.ctx, self.world, self.rank, buf) != 0:
+                err = "peer_attach: " + api.error()
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # all ranks or none: a half-attached exchange would leave kernels spinning
+        if int(ok.item()) != 1:
+            raise SdError("peer exchange unavailable on at least one rank" + (": " + err if err else ""))
         self.library_nccl = True                      # sd_cut reduces inside the library from now on
 
     # ---- tables -----------------------------------------------------------------------------------------
