@@ -1874,7 +1874,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		m.n1 = c->n1; m.CCols = c->d_CCols; m.qCols = c->rvd > 0 ? c->d_rvCOmCols : c->d_rvCols;       // cuts.c:157 vs :167
 		const bool peer = sd_use_peer(c);
 		m.partial = c->d_cutPartial; m.fuseNormalise = (peer || !sd_use_nccl(c)) && fuseNormalise; m.numSamples = numSamples;
-		m.peerRanks = peer ? c->peerRanks : 0; m.peerRank = c->peerRank; m.peerSeq = peer ? ++c->peerSeq : 0;
+		m.peerRanks = peer ? c->peerRanks : 0; m.peerRank = c->peerRank; m.peerSeq = peer ? c->peerSeq + 1 : 0;   // committed once the launch has succeeded
 		for (int r = 0; r < 16; r++) m.peerBufs[r] = peer && r < c->peerRanks ? c->d_peerBufs[r] : nullptr;
 		m.hostRes = c->d_cutRes; m.st = c->d_state;
 		c->cutFused = m.fuseNormalise != 0;
@@ -1891,6 +1891,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		// static: s_istar, s_w (2 x 2 KiB), s_red, s_mv (8 KiB), s_mi (4 KiB)
 		if (sd_smem_optin(c, k_cut_merge, SD_SMEM_MERGE, 17 * 1024, dyn, "k_cut_merge")) return SDGPU_ERR;
 		SD_CUDA(sd_launch(k_cut_merge, dim3((unsigned) ((N + mW - 1) / mW)), dim3(MG_THREADS), dyn, c->stream, c->pdl && !c->timing, m));
+		if (peer) c->peerSeq++;                   // this rank now takes part in exchange number peerSeq
 		sd_count_launch(c);
 		if (c->timing) SD_CUDA(cudaEventRecord(c->evE, c->stream));
 	}

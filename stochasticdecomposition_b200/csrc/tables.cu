@@ -243,22 +243,16 @@ __device__ __forceinline__ void sd_delta_cell_T(int Rb, int Q, const int32_t *__
 }
 
 #define DC_THREADS 128     // threads per CTA of the row / column kernels
-#define DC_GROUP   16      // operands per cp.async group; ng groups (2 for small tables, 4 for large ones) rotate through shared memory, so
-                           // ng - 1 groups are in flight while the (sequential) adds of the oldest one run
-#define DC_SMEM(ng) ((size_t) (ng) * DC_GROUP * DC_THREADS * 8)
-__device__ __forceinline__ void sd_cp_async_wait_ng(int ng) {          // the oldest of ng committed groups has landed
-	if (ng >= 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
-	else asm volatile("cp.async.wait_group 1;" ::: "memory");
-}
+#define DC_BATCH   32      // operands a thread keeps in flight (DC_BATCH x DC_THREADS x 8 bytes of shared memory)
 
 // calcDelta case II stocUpdate.c:230-254: a new dual -> one delta row, one thread per observation (coalesced
 // reads of omega, contiguous W-segment writes).  The lambda row sits in shared memory.
 __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restrict__ lambda, int64_t LP, int R, const double *__restrict__ omega, int64_t NP,
 		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
-		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedRow, int ng) {
-	extern __shared__ double s_lam[];            // [Rb] the lambda entry each random RHS row meets (0.0 where it meets none), then [R] the row itself,
-	double *s_row = s_lam + Rb;                  // then [ng][DC_GROUP][DC_THREADS] operand groups
-	double *s_buf = s_row + R;
+		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedRow) {
+	__shared__ double s_buf[DC_BATCH][DC_THREADS];
+	extern __shared__ double s_lam[];            // [Rb] the lambda entry each random RHS row meets (0.0 where it meets none), then [R] the row itself
+	double *s_row = s_lam + Rb;
 	sd_pdl_wait();                               // (launched as the programmatic dependent of the find-or-append kernel)
 	int l = forcedRow >= 0 ? forcedRow : (st->newLambda ? st->lambdaIdx : -1);
 	if (l < 0) return;
@@ -268,19 +262,20 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restri
 	int64_t o = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (o >= st->omegaCnt) return;
 	double s = 0.0;                                                                        // vXvSparse :244, index order
-	constexpr int H = DC_GROUP;
+	// two half-batches alternate: the loads of group g+1 are in flight while the (sequential) adds of group g run
+	constexpr int H = DC_BATCH / 2;
 	const int G = (Rb + H - 1) / H;
-	auto issue = [&](int g) {                    // (an empty group past the end keeps the group count uniform)
-		const int j0 = g * H, n = g < G ? min(H, Rb - j0) : 0;
-		for (int u = 0; u < n; u++) sd_cp_async8(&s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x], omega + (size_t) (j0 + u) * NP + o);
+	auto issue = [&](int g) {
+		const int j0 = g * H, n = min(H, Rb - j0);
+		for (int u = 0; u < n; u++) sd_cp_async8(&s_buf[(g & 1) * H + u][threadIdx.x], omega + (size_t) (j0 + u) * NP + o);
 		sd_cp_async_commit();
 	};
-	for (int g = 0; g < ng - 1; g++) issue(g);
+	if (G > 0) issue(0);
 	for (int g = 0; g < G; g++) {
-		issue(g + ng - 1);
-		sd_cp_async_wait_ng(ng);
+		if (g + 1 < G) issue(g + 1);
+		sd_cp_async_wait(g + 1 < G);
 		const int j0 = g * H, n = min(H, Rb - j0);
-		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x], s_lam[j0 + u]));
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_buf[(g & 1) * H + u][threadIdx.x], s_lam[j0 + u]));
 	}
 	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
 	out[0] = s;
@@ -291,10 +286,10 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_row(const double *__restri
 // reads of lambda, strided 8-byte writes).  The observation sits in shared memory.
 __global__ void __launch_bounds__(DC_THREADS) k_delta_col(const double *__restrict__ lambda, int64_t LP, const double *__restrict__ omega, int64_t NP, int numRV,
 		int Rb, int Q, const int32_t *__restrict__ bLamPos, const int32_t *__restrict__ cLamPos, const int32_t *__restrict__ cListStart,
-		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedCol, int ng) {
-	extern __shared__ double s_om[];             // [numRV] the observation, then [Rb] ints: position of each random RHS row inside a lambda,
-	int32_t *s_pos = reinterpret_cast<int32_t *>(s_om + numRV);                    // then [ng][DC_GROUP][DC_THREADS] operand groups
-	double *s_buf = reinterpret_cast<double *>(s_pos + ((Rb + 1) & ~1));
+		const int32_t *__restrict__ cList, double *__restrict__ delta, int64_t Dcap, const SdDevState *st, int forcedCol) {
+	__shared__ double s_buf[DC_BATCH][DC_THREADS];
+	extern __shared__ double s_om[];             // [numRV] the observation, then [Rb] ints: position of each random RHS row inside a lambda
+	int32_t *s_pos = reinterpret_cast<int32_t *>(s_om + numRV);
 	int o = forcedCol >= 0 ? forcedCol : (st->newOmega ? st->omegaIdx : -1);
 	if (o < 0) return;
 	for (int j = threadIdx.x; j < numRV; j += blockDim.x) s_om[j] = omega[(size_t) j * NP + o];
@@ -303,19 +298,20 @@ __global__ void __launch_bounds__(DC_THREADS) k_delta_col(const double *__restri
 	int64_t l = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (l >= st->lambdaCnt) return;
 	double s = 0.0;                                                                        // vXvSparse :218, index order
-	constexpr int H = DC_GROUP;
+	// two half-batches alternate: the loads of group g+1 are in flight while the (sequential) adds of group g run
+	constexpr int H = DC_BATCH / 2;
 	const int G = (Rb + H - 1) / H;
-	auto issue = [&](int g) {                    // (an empty group past the end keeps the group count uniform)
-		const int j0 = g * H, n = g < G ? min(H, Rb - j0) : 0;
-		for (int u = 0; u < n; u++) { const int p = s_pos[j0 + u]; if (p >= 0) sd_cp_async8(&s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x], lambda + (size_t) p * LP + l); }
+	auto issue = [&](int g) {
+		const int j0 = g * H, n = min(H, Rb - j0);
+		for (int u = 0; u < n; u++) { const int p = s_pos[j0 + u]; if (p >= 0) sd_cp_async8(&s_buf[(g & 1) * H + u][threadIdx.x], lambda + (size_t) p * LP + l); }
 		sd_cp_async_commit();
 	};
-	for (int g = 0; g < ng - 1; g++) issue(g);
+	if (G > 0) issue(0);
 	for (int g = 0; g < G; g++) {
-		issue(g + ng - 1);
-		sd_cp_async_wait_ng(ng);
+		if (g + 1 < G) issue(g + 1);
+		sd_cp_async_wait(g + 1 < G);
 		const int j0 = g * H, n = min(H, Rb - j0);
-		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_om[j0 + u], s_pos[j0 + u] >= 0 ? s_buf[((size_t) (g % ng) * H + u) * DC_THREADS + threadIdx.x] : 0.0));
+		for (int u = 0; u < n; u++) s = __dadd_rn(s, __dmul_rn(s_om[j0 + u], s_pos[j0 + u] >= 0 ? s_buf[(g & 1) * H + u][threadIdx.x] : 0.0));
 	}
 	double *out = delta + sd_delta_off(Dcap, Q, l, 0, o);
 	out[0] = s;
@@ -1050,17 +1046,11 @@ static int sd_launch_sigma(sdgpu_ctx *c, int iter, double tol, int64_t sigmaUppe
 	return 0;
 }
 
-// operand groups in flight per thread of the row / column kernels: large tables are bandwidth business (four groups, 64 KiB per CTA), small
-// ones are over before a deeper pipeline fills (two groups, 32 KiB)
-static inline int sd_dc_groups(int64_t cells) { return cells >= 16384 ? 4 : 2; }
-
 static int sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
 	if (omegaUpper <= 0) return 0;
-	const int ng = sd_dc_groups(omegaUpper);
-	const size_t smem = (size_t) (c->R + c->Rb) * 8 + DC_SMEM(ng);
-	if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, 0, smem, "k_delta_row")) return SDGPU_ERR;
-	k_delta_row<<<sd_blocks(omegaUpper, DC_THREADS), DC_THREADS, smem, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
-			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow, ng);
+	if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->R + c->Rb) * 8, "k_delta_row")) return SDGPU_ERR;
+	k_delta_row<<<sd_blocks(omegaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->R + c->Rb) * 8, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow);
 	SD_LAUNCH_OK("k_delta_row");
 	sd_count_launch(c);
 	return 0;
@@ -1068,11 +1058,9 @@ static int sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) 
 
 static int sd_launch_delta_col(sdgpu_ctx *c, int forcedCol, int64_t lambdaUpper) {
 	if (lambdaUpper <= 0) return 0;
-	const int ng = sd_dc_groups(lambdaUpper);
-	const size_t smem = (size_t) c->numRV * 8 + (size_t) ((c->Rb + 1) & ~1) * 4 + DC_SMEM(ng);
-	if (sd_smem_optin(c, k_delta_col, SD_SMEM_DELTA_COL, 0, smem, "k_delta_col")) return SDGPU_ERR;
-	k_delta_col<<<sd_blocks(lambdaUpper, DC_THREADS), DC_THREADS, smem, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
-			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol, ng);
+	if (sd_smem_optin(c, k_delta_col, SD_SMEM_DELTA_COL, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, "k_delta_col")) return SDGPU_ERR;
+	k_delta_col<<<sd_blocks(lambdaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol);
 	SD_LAUNCH_OK("k_delta_col");
 	sd_count_launch(c);
 	return 0;
@@ -1154,12 +1142,11 @@ static int sd_launch_update_fused(sdgpu_ctx *c, const double *hostPi, double mub
 	SD_LAUNCH_OK("k_update_fused");
 	sd_count_launch(c);
 	if (c->omegaCnt > 0) {                                 // :84-85, a no-op kernel unless the lambda was new
-		const int ng = sd_dc_groups(c->omegaCnt);
-		const size_t rs = (size_t) (c->R + c->Rb) * 8 + DC_SMEM(ng);
-		if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, 0, rs, "k_delta_row")) return SDGPU_ERR;
+		const size_t rs = (size_t) std::max(1, c->R + c->Rb) * 8;
+		if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, rs, "k_delta_row")) return SDGPU_ERR;
 		SD_CUDA(sd_launch(k_delta_row, dim3((unsigned) sd_blocks(c->omegaCnt, DC_THREADS)), dim3(DC_THREADS), rs, c->stream, c->pdl,
 				(const double *) c->d_lambda, c->LP, c->R, (const double *) c->d_omega, c->NP, c->Rb, c->Q, (const int32_t *) c->d_bLamPos, (const int32_t *) c->d_cLamPos,
-				(const int32_t *) c->d_cListStart, (const int32_t *) c->d_cList, c->d_delta, (int64_t) c->caps.maxLambda, (const SdDevState *) c->d_state, -1, ng));
+				(const int32_t *) c->d_cListStart, (const int32_t *) c->d_cList, c->d_delta, (int64_t) c->caps.maxLambda, (const SdDevState *) c->d_state, -1));
 		sd_count_launch(c);
 	}
 	return 0;

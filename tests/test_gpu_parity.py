@@ -452,3 +452,28 @@ def test_multi_tile_both_sweep_directions():
     for pe, c in ((1, cuts[0]), (0, cuts[3])):
         pc = port.sd_cut(x, int(w.sum()), pe, 0.0)
         assert np.array_equal(pc.iStar, c.iStar)
+
+
+def test_instrumentation_and_collective_selection_errors():
+    """sdgpu_fp64_peak returns plausible rates (separately rounded multiply + add below the fused rate); sdgpu_set_collective refuses an
+    exchange that is not attached; the per-phase split of a cut is reported when timing is on"""
+    api = sd.load_library()
+    mul_add, fma = api.fp64_peak(0, 2)
+    assert 1e12 < mul_add < fma < 1e14, (mul_add, fma)
+    prob = problem_for("pgp2")
+    t = api.create(prob, Caps(8, 8, 8, 8, 1))
+    for mode in (1, 2):
+        with pytest.raises(sd.SdError):
+            t.set_collective(mode)
+    t.set_collective(0)
+    t.set_timing(True)
+    rng = np.random.default_rng(0)
+    ob = rng.normal(0, 1, prob.numRV + 1); ob[0] = 0
+    pi = rng.uniform(-1, 1, prob.rows + 1); pi[0] = 0
+    oi, onew = t.calc_omega(ob, 1e-3)
+    t.stochastic_updates(oi, onew, pi, 0.0, 1, 1e-3)
+    x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
+    assert t.sd_cut(x, 1, 1, 0.0) is not None
+    st = t.stats()
+    assert st["last_cut_ms"] > 0 and st["last_sweep_ms"] > 0 and st["last_merge_ms"] > 0 and st["last_collective_ms"] >= 0
+    assert abs(st["last_prep_ms"] + st["last_sweep_ms"] + st["last_merge_ms"] + st["last_collective_ms"] - st["last_cut_ms"]) < 0.05 * st["last_cut_ms"] + 1e-3
