@@ -322,6 +322,9 @@ int  sdgpu_plan_sweep_kind(int rvCOmCnt, int rvdOmCnt, int rvbOmCnt, int maxPhiL
  * operations per pair; the library never fuses them) and, for comparison, DFMA flops.  Best of `reps` launches.
  * The roofline denominator of the FP64-bound kernels (recompute sweep, bulk delta build). */
 int  sdgpu_fp64_peak(int device, int reps, double *mulAddOpsPerSec, double *fmaFlopsPerSec);
+/* instrumentation: median wall time (us) of `launches` empty kernels in a row followed by mode 0: a stream synchronise, mode 1: the host
+ * spinning on a word the last kernel writes into mapped pinned memory -- the floor under every synchronous call of this library */
+int  sdgpu_launch_roundtrip(int device, int mode, int launches, int reps, double *medianUs);
 /* run subsequent work on an existing CUDA stream (cudaStream_t) instead of the context's own */
 int  sdgpu_set_stream(sdgpu_ctx *ctx, void *cudaStream);
 

@@ -234,7 +234,7 @@ class Api:
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
             "get_stats": (i, [vp, C.POINTER(CStats)]),
             "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]), "set_collective": (i, [vp, i]),
-            "fp64_peak": (i, [i, i, c_f64p, c_f64p]),
+            "fp64_peak": (i, [i, i, c_f64p, c_f64p]), "launch_roundtrip": (i, [i, i, i, i, c_f64p]),
             "plan_sweep_grid": (i, [i, i64, i64, i, c_intp, c_intp, c_intp]),
             "plan_sweep_kind": (i, [i, i, i, i, i, i, i, i64, i64, i64, i64, i, c_intp]),
         }
@@ -266,6 +266,13 @@ class Api:
         if self._fn("fp64_peak")(device, reps, C.byref(a), C.byref(b)) != 0:
             raise SdError(self.error())
         return a.value, b.value
+
+    def launch_roundtrip(self, mode: int, launches: int = 1, reps: int = 200, device: int = 0) -> float:
+        """median wall microseconds of `launches` empty kernels + a stream synchronise (mode 0) or a host spin on mapped memory (mode 1)"""
+        a = C.c_double(0.0)
+        if self._fn("launch_roundtrip")(device, mode, launches, reps, C.byref(a)) != 0:
+            raise SdError(self.error())
+        return a.value
 
     def error(self) -> str:
         fn = self._fn("last_error")

@@ -52,3 +52,51 @@ extern "C" int sdgpu_fp64_peak(int device, int reps, double *mulAddOpsPerSec, do
 	*mulAddOpsPerSec = best[0]; *fmaFlopsPerSec = best[1];
 	return 0;
 }
+
+// ---- the floor under every synchronous call: launch -> kernel start -> completion seen by the host ----------------------------
+__global__ void k_roundtrip(volatile unsigned *flag, unsigned seq, int chain) {
+	if (chain) sd_pdl_wait();
+	if (flag && threadIdx.x == 0) { __threadfence_system(); *flag = seq; }
+}
+
+#include <chrono>
+#include <vector>
+#include <algorithm>
+// median wall time in us of `launches` empty kernels in a row (chained with programmatic dependent launch when launches > 1) followed by
+//   mode 0: cudaStreamSynchronize        mode 1: the host spinning on a word the last kernel writes into mapped pinned memory
+extern "C" int sdgpu_launch_roundtrip(int device, int mode, int launches, int reps, double *medianUs) {
+	if (!medianUs || launches < 1 || reps < 1) return sdgpu_fail("launch_roundtrip: bad argument");
+	SD_CUDA(cudaSetDevice(device));
+	cudaStream_t st;
+	SD_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	unsigned *h = nullptr, *d = nullptr;
+	SD_CUDA(cudaHostAlloc((void **) &h, 64, cudaHostAllocMapped));
+	SD_CUDA(cudaHostGetDevicePointer((void **) &d, h, 0));
+	*h = 0;
+	std::vector<double> us;
+	int rc = 0;
+	for (int r = 0; r < reps + 8 && rc == 0; r++) {
+		const unsigned seq = (unsigned) r + 1;
+		const auto t0 = std::chrono::steady_clock::now();
+		for (int l = 0; l < launches && rc == 0; l++) {
+			const bool last = l == launches - 1;
+			if (sd_launch(k_roundtrip, dim3(1), dim3(32), 0, st, l > 0, (volatile unsigned *) (last && mode == 1 ? d : nullptr), seq, l > 0 ? 1 : 0) != cudaSuccess)
+				rc = sdgpu_fail("launch_roundtrip: launch failed");
+		}
+		if (rc) break;
+		if (mode == 1) {
+			long spins = 0;
+			while (*(volatile unsigned *) h != seq)
+				if ((++spins & 0xfffff) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;
+		}
+		else if (cudaStreamSynchronize(st) != cudaSuccess) rc = sdgpu_fail("launch_roundtrip: sync failed");
+		const auto t1 = std::chrono::steady_clock::now();
+		if (r >= 8) us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+		if (mode == 1) cudaStreamSynchronize(st);
+	}
+	cudaStreamDestroy(st); cudaFreeHost(h);
+	if (rc) return rc;
+	std::sort(us.begin(), us.end());
+	*medianUs = us[us.size() / 2];
+	return 0;
+}

@@ -88,6 +88,12 @@ if __name__ == "__main__":
     shapes = [(1000, 1000, 86, 89), (5000, 5000, 86, 89), (7500, 5000, 118, 121)]
     if "--quick" in sys.argv:
         shapes = shapes[1:2]
+    if "--floor" in sys.argv or "--quick" not in sys.argv:
+        api = sd.load_library()
+        floor = {f"{l}_launch_{'poll' if m else 'sync'}_us": round(api.launch_roundtrip(m, l, 400), 2) for l in (1, 2, 3) for m in (0, 1)}
+        print(json.dumps({"launch_roundtrip_floor": floor}), flush=True)
+        if "--floor" in sys.argv:
+            sys.exit(0)
     combos = [(0, 0, 0, 0, 0), (1, 0, 0, 0, 0), (0, 1, 0, 0, 0), (1, 1, 0, 0, 0), (1, 1, 1, 0, 0)]
     for D, N, rv, n1 in shapes:
         base = None
