@@ -83,14 +83,15 @@ __device__ __forceinline__ void sd_block_sum4(double (&v)[4], double *s_red) {
 // sum_k col[k*stride] * s_x[k], left to right from 0.0 with separate multiply and add (vXv, cuts.c:106); the loads of a
 // batch of 32 are issued together (past the end: the last element again, not added) so the chain of dependent adds does not
 // also serialise the memory latency -- three round trips for the 89 columns of ssn instead of twelve
+template <int BATCH = 32>
 __device__ __forceinline__ double sd_dot_strided(const double *__restrict__ col, size_t stride, const double *s_x, int n) {
 	double acc = 0.0;
-	for (int k = 0; k < n; k += 32) {
-		double v[32];
+	for (int k = 0; k < n; k += BATCH) {
+		double v[BATCH];
 #pragma unroll
-		for (int u = 0; u < 32; u++) v[u] = col[(size_t) min(k + u, n - 1) * stride];
+		for (int u = 0; u < BATCH; u++) v[u] = col[(size_t) min(k + u, n - 1) * stride];
 #pragma unroll
-		for (int u = 0; u < 32; u++) if (k + u < n) acc = __dadd_rn(acc, __dmul_rn(v[u], s_x[k + u]));
+		for (int u = 0; u < BATCH; u++) if (k + u < n) acc = __dadd_rn(acc, __dmul_rn(v[u], s_x[k + u]));
 	}
 	return acc;
 }
@@ -118,7 +119,7 @@ __global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, doubl
 	if (piCbarXAll && i < sigmaCnt) piCbarXAll[i] = sd_dot_strided(piCk + i, (size_t) SP, s_x, n1c);
 	if (i < basisCnt) {
 		const int s = tSigma[bTermStart[i]];
-		const double acc = sd_dot_strided(piCk + s, (size_t) SP, s_x, n1c);
+		const double acc = sd_dot_strided<64>(piCk + s, (size_t) SP, s_x, n1c);      // ssn's 89 columns in two round trips
 		const int ck = bCk[i];
 		int win = 0;
 		if (bFeas[i]) {
@@ -968,6 +969,25 @@ __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, c
 	}
 }
 
+// both windows at once (pi_eval): the new window's maxima sit `winOff` elements after the old window's; sixteen loads in flight
+__device__ __forceinline__ void sd_merge_chunks2(const double *__restrict__ pv, const int32_t *__restrict__ pi, size_t winOff, int c0, int c1, int64_t NP,
+		bool lex, double &oV, int &oI, double &nV, int &nI) {
+	for (int c = c0; c < c1; c += 8) {
+		double v[8], w[8]; int ix[8], iw[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			const size_t at = (size_t) min(c + u, c1 - 1) * NP;
+			v[u] = __ldcg(pv + at); ix[u] = __ldcg(pi + at);
+			w[u] = __ldcg(pv + winOff + at); iw[u] = __ldcg(pi + winOff + at);
+		}
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			if (v[u] > oV || (lex && v[u] == oV && ix[u] >= 0 && ix[u] < oI)) { oV = v[u]; oI = ix[u]; }
+			if (w[u] > nV || (lex && w[u] == nV && iw[u] >= 0 && iw[u] < nI)) { nV = w[u]; nI = iw[u]; }
+		}
+	}
+}
+
 // Tail of a cut, run by one block with the un-normalised vector [alpha, beta[1..n1], cummOld, cummAll, missing] in shared memory:
 // optional all-reduce over NVLink peer memory, then cuts.c:184-188 and the hand-over to the host.
 //   peer exchange: push this rank's sums into every rank's slot, raise the flags, wait for everyone's flag, add the slots in
@@ -1048,8 +1068,8 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 	SD_PHASE(0);
 	if (valid) {
 		const int cpl = (a.nChunks + L - 1) / L, c0 = lane * cpl, c1 = min(a.nChunks, c0 + cpl);
-		sd_merge_chunks(a.partV + o, a.partI + o, c0, c1, a.NP, a.lex != 0, oldV, oldI);
-		if (a.pi_eval) sd_merge_chunks(a.partV + (size_t) a.nChunks * a.NP + o, a.partI + (size_t) a.nChunks * a.NP + o, c0, c1, a.NP, a.lex != 0, newV, newI);
+		if (!a.pi_eval) sd_merge_chunks(a.partV + o, a.partI + o, c0, c1, a.NP, a.lex != 0, oldV, oldI);
+		else sd_merge_chunks2(a.partV + o, a.partI + o, (size_t) a.nChunks * a.NP, c0, c1, a.NP, a.lex != 0, oldV, oldI, newV, newI);
 	}
 	SD_PHASE(10);
 	if (L > 1) {
@@ -1140,12 +1160,12 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 			double acc = 0.0;
 			int w = w0;
 			if (!a.randCost) {
-				for (; w + 8 <= w1; w += 8) {                    // gathers of a batch issued together, adds still in observation order
-					double v[8];
+				for (; w < w1; w += 16) {                        // gathers of a batch issued together (the last batch predicated, not
+					double v[16];                                // walked one dependent load at a time), adds still in observation order
 #pragma unroll
-					for (int u = 0; u < 8; u++) { const int is = s_istar[w + u]; v[u] = is >= 0 ? a.sigmaPiCr[(size_t) is * a.n1cP + k] : 0.0; }
+					for (int u = 0; u < 16; u++) { const int is = w + u < w1 ? s_istar[w + u] : -1; v[u] = is >= 0 ? a.sigmaPiCr[(size_t) is * a.n1cP + k] : 0.0; }
 #pragma unroll
-					for (int u = 0; u < 8; u++) if (s_istar[w + u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], (double) s_w[w + u]));
+					for (int u = 0; u < 16; u++) if (w + u < w1 && s_istar[w + u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], (double) s_w[w + u]));
 				}
 			}
 			for (; w < w1; w++) {
@@ -1190,14 +1210,13 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 		for (int p = tid % kpP; g < groupsP && p < a.P; p += kpP) {
 			double acc = 0.0;
 			int t = t0;
-			for (; t + 8 <= t1; t += 8) {
-				double v[8];
+			for (; t < t1; t += 16) {                            // sixteen loads in flight, the last batch predicated
+				double v[16];
 #pragma unroll
-				for (int u = 0; u < 8; u++) v[u] = __ldcg(a.tilePart + (size_t) (t + u) * a.P + p);
+				for (int u = 0; u < 16; u++) v[u] = t + u < t1 ? __ldcg(a.tilePart + (size_t) (t + u) * a.P + p) : 0.0;
 #pragma unroll
-				for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, v[u]);
+				for (int u = 0; u < 16; u++) if (t + u < t1) acc = __dadd_rn(acc, v[u]);
 			}
-			for (; t < t1; t++) acc = __dadd_rn(acc, __ldcg(a.tilePart + (size_t) t * a.P + p));
 			s_grp[g * a.P + p] = acc;
 		}
 	}
