@@ -494,15 +494,16 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS) k_sweep_tma(SweepArgs a
 
 // The RHS-only ring for tables in which several bases share a lambda row (calcSigma appends a sigma -- and stochasticUpdates a basis
 // -- whenever pi x bBar or pi x Cbar differ, while the entries on the random rows, the lambda, are already stored: stocUpdate.c:299-318).
-// The host keeps the bases sorted by (lambda row, basis index); the sweep walks that list, and an entry whose row equals its
-// predecessor's inside the same 8-entry stage re-uses the predecessor's ring slot instead of copying the row again: the delta stream
-// shrinks from one row per basis towards one row per distinct lambda (SURVEY.md section 8d counts the algorithmic bytes per distinct
-// row).  The walk is no longer in basis order, so the running maximum is kept lexicographically -- greater score, or equal score and
-// lower basis index -- which is what the strict '>' of stocUpdate.c:178 yields in basis order.
+// The host keeps the bases sorted by (lambda row, basis index) and numbers the groups (= distinct rows) densely; the sweep walks that
+// list and copies every distinct row of a chunk ONCE: the delta stream shrinks from one row per basis to one row per distinct lambda
+// (SURVEY.md section 8d counts the algorithmic bytes per distinct row).  The walk is no longer in basis order, so the running maximum
+// is kept lexicographically -- greater score, or equal score and lower basis index -- which is what the strict '>' of
+// stocUpdate.c:178 yields in basis order.
 struct SweepGrpArgs {
 	const double *delta; int64_t Dcap;
 	const double *descA, *descC; const int32_t *descWin;
-	const int32_t *entBasis, *entRow;                    // the bases sorted by (lambda row, basis index) and the row of each
+	const int32_t *entBasis;                             // the bases sorted by (lambda row, basis index)
+	const int32_t *entGroup, *groupRow;                  // dense group number of each entry (one group per distinct row), row of each group
 	int basisCnt, chunkSize, nChunks;
 	double *partV; int32_t *partI; int64_t NP;
 };
@@ -513,95 +514,168 @@ struct SweepGrpArgs {
 // greater score, or equal score and lower basis index; the equal case is rare, so the common path is one compare
 #define SD_LEX_UPDATE(sc, bb, bestV, bestI) do { if ((sc) >= (bestV)) { if ((sc) > (bestV) || (bb) < (bestI)) { (bestV) = (sc); (bestI) = (bb); } } } while (0)
 
-__global__ void __launch_bounds__(TMA_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a) {
+// Shape of the kernel (round 2; the round-1 form had eight ENTRIES per stage and two observations per thread and stopped at ~1.4e12
+// pairs/s for every group size: with g bases per row a stage held only 8/g rows, and it spent ~18 instructions per pair, issue slots
+// 75-83 % -- profiles/r02_sweep_grp_ncu.md):
+//   * a ring stage is eight distinct ROWS with however many entries share them: inside a chunk, group k lives in slot k mod 16 and
+//     belongs to stage k / 8; the producer warp copies rows groupRow[G0 + 8 s .. + 7], a consumer warp moves on when an entry's stage
+//     number changes;
+//   * 128 consumers per CTA, thread t owning observations 2t, 2t+1, 256+2t, 257+2t of the tile (two conflict-free LDS.128 per entry),
+//     so the per-entry bookkeeping pays for four scores; window, slot offset, basis index and stage of an entry come pre-decoded in one
+//     16-byte broadcast load, and the descriptors of the next 256 entries are fetched into registers while the current batch is consumed;
+//   * four entries at a time, sixteen independent score chains per thread, go through one filter: a running maximum only grows, so a
+//     score below the maximum as it stood before the batch cannot win after any of its entries; only when some lane of the warp has
+//     a candidate are the four entries applied one after the other, exactly.
+// 4 096 rows x 131 072 observations: 1.72 / 1.98 / 1.82-2.2 / 1.9-2.3e12 pairs/s at 2 / 3 / 4 / 8 bases per row (6.9 TB/s per distinct
+// row at 2 = the HBM roof; before: 1.54 / 1.60 / 1.42 / 1.35e12) -- profiles/r02_group_probe.jsonl, r02_sweep_grp_v2_ncu.md.
+#define GRP_CONSUMERS 128
+#define GRP_THREADS (GRP_CONSUMERS + 32)
+
+#define SD_LEX_UPDATE4_RARE(sc, bb, V, I) do { \
+		const bool h0_ = (sc)[0] >= (V)[0], h1_ = (sc)[1] >= (V)[1], h2_ = (sc)[2] >= (V)[2], h3_ = (sc)[3] >= (V)[3]; \
+		if (__any_sync(0xffffffffu, h0_ || h1_ || h2_ || h3_)) { \
+			if (h0_ && ((sc)[0] > (V)[0] || (bb) < (I)[0])) { (V)[0] = (sc)[0]; (I)[0] = (bb); } \
+			if (h1_ && ((sc)[1] > (V)[1] || (bb) < (I)[1])) { (V)[1] = (sc)[1]; (I)[1] = (bb); } \
+			if (h2_ && ((sc)[2] > (V)[2] || (bb) < (I)[2])) { (V)[2] = (sc)[2]; (I)[2] = (bb); } \
+			if (h3_ && ((sc)[3] > (V)[3] || (bb) < (I)[3])) { (V)[3] = (sc)[3]; (I)[3] = (bb); } \
+		} } while (0)
+
+__global__ void __launch_bounds__(GRP_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	double *ring = reinterpret_cast<double *>(smem_raw);                                   // [stage][slot][512]
+	unsigned char *ring = smem_raw;                                                        // [stage][slot][4 KiB]
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES);
 	uint64_t *empty = full + GRP_STAGES;
 	double2 *s_ac = reinterpret_cast<double2 *>(empty + GRP_STAGES);                        // [SW_BATCH] (sigma.pib, piCbarX)
-	int *s_meta = reinterpret_cast<int *>(s_ac + SW_BATCH);                                // [SW_BATCH] window | leader slot << 2 | basis << 5
-	int *s_row = s_meta + SW_BATCH;                                                        // [SW_BATCH] lambda row of the entry
+	int4 *s_m = reinterpret_cast<int4 *>(s_ac + SW_BATCH);                                 // [SW_BATCH] (window, slot byte offset, basis, stage)
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	const int e0 = chunk * a.chunkSize, e1 = min(a.basisCnt, e0 + a.chunkSize);
-	const int nEnt = e1 - e0, nIter = (nEnt + GRP_ROWS - 1) / GRP_ROWS;
+	const int nEnt = e1 - e0;
 	const double *tileBase = a.delta + (size_t) tile * a.Dcap * SD_TILE_W;
 	if (tid == 0) {
-		for (int s = 0; s < GRP_STAGES; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], TMA_CONSUMERS / 32); }
+		for (int s = 0; s < GRP_STAGES; s++) { sd_mbar_init(&full[s], 1); sd_mbar_init(&empty[s], GRP_CONSUMERS / 32); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
+	// sorted entries: first and last group of the chunk (an empty chunk still writes its "nothing found" maxima)
+	const int G0 = nEnt > 0 ? a.entGroup[e0] : 0, G1 = nEnt > 0 ? a.entGroup[e1 - 1] : -1;
+	const int nGroups = G1 - G0 + 1, nStages = (nGroups + GRP_ROWS - 1) / GRP_ROWS;
 	sd_pdl_wait();
 	sd_pdl_launch_dependents();
 
-	if (tid >= TMA_CONSUMERS) {
-		// ---------------- producer warp: lane r looks after entry r of the stage; only group leaders copy ----------------
-		const int lane = tid - TMA_CONSUMERS;
-		for (int it = 0; it < nIter; it++) {
-			const int s = it % GRP_STAGES;
-			const int e = e0 + it * GRP_ROWS + lane;
-			const bool in = lane < GRP_ROWS && e < e1;
-			const int row = in ? a.entRow[e] : -1;
-			const int prev = __shfl_up_sync(0xffffffffu, row, 1);
-			const bool leader = in && (lane == 0 || prev != row);
-			const unsigned leaders = __ballot_sync(0xffffffffu, leader);
-			sd_mbar_wait(&empty[s], ((it / GRP_STAGES) & 1) ^ 1);
-			if (lane == 0) sd_mbar_expect_tx(&full[s], (uint32_t) __popc(leaders) * TMA_ROW_BYTES);
+	if (tid >= GRP_CONSUMERS) {
+		// ---------------- producer warp: lane r copies the row of group G0 + 8 k + r into slot r of stage k ----------------
+		const int lane = tid - GRP_CONSUMERS;
+		for (int k = 0; k < nStages; k++) {
+			const int s = k % GRP_STAGES;
+			const int cnt = min(GRP_ROWS, nGroups - k * GRP_ROWS);
+			const int row = lane < cnt ? a.groupRow[G0 + k * GRP_ROWS + lane] : 0;
+			sd_mbar_wait(&empty[s], ((k / GRP_STAGES) & 1) ^ 1);
+			if (lane == 0) sd_mbar_expect_tx(&full[s], (uint32_t) cnt * TMA_ROW_BYTES);
 			__syncwarp();
-			if (leader) sd_bulk_g2s(ring + ((size_t) s * GRP_ROWS + lane) * SD_TILE_W, tileBase + (size_t) row * SD_TILE_W, TMA_ROW_BYTES, &full[s]);
+			if (lane < cnt) sd_bulk_g2s(ring + ((size_t) s * GRP_ROWS + lane) * TMA_ROW_BYTES, tileBase + (size_t) row * SD_TILE_W, TMA_ROW_BYTES, &full[s]);
 		}
 		return;
 	}
 
 	// ---------------- consumers --------------------------------------------------------------------------------------
-	double oV0 = -DBL_MAX, oV1 = -DBL_MAX, nV0 = -DBL_MAX, nV1 = -DBL_MAX;
-	int oI0 = -1, oI1 = -1, nI0 = -1, nI1 = -1;
-	for (int it = 0; it < nIter; it++) {
-		const int r0 = it * GRP_ROWS;
-		if (r0 % SW_BATCH == 0) {                                                           // refill the descriptor batch (consumers only)
-			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
-			const int e = e0 + r0 + tid;
-			const bool ok = e < e1;
-			const int b = ok ? a.entBasis[e] : 0;
-			const int win = ok ? a.descWin[b] : 0;
-			s_ac[tid] = ok ? make_double2(a.descA[b], a.descC[b]) : make_double2(0.0, 0.0);
-			s_row[tid] = ok ? a.entRow[e] : -1;
-			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
-			int l = tid;                                                                    // walk back to the leader inside the 8-entry stage
-			while ((l % GRP_ROWS) != 0 && s_row[l - 1] == s_row[tid]) l--;
-			s_meta[tid] = win | ((l % GRP_ROWS) << 2) | (b << 5);
-			asm volatile("bar.sync 1, %0;" :: "n"(TMA_CONSUMERS) : "memory");
-		}
-		const int s = it % GRP_STAGES;
-		sd_mbar_wait(&full[s], (it / GRP_STAGES) & 1);
-		const double2 *stage = reinterpret_cast<const double2 *>(ring + (size_t) s * GRP_ROWS * SD_TILE_W) + tid;
-		const int j0 = r0 % SW_BATCH;
-		double2 d[GRP_ROWS];
-		int meta[GRP_ROWS];
+	double oV[4] = {-DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX}, nV[4] = {-DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
+	int oI[4] = {-1, -1, -1, -1}, nI[4] = {-1, -1, -1, -1};
+	constexpr int PER = SW_BATCH / GRP_CONSUMERS;                                         // descriptor entries per thread and batch
+	int pB[PER], pW[PER], pG[PER]; double pA[PER], pC[PER];
+	// entries past the end of the chunk: window 0 (ignored), last group (no stage change)
+#define SD_GRP_FETCH(base) do { _Pragma("unroll") for (int u = 0; u < PER; u++) { \
+			const int e_ = e0 + (base) + tid + u * GRP_CONSUMERS; const bool ok_ = e_ < e1; \
+			pB[u] = ok_ ? a.entBasis[e_] : 0; pG[u] = ok_ ? a.entGroup[e_] - G0 : nGroups - 1; \
+			pW[u] = ok_ ? a.descWin[pB[u]] : 0; pA[u] = ok_ ? a.descA[pB[u]] : 0.0; pC[u] = ok_ ? a.descC[pB[u]] : 0.0; } } while (0)
+	if (nEnt > 0) SD_GRP_FETCH(0);
+	int cur = -1;                                                                          // stage this warp holds
+	const unsigned char *mine = ring + tid * 16;
+	for (int j0 = 0; j0 < nEnt; j0 += SW_BATCH) {
+		asm volatile("bar.sync 1, %0;" :: "n"(GRP_CONSUMERS) : "memory");                 // everyone is done with the previous batch
 #pragma unroll
-		for (int r = 0; r < GRP_ROWS; r++) {
-			meta[r] = s_meta[j0 + r];
-			d[r] = (meta[r] & 3) ? stage[(size_t) ((meta[r] >> 2) & 7) * (SD_TILE_W / 2)] : make_double2(0.0, 0.0);
+		for (int u = 0; u < PER; u++) {
+			const int q = tid + u * GRP_CONSUMERS;
+			s_ac[q] = make_double2(pA[u], pC[u]);
+			s_m[q] = make_int4(pW[u], (pG[u] % (GRP_ROWS * GRP_STAGES)) * TMA_ROW_BYTES, pB[u], pG[u] / GRP_ROWS);
 		}
-		__syncwarp();
-		if ((tid & 31) == 0) sd_mbar_arrive(&empty[s]);                                    // this warp is done with the stage
+		asm volatile("bar.sync 1, %0;" :: "n"(GRP_CONSUMERS) : "memory");
+		SD_GRP_FETCH(j0 + SW_BATCH);                                                       // in flight while this batch is consumed
+		const int n = min(SW_BATCH, nEnt - j0);
+		for (int j = 0; j < n; j += 4) {
+			int4 m[4];
 #pragma unroll
-		for (int r = 0; r < GRP_ROWS; r++) {
-			const int win = meta[r] & 3;
-			if (win == 0) continue;
-			const double2 ac = s_ac[j0 + r];
-			const int b = meta[r] >> 5;
-			const double s0 = __dsub_rn(__dadd_rn(ac.x, d[r].x), ac.y);                     // stocUpdate.c:174
-			const double s1 = __dsub_rn(__dadd_rn(ac.x, d[r].y), ac.y);
-			if (win == 1) { SD_LEX_UPDATE(s0, b, oV0, oI0); SD_LEX_UPDATE(s1, b, oV1, oI1); }
-			else          { SD_LEX_UPDATE(s0, b, nV0, nI0); SD_LEX_UPDATE(s1, b, nV1, nI1); }
+			for (int r = 0; r < 4; r++) m[r] = s_m[j + r];
+			double2 dA[4], dB[4];
+			if (m[0].w != cur) {                                                            // the batch starts in the next stage: hand the old one back, wait for the new one
+				if (cur >= 0) { __syncwarp(); if ((tid & 31) == 0) sd_mbar_arrive(&empty[cur % GRP_STAGES]); }
+				cur = m[0].w;
+				sd_mbar_wait(&full[cur % GRP_STAGES], (cur / GRP_STAGES) & 1);
+			}
+			const int wOr = m[0].x | m[1].x | m[2].x | m[3].x, wAnd = m[0].x & m[1].x & m[2].x & m[3].x;
+			if (m[3].w == cur && wOr == wAnd && wOr != 0) {
+				// ---- the four entries lie in the stage this warp holds (stage numbers never decrease) and belong to the same window
+				// (every entry outside the two-window mode; inside it the windows split by basis age, so mixed batches are few): one
+				// filter for all sixteen scores.  A running maximum only grows, so a score that does not reach the maximum as it stood
+				// BEFORE these entries cannot replace it after any of them either: if no lane has a candidate the batch is done;
+				// otherwise the four entries are applied one after the other, exactly.
+				double sc[4][4];
+#pragma unroll
+				for (int r = 0; r < 4; r++) {
+					dA[r] = *reinterpret_cast<const double2 *>(mine + m[r].y);
+					dB[r] = *reinterpret_cast<const double2 *>(mine + m[r].y + TMA_ROW_BYTES / 2);
+				}
+#pragma unroll
+				for (int r = 0; r < 4; r++) {
+					const double2 ac = s_ac[j + r];
+					sc[r][0] = __dsub_rn(__dadd_rn(ac.x, dA[r].x), ac.y);                  // stocUpdate.c:174
+					sc[r][1] = __dsub_rn(__dadd_rn(ac.x, dA[r].y), ac.y);
+					sc[r][2] = __dsub_rn(__dadd_rn(ac.x, dB[r].x), ac.y);
+					sc[r][3] = __dsub_rn(__dadd_rn(ac.x, dB[r].y), ac.y);
+				}
+#define SD_GRP_BATCH(V, I) do { \
+					bool hit = false; \
+					_Pragma("unroll") for (int r = 0; r < 4; r++) { _Pragma("unroll") for (int o = 0; o < 4; o++) hit |= sc[r][o] >= (V)[o]; } \
+					if (__any_sync(0xffffffffu, hit)) { \
+						_Pragma("unroll") for (int r = 0; r < 4; r++) { _Pragma("unroll") for (int o = 0; o < 4; o++) SD_LEX_UPDATE(sc[r][o], m[r].z, (V)[o], (I)[o]); } \
+					} } while (0)
+				if (wOr == 1) SD_GRP_BATCH(oV, oI); else SD_GRP_BATCH(nV, nI);
+#undef SD_GRP_BATCH
+				continue;
+			}
+			// ---- a stage boundary inside the batch, or entries of the new window / of no window: entry by entry
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				if (m[r].w != cur) {                                                        // next stage: hand the old one back, wait for the new one
+					if (cur >= 0) { __syncwarp(); if ((tid & 31) == 0) sd_mbar_arrive(&empty[cur % GRP_STAGES]); }
+					cur = m[r].w;
+					sd_mbar_wait(&full[cur % GRP_STAGES], (cur / GRP_STAGES) & 1);
+				}
+				dA[r] = *reinterpret_cast<const double2 *>(mine + m[r].y);
+				dB[r] = *reinterpret_cast<const double2 *>(mine + m[r].y + TMA_ROW_BYTES / 2);
+				if (m[r].x == 0) continue;
+				const double2 ac = s_ac[j + r];
+				const int b = m[r].z;
+				double sc[4];
+				sc[0] = __dsub_rn(__dadd_rn(ac.x, dA[r].x), ac.y);
+				sc[1] = __dsub_rn(__dadd_rn(ac.x, dA[r].y), ac.y);
+				sc[2] = __dsub_rn(__dadd_rn(ac.x, dB[r].x), ac.y);
+				sc[3] = __dsub_rn(__dadd_rn(ac.x, dB[r].y), ac.y);
+				if (m[r].x == 1) { SD_LEX_UPDATE4_RARE(sc, b, oV, oI); }
+				else             { SD_LEX_UPDATE4_RARE(sc, b, nV, nI); }
+			}
 		}
 	}
+#undef SD_GRP_FETCH
 	const size_t o = (size_t) tile * SD_TILE_W + 2 * tid;
 	const size_t oldAt = ((size_t) 0 * a.nChunks + chunk) * a.NP + o, newAt = ((size_t) 1 * a.nChunks + chunk) * a.NP + o;
-	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV0, oV1);
-	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI0, oI1);
-	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV0, nV1);
-	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI0, nI1);
+	*reinterpret_cast<double2 *>(a.partV + oldAt) = make_double2(oV[0], oV[1]);
+	*reinterpret_cast<double2 *>(a.partV + oldAt + SD_TILE_W / 2) = make_double2(oV[2], oV[3]);
+	*reinterpret_cast<int2 *>(a.partI + oldAt) = make_int2(oI[0], oI[1]);
+	*reinterpret_cast<int2 *>(a.partI + oldAt + SD_TILE_W / 2) = make_int2(oI[2], oI[3]);
+	*reinterpret_cast<double2 *>(a.partV + newAt) = make_double2(nV[0], nV[1]);
+	*reinterpret_cast<double2 *>(a.partV + newAt + SD_TILE_W / 2) = make_double2(nV[2], nV[3]);
+	*reinterpret_cast<int2 *>(a.partI + newAt) = make_int2(nI[0], nI[1]);
+	*reinterpret_cast<int2 *>(a.partI + newAt + SD_TILE_W / 2) = make_int2(nI[2], nI[3]);
 }
 
 // The same ring for problems with random technology-matrix elements (Q > 0): in the tiled layout the 1+Q planes of one
@@ -1679,8 +1753,19 @@ static int sd_group_sort(sdgpu_ctx *c) {
 	}
 	c->grpSorted = B;
 	if (dirtyFrom < B) {
+		// dense group numbers (one group = one distinct lambda row) from the first changed entry on, and the row of each group
+		c->grpGroup.resize((size_t) B);
+		int32_t g = dirtyFrom > 0 ? c->grpGroup[dirtyFrom - 1] : -1;       // groups 0..g are untouched (g continues if the next entry shares its row)
+		const int32_t gFrom = g + 1;
+		c->grpGroupRow.resize((size_t) gFrom);
+		for (int64_t i = dirtyFrom; i < B; i++) {
+			if (i == 0 || c->grpRow[i] != c->grpRow[i - 1]) { g++; c->grpGroupRow.push_back(c->grpRow[i]); }
+			c->grpGroup[i] = g;
+		}
+		SD_CUDA(cudaMemcpyAsync(c->d_entGroup + dirtyFrom, c->grpGroup.data() + dirtyFrom, (size_t) (B - dirtyFrom) * 4, cudaMemcpyHostToDevice, c->stream));
+		if ((int64_t) c->grpGroupRow.size() > gFrom)
+			SD_CUDA(cudaMemcpyAsync(c->d_groupRow + gFrom, c->grpGroupRow.data() + gFrom, (c->grpGroupRow.size() - (size_t) gFrom) * 4, cudaMemcpyHostToDevice, c->stream));
 		SD_CUDA(cudaMemcpyAsync(c->d_entBasis + dirtyFrom, c->grpBasis.data() + dirtyFrom, (size_t) (B - dirtyFrom) * 4, cudaMemcpyHostToDevice, c->stream));
-		SD_CUDA(cudaMemcpyAsync(c->d_entRow + dirtyFrom, c->grpRow.data() + dirtyFrom, (size_t) (B - dirtyFrom) * 4, cudaMemcpyHostToDevice, c->stream));
 		SD_CUDA(cudaStreamSynchronize(c->stream));          // the vectors are pageable and may change before the next cut
 	}
 	return 0;
@@ -1816,11 +1901,11 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 	case SD_SW_TMA_GRP: {
 		SweepGrpArgs g;
 		g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
-		g.entBasis = c->d_entBasis; g.entRow = c->d_entRow;
+		g.entBasis = c->d_entBasis; g.entGroup = c->d_entGroup; g.groupRow = c->d_groupRow;
 		g.basisCnt = (int) c->basisCnt; g.chunkSize = p.chunkSize; g.nChunks = p.nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
-		const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + 2 * sizeof(int));
-		if (!c->tmaAttrSet[7]) { SD_CUDA(cudaFuncSetAttribute(k_sweep_tma_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); c->tmaAttrSet[7] = true; }
-		SD_SWEEP_GO(k_sweep_tma_grp, TMA_THREADS, smem, g);
+		const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int4));
+		if (sd_smem_optin(c, k_sweep_tma_grp, SD_SMEM_GRP, 0, smem, "k_sweep_tma_grp")) return SDGPU_ERR;
+		SD_SWEEP_GO(k_sweep_tma_grp, GRP_THREADS, smem, g);
 		return 0;
 	}
 	default: break;

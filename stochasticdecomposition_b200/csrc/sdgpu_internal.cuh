@@ -165,7 +165,9 @@ struct sdgpu_ctx {
 	int64_t grpCounted = 0, grpDistinct = 0;      // bases counted so far, distinct rows among them
 	std::vector<int32_t> grpBasis, grpRow;        // bases sorted by (row, basis index), and the row of each entry
 	int64_t grpSorted = 0;                        // bases present in the sorted arrays
-	int32_t *d_entBasis = nullptr, *d_entRow = nullptr;
+	int32_t *d_entBasis = nullptr;
+	std::vector<int32_t> grpGroup, grpGroupRow;   // dense group (= distinct row) number of each sorted entry, and the row of each group
+	int32_t *d_entGroup = nullptr, *d_groupRow = nullptr;
 
 	// NVLink peer-memory exchange (sdgpu_peer_export / _attach): slots[2][G][n1+4] doubles then flags[2][G] uint32
 	static const int kMaxPeers = 16;
@@ -189,7 +191,7 @@ static inline int64_t sd_round_up(int64_t v, int64_t m) { return (v + m - 1) / m
 // Kernels whose dynamic shared memory grows with the problem: opt in above 48 KiB (static + dynamic), fail loudly above the 227 KiB
 // a CTA can have on sm_100 -- a rejected launch must not pass for a finished call.
 enum SdSmemSlot { SD_SMEM_OMEGA, SD_SMEM_LAMBDA, SD_SMEM_DELTA_ROW, SD_SMEM_DELTA_COL, SD_SMEM_MERGE, SD_SMEM_REFORM, SD_SMEM_PREP, SD_SMEM_LDG_FUSED,
-                  SD_SMEM_RC_FUSED, SD_SMEM_UPD1, SD_SMEM_UPD2, SD_SMEM_SPARE };
+                  SD_SMEM_RC_FUSED, SD_SMEM_UPD1, SD_SMEM_UPD2, SD_SMEM_GRP };
 #define SD_SMEM_LIMIT ((size_t) 227 * 1024)
 template <class K>
 static inline int sd_smem_optin(sdgpu_ctx *c, K kernel, int slot, size_t staticBytes, size_t dynBytes, const char *what) {

@@ -860,7 +860,8 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	SD_TRY(sd_alloc(&c->d_x, (size_t) c->n1 + 2)); SD_TRY(sd_alloc(&c->d_piCbarX, (size_t) c->SP));
 	SD_TRY(sd_alloc(&c->d_descA, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_descC, (size_t) c->BP));
 	SD_TRY(sd_alloc(&c->d_descRow, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_descWin, (size_t) c->BP));
-	SD_TRY(sd_alloc(&c->d_entBasis, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_entRow, (size_t) c->BP));
+	SD_TRY(sd_alloc(&c->d_entBasis, (size_t) c->BP));
+	SD_TRY(sd_alloc(&c->d_entGroup, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_groupRow, (size_t) c->BP));
 	if (c->rvd > 0) {
 		SD_TRY(sd_alloc(&c->d_termA, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_termC, (size_t) c->termCap));
 		SD_TRY(sd_alloc(&c->d_termRow, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_termMeta, (size_t) c->termCap));
@@ -887,7 +888,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 		c->d_sigmaLam, c->d_sigmaCk, c->d_delta, c->d_mask, c->d_bCk, c->d_bFeas, c->d_bPhiLen, c->d_bTermStart, c->d_tSigma, c->d_tOmega, c->d_state,
 		c->d_rvdOmCols, c->d_senx, c->d_fPiDet, c->d_fPhi, c->d_fGBar, c->d_fPsi, c->d_fCstat, c->d_fHas, c->d_fFlags,
 		c->d_vecIn, c->d_cand, c->d_candC, c->d_x, c->d_piCbarX, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin, c->d_partV, c->d_partI,
-		c->d_iStar, c->d_tilePart, c->d_cutPartial, c->d_cutOut, c->d_termA, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis, c->d_entBasis, c->d_entRow };
+		c->d_iStar, c->d_tilePart, c->d_cutPartial, c->d_cutOut, c->d_termA, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis, c->d_entBasis, c->d_entGroup, c->d_groupRow };
 	for (void *p : dev) if (p) cudaFree(p);
 	if (c->h_pinD) cudaFreeHost(c->h_pinD);
 	if (c->h_pinI) cudaFreeHost(c->h_pinI);
@@ -918,7 +919,7 @@ extern "C" int sdgpu_reset(sdgpu_ctx *c) {
 	c->omegaCnt = c->lambdaCnt = c->sigmaCnt = c->basisCnt = c->termCnt = 0;
 	c->maxPhiLen = 0; c->anyInfeasibleBasis = false; c->lastOmegaCnt = 0; c->fpCnt = 0;      // (freeCutsType(cell->fcutsPool, true), setup.c:236)
 	c->basis.clear(); c->hostMask.clear();
-	c->hostLam.clear(); c->grpRowCount.clear(); c->grpBasis.clear(); c->grpRow.clear(); c->grpCounted = c->grpDistinct = c->grpSorted = 0;
+	c->hostLam.clear(); c->grpRowCount.clear(); c->grpBasis.clear(); c->grpRow.clear(); c->grpGroup.clear(); c->grpGroupRow.clear(); c->grpCounted = c->grpDistinct = c->grpSorted = 0;
 	if (c->d_fHas) SD_CUDA(cudaMemset(c->d_fHas, 0, (size_t) c->caps.maxBasis));
 	return 0;
 }

@@ -102,13 +102,15 @@ def test_bulk_multi_tile_multi_chunk(D, N, Q, variant):
     assert np.array_equal(a.view(np.int64), b.view(np.int64))
 
 
-@pytest.mark.parametrize("D,N,extra", [(500, 1500, 2), (900, 700, 1), (300, 1100, 5)])
-def test_grouped_sweep_shared_lambda_rows(D, N, extra):
+@pytest.mark.parametrize("D,N,extra", [(500, 1500, 2), (900, 700, 1), (300, 1100, 5), (2600, 600, 3)])
+def test_grouped_sweep_shared_lambda_rows(D, N, extra, monkeypatch):
     """Several sigmas / bases per lambda row (calcSigma appends a sigma whenever pi x bBar or pi x Cbar differ while the lambda is
     already stored): the grouped sweep (variant 4) walks the bases sorted by (row, basis index) and keeps the running maximum
     lexicographically.  iStar equals the oracle's, and the cut is bit-identical to the plain kernels'.  Bases are interleaved
     (second sigmas appended after all first ones) so the sorted walk is far from basis order; duplicated duals force ties
-    across groups."""
+    across groups.  The last shape has more than one descriptor batch (256 entries) per chunk."""
+    if D == 2600:
+        monkeypatch.setenv("SDGPU_CHUNKS", "3")          # ~3 500 entries per chunk: fourteen descriptor batches, a ragged last one
     prob = make_problem(17, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=0)
     rng = np.random.default_rng(D + N + extra)
     pis = rng.uniform(-1, 1, (D, prob.rows + 1)) * (rng.random((D, prob.rows + 1)) > 0.3)

@@ -15,6 +15,9 @@ from stochasticdecomposition_b200._abi import Caps  # noqa: E402
 from stochasticdecomposition_b200.synthetic import make_problem  # noqa: E402
 
 
+FRESH_X = float(os.environ.get("PROBE_FRESH_X", "0.5"))      # half-width of the per-cut perturbation of x (0: the same x every cut)
+
+
 def run(D, N, g, reps=8, R=40, n1=63):
     prob = make_problem(bench.SEED, rows=R + 8, cols=2 * R, n1=n1, n1c=n1, R=R, Rb=R, Q=0)
     rng = np.random.default_rng(bench.SEED)
@@ -34,14 +37,19 @@ def run(D, N, g, reps=8, R=40, n1=63):
             t.basis_append(int(iters[d]), True, [si])
     t.set_timing(True)
     x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
-    out = {"lambda_rows": D, "bases": g * D, "observations": N}
+    out = {"lambda_rows": D, "bases": g * D, "observations": N, "x_perturbation": FRESH_X}
     cuts = {}
     for name, v in (("ldg", 1), ("tma", 2), ("auto", 0), ("grouped", 4)):
         t.set_sweep_variant(v)
         cuts[name] = t.sd_cut(x, k, 1, 0.0)
         ms = []
+        xr = np.random.default_rng(7)
         for s in range(reps):
-            t.sd_cut(x, k, 1, 0.0, want_istar=False)
+            if FRESH_X:                                     # a new first-stage point per cut (the seeded ring must not be timed on a repeated x)
+                xs = x + xr.uniform(-FRESH_X, FRESH_X, x.shape); xs[0] = 0
+            else:
+                xs = x
+            t.sd_cut(xs, k, 1, 0.0, want_istar=False)
             ms.append(t.stats()["last_sweep_ms"])
         m = float(np.median(ms))
         out[f"{name}_variant"] = t.stats()["last_sweep_variant"]
