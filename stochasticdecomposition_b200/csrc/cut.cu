@@ -508,8 +508,12 @@ struct SweepGrpArgs {
 	double *partV; int32_t *partI; int64_t NP;
 };
 
-#define GRP_ROWS 8
+#ifndef GRP_ROWS
+#define GRP_ROWS 8      // distinct rows per ring stage
 #define GRP_STAGES 2
+#define GRP_BATCH 256   // entry descriptors per shared-memory refill
+#define GRP_CTAS 3      // CTAs per SM the kernel is compiled for
+#endif
 
 // greater score, or equal score and lower basis index; the equal case is rare, so the common path is one compare
 #define SD_LEX_UPDATE(sc, bb, bestV, bestI) do { if ((sc) >= (bestV)) { if ((sc) > (bestV) || (bb) < (bestI)) { (bestV) = (sc); (bestI) = (bb); } } } while (0)
@@ -540,13 +544,13 @@ struct SweepGrpArgs {
 			if (h3_ && ((sc)[3] > (V)[3] || (bb) < (I)[3])) { (V)[3] = (sc)[3]; (I)[3] = (bb); } \
 		} } while (0)
 
-__global__ void __launch_bounds__(GRP_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a) {
+__global__ void __launch_bounds__(GRP_THREADS, GRP_CTAS) k_sweep_tma_grp(SweepGrpArgs a) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	unsigned char *ring = smem_raw;                                                        // [stage][slot][4 KiB]
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES);
 	uint64_t *empty = full + GRP_STAGES;
-	double2 *s_ac = reinterpret_cast<double2 *>(empty + GRP_STAGES);                        // [SW_BATCH] (sigma.pib, piCbarX)
-	int4 *s_m = reinterpret_cast<int4 *>(s_ac + SW_BATCH);                                 // [SW_BATCH] (window, slot byte offset, basis, stage)
+	double2 *s_ac = reinterpret_cast<double2 *>(empty + GRP_STAGES);                        // [GRP_BATCH] (sigma.pib, piCbarX)
+	int4 *s_m = reinterpret_cast<int4 *>(s_ac + GRP_BATCH);                                 // [GRP_BATCH] (window, slot byte offset, basis, stage)
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	const int e0 = chunk * a.chunkSize, e1 = min(a.basisCnt, e0 + a.chunkSize);
 	const int nEnt = e1 - e0;
@@ -580,7 +584,7 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a
 	// ---------------- consumers --------------------------------------------------------------------------------------
 	double oV[4] = {-DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX}, nV[4] = {-DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX};
 	int oI[4] = {-1, -1, -1, -1}, nI[4] = {-1, -1, -1, -1};
-	constexpr int PER = SW_BATCH / GRP_CONSUMERS;                                         // descriptor entries per thread and batch
+	constexpr int PER = GRP_BATCH / GRP_CONSUMERS;                                         // descriptor entries per thread and batch
 	int pB[PER], pW[PER], pG[PER]; double pA[PER], pC[PER];
 	// entries past the end of the chunk: window 0 (ignored), last group (no stage change)
 #define SD_GRP_FETCH(base) do { _Pragma("unroll") for (int u = 0; u < PER; u++) { \
@@ -590,7 +594,7 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a
 	if (nEnt > 0) SD_GRP_FETCH(0);
 	int cur = -1;                                                                          // stage this warp holds
 	const unsigned char *mine = ring + tid * 16;
-	for (int j0 = 0; j0 < nEnt; j0 += SW_BATCH) {
+	for (int j0 = 0; j0 < nEnt; j0 += GRP_BATCH) {
 		asm volatile("bar.sync 1, %0;" :: "n"(GRP_CONSUMERS) : "memory");                 // everyone is done with the previous batch
 #pragma unroll
 		for (int u = 0; u < PER; u++) {
@@ -599,8 +603,8 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_sweep_tma_grp(SweepGrpArgs a
 			s_m[q] = make_int4(pW[u], (pG[u] % (GRP_ROWS * GRP_STAGES)) * TMA_ROW_BYTES, pB[u], pG[u] / GRP_ROWS);
 		}
 		asm volatile("bar.sync 1, %0;" :: "n"(GRP_CONSUMERS) : "memory");
-		SD_GRP_FETCH(j0 + SW_BATCH);                                                       // in flight while this batch is consumed
-		const int n = min(SW_BATCH, nEnt - j0);
+		SD_GRP_FETCH(j0 + GRP_BATCH);                                                       // in flight while this batch is consumed
+		const int n = min(GRP_BATCH, nEnt - j0);
 		for (int j = 0; j < n; j += 4) {
 			int4 m[4];
 #pragma unroll
@@ -1903,7 +1907,7 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 		g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
 		g.entBasis = c->d_entBasis; g.entGroup = c->d_entGroup; g.groupRow = c->d_groupRow;
 		g.basisCnt = (int) c->basisCnt; g.chunkSize = p.chunkSize; g.nChunks = p.nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
-		const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + SW_BATCH * (sizeof(double2) + sizeof(int4));
+		const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + GRP_BATCH * (sizeof(double2) + sizeof(int4));
 		if (sd_smem_optin(c, k_sweep_tma_grp, SD_SMEM_GRP, 0, smem, "k_sweep_tma_grp")) return SDGPU_ERR;
 		SD_SWEEP_GO(k_sweep_tma_grp, GRP_THREADS, smem, g);
 		return 0;

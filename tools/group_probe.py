@@ -26,7 +26,7 @@ def run(D, N, g, reps=8, R=40, n1=63):
     w = (1 + rng.poisson(0.25, N)).astype(np.int32)
     k = int(w.sum())
     iters = np.ceil((np.arange(D) + 1) * (k / D)).astype(np.int32)
-    t = sd.load_library().create(prob, Caps(D + 2, g * D + 2, g * D + 2, N + 2, 1))
+    t = sd.load_library(os.environ.get("PROBE_LIB")).create(prob, Caps(D + 2, g * D + 2, g * D + 2, N + 2, 1))
     t.omega_append_bulk(obs, w)
     t.update_dual_bulk(pis, None, iters, -1.0)
     t.calc_delta_block(0, D, 0, N)
