@@ -61,11 +61,13 @@ def _caps(slp, K):
     return Caps(n, n, 2 * K + 2, K + 1, 1 + slp.rvd)
 
 
-def _run(shape, K, reps=1, force_second=None, seed=3):
+def _run(shape, K, reps=1, force_second=None, seed=3, force_first=None):
     import stochasticdecomposition_b200 as sd
     slp = make_slp(shape)
     prob = slp.problem()
     gpu = Recorder(sd.load_library().create(prob, _caps(slp, K)))
+    if force_first is not None:
+        gpu.set_sweep_variant(force_first)
     cpu = OmpPort(oracle_loader.oracle().create(prob, _caps(slp, K)))
     tabs = Lockstep([gpu, cpu], rtol=1e-9)
     out = []
@@ -106,3 +108,23 @@ def test_storm_random_cost_two_replications_through_reset():
     assert c1["omega"] > 512 and c2["omega"] > 512 and c1["sigma"] > c1["basis"]         # phi columns were stored (multi-term bases)
     assert {3, 4} <= gpu.variants, gpu.variants                                          # per-term gathers, then the term-linear ring (forced in replication 2)
     assert st1.iterations == st2.iterations == 600
+
+
+def test_ssn_800_iterations_on_the_grouped_ring():
+    """the grouped ring (bases walked in (lambda row, basis) order, lexicographic running maximum, four entries per filter, chunk merge
+    by basis index) forced on LP duals: the ties are the LP's.  (The synthetic instances rarely store two sigmas on one lambda row, so
+    the sharing itself is covered by tests/test_gpu_parity.py::test_grouped_sweep_shared_lambda_rows; here the point is the order-free
+    walk and the incremental re-sort as one basis after the other arrives.)"""
+    gpu, out = _run("ssn", 800, force_first=4)
+    st, counts = out[0]
+    assert gpu.variants == {6}, gpu.variants
+    assert counts["omega"] > 512 and st.iterations == 800
+
+
+def test_pgp2_1000_iterations_recompute_sweep():
+    """pgp2 shape: 3 random right-hand sides with a small discrete support -- every observation is found again by calcOmega
+    (weights >> 1, N stays at the support size) and the automatic choice is the sweep that recomputes delta.pib from the factors"""
+    gpu, out = _run("pgp2", 1000)
+    st, counts = out[0]
+    assert gpu.variants == {5}, gpu.variants
+    assert counts["omega"] <= 64 and counts["basis"] >= 4 and st.iterations == 1000, counts
