@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_ldg(SweepArgs a, typ
 	const SweepPrepArgs &pa = *reinterpret_cast<const SweepPrepArgs *>(&pa_);      // only dereferenced when FUSED
 	__shared__ double2 s_ac[SW_BATCH];       // (sigma.pib, piCbarX)
 	__shared__ int2 s_rw[SW_BATCH];          // (lambda row, window)
-	__shared__ double s_xq[HAS_Q ? 64 : 1];
+	__shared__ double s_xq[HAS_Q ? SD_MAX_Q : 1];
 	extern __shared__ double s_xc[];         // FUSED: x[CCols[k]]
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	if (FUSED) for (int k = tid; k < pa.n1c; k += blockDim.x) s_xc[k] = pa.xp.v[pa.CCols[k]];
@@ -794,7 +794,7 @@ struct SweepGenArgs {
 };
 
 __global__ void __launch_bounds__(SD_SWEEP_THREADS) k_sweep_general(SweepGenArgs a) {
-	__shared__ double s_xq[64];
+	__shared__ double s_xq[SD_MAX_Q];
 	const int tile = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
 	const int b0 = chunk * a.chunkSize, b1 = min(a.basisCnt, b0 + a.chunkSize);
 	sd_pdl_wait();
@@ -1942,7 +1942,7 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples, int pi_eval_flag, double lb, bool fuseNormalise) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
 	if (numSamples == 0) return sdgpu_fail("sd_cut: numSamples is zero");
-	if (c->Q > 64) return sdgpu_fail("sd_cut: rvCOmCnt %d exceeds the 64 random T elements this build stages in shared memory", c->Q);
+	if (c->Q > SD_MAX_Q) return sdgpu_fail("sd_cut: rvCOmCnt %d exceeds the %d random T elements this build stages in shared memory", c->Q, SD_MAX_Q);
 	SD_CUDA(cudaSetDevice(c->device));
 	int64_t launches0 = c->stats.total_launches;
 	if (c->timing) SD_CUDA(cudaEventRecord(c->evA, c->stream));
@@ -2123,7 +2123,7 @@ extern "C" int sdgpu_set_sweep_variant(sdgpu_ctx *c, int variant) {
 extern "C" int sdgpu_compute_istar(sdgpu_ctx *c, const double *Xvect, int obs, int numSamples, int pi_eval, int isNew, double *argmax) {
 	if (!c || !Xvect) return sdgpu_fail("null argument");
 	if (obs < 0 || obs >= c->omegaCnt) return sdgpu_fail("compute_istar: observation %d out of range", obs);
-	if (c->Q > 64) return sdgpu_fail("compute_istar: rvCOmCnt too large");
+	if (c->Q > SD_MAX_Q) return sdgpu_fail("compute_istar: rvCOmCnt too large");
 	SD_CUDA(cudaSetDevice(c->device));
 	// always split at the (possibly shrunk) sample count: isNew asks for the bases above it, !isNew for those at or below
 	if (sd_launch_prep(c, Xvect, sd_window_cutoff(numSamples, pi_eval != 0), 1, true)) return SDGPU_ERR;

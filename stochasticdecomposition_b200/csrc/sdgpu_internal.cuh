@@ -193,6 +193,8 @@ static inline int64_t sd_round_up(int64_t v, int64_t m) { return (v + m - 1) / m
 enum SdSmemSlot { SD_SMEM_OMEGA, SD_SMEM_LAMBDA, SD_SMEM_DELTA_ROW, SD_SMEM_DELTA_COL, SD_SMEM_MERGE, SD_SMEM_REFORM, SD_SMEM_PREP, SD_SMEM_LDG_FUSED,
                   SD_SMEM_RC_FUSED, SD_SMEM_UPD1, SD_SMEM_UPD2, SD_SMEM_GRP };
 #define SD_SMEM_LIMIT ((size_t) 227 * 1024)
+#define SD_MAX_Q 512             // random T elements (rvCOmCnt): their x entries sit in 4 KiB of shared memory in the load-based sweeps; the rings
+                                 // take a dual row with all its planes into one stage and bow out far earlier (1 + Q planes of 4 KiB each)
 template <class K>
 static inline int sd_smem_optin(sdgpu_ctx *c, K kernel, int slot, size_t staticBytes, size_t dynBytes, const char *what) {
 	if (staticBytes + dynBytes > SD_SMEM_LIMIT)

@@ -57,11 +57,13 @@ def _bulk_tables(api, prob, pis, mub, iters, obs, weights, caps, tol=-1.0):
 
 
 @pytest.mark.parametrize("variant", [1, 2])
-@pytest.mark.parametrize("D,N,Q", [(700, 1500, 0), (300, 1100, 3), (2100, 600, 0)])
+@pytest.mark.parametrize("D,N,Q", [(700, 1500, 0), (300, 1100, 3), (2100, 600, 0), (150, 700, 90)])
 def test_bulk_multi_tile_multi_chunk(D, N, Q, variant):
     """Several observation tiles and several basis chunks; ties forced by duplicated duals (lowest index must
-    win) and all-zero observations; both pi_eval modes; weights > 1."""
-    prob = make_problem(9, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=Q)
+    win) and all-zero observations; both pi_eval modes; weights > 1.  The last shape has 90 random T elements: past what a ring stage
+    holds, the load-based sweep with all the x entries in shared memory."""
+    prob = make_problem(9, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=Q) if Q <= 14 else \
+        make_problem(9, rows=120, cols=200, n1=100, n1c=60, R=40, Rb=30, Q=Q)
     rng = np.random.default_rng(D + N)
     pis = rng.uniform(-1, 1, (D, prob.rows + 1)) * (rng.random((D, prob.rows + 1)) > 0.3)
     dup = rng.choice(np.arange(1, D), size=max(1, D // 50), replace=False)
