@@ -322,6 +322,12 @@ int  sdgpu_plan_sweep_kind(int rvCOmCnt, int rvdOmCnt, int rvbOmCnt, int maxPhiL
  * operations per pair; the library never fuses them) and, for comparison, DFMA flops.  Best of `reps` launches.
  * The roofline denominator of the FP64-bound kernels (recompute sweep, bulk delta build). */
 int  sdgpu_fp64_peak(int device, int reps, double *mulAddOpsPerSec, double *fmaFlopsPerSec);
+/* The delta table (8 (1+Q) bytes x dual rows x observations, the one table whose CAPACITY can exceed the GPU) is allocated whole by default.
+ * With the environment variable SDGPU_VMM=1 -- or automatically when the capacity passed to sdgpu_create does not fit the free device
+ * memory -- the library reserves the table's address range and maps physical memory only under the part in use (512 dual rows of an
+ * observation tile at a time; nothing is ever copied or moved).  An append that cannot get memory fails with SDGPU_ERR and a message.
+ * Returns 1 when the table is mapped on demand, 0 when it was allocated whole; the byte counts are optional outputs. */
+int  sdgpu_delta_memory(sdgpu_ctx *ctx, int64_t *reservedBytes, int64_t *mappedBytes);
 /* instrumentation: median wall time (us) of `launches` empty kernels in a row followed by mode 0: a stream synchronise, mode 1: the host
  * spinning on a word the last kernel writes into mapped pinned memory -- the floor under every synchronous call of this library */
 int  sdgpu_launch_roundtrip(int device, int mode, int launches, int reps, double *medianUs);

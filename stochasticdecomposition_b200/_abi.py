@@ -234,7 +234,7 @@ class Api:
             "last_istar_device": (i, [vp, C.POINTER(vp), c_intp]),
             "get_stats": (i, [vp, C.POINTER(CStats)]),
             "set_sweep_variant": (i, [vp, i]), "set_timing": (i, [vp, i]), "set_stream": (i, [vp, vp]), "set_collective": (i, [vp, i]),
-            "fp64_peak": (i, [i, i, c_f64p, c_f64p]), "launch_roundtrip": (i, [i, i, i, i, c_f64p]),
+            "fp64_peak": (i, [i, i, c_f64p, c_f64p]), "launch_roundtrip": (i, [i, i, i, i, c_f64p]), "delta_memory": (i, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "plan_sweep_grid": (i, [i, i64, i64, i, c_intp, c_intp, c_intp]),
             "plan_sweep_kind": (i, [i, i, i, i, i, i, i, i64, i64, i64, i64, i, c_intp]),
         }
@@ -652,6 +652,13 @@ class Tables:
 
     def set_timing(self, on: bool = True):
         self._check(self._call("set_timing", int(on)), "set_timing")
+
+    def delta_memory(self):
+        """(mapped on demand?, bytes of address space reserved, bytes of physical memory mapped) of the delta table"""
+        r, m = C.c_int64(0), C.c_int64(0)
+        st = self._call("delta_memory", C.byref(r), C.byref(m))
+        self._check(st, "delta_memory")
+        return bool(st), r.value, m.value
 
     def set_sweep_variant(self, v: int):
         self._check(self._call("set_sweep_variant", v), "set_sweep_variant")

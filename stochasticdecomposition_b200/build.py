@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdgpu.so")
-SOURCES = ["tables.cu", "cut.cu", "feaspool.cu", "nccl_glue.cu", "group.cu", "peaks.cu"]
+SOURCES = ["tables.cu", "cut.cu", "feaspool.cu", "nccl_glue.cu", "group.cu", "peaks.cu", "vmem.cu"]
 
 
 def nvcc_path() -> str:

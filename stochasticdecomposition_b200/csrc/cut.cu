@@ -1566,7 +1566,7 @@ static int sd_window_cutoff(int numSamples, int pi_eval) {
 
 static SweepGenArgs sd_gen_args(sdgpu_ctx *c, int chunkSize, int nChunks) {
 	SweepGenArgs g;
-	g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
+	g.delta = c->d_delta; g.Dcap = c->Dcap; g.Q = c->Q;
 	g.bTermStart = c->d_bTermStart; g.tSigma = c->d_tSigma; g.tOmega = c->d_tOmega; g.descWin = c->d_descWin;
 	g.sigmaPib = c->d_sigmaPib; g.piCbarX = c->d_piCbarX; g.sigmaLam = c->d_sigmaLam;
 	g.omega = c->d_omega; g.NP = c->NP; g.rvOffset2 = c->rvOffset[2];
@@ -1865,7 +1865,7 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 	switch (p.kind) {
 	case SD_SW_TMA_GEN: {
 		SweepTGArgs g;
-		g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.Q = c->Q;
+		g.delta = c->d_delta; g.Dcap = c->Dcap; g.Q = c->Q;
 		g.termA = c->d_termA; g.termC = c->d_termC; g.termRow = c->d_termRow; g.termMeta = c->d_termMeta; g.termBasis = c->d_termBasis;
 		g.bTermStart = c->d_bTermStart;
 		g.omegaCost = c->d_omega + (size_t) c->rvOffset[2] * c->NP; g.NP = c->NP; g.nCost = c->numRV - c->rvOffset[2];
@@ -1904,7 +1904,7 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 	}
 	case SD_SW_TMA_GRP: {
 		SweepGrpArgs g;
-		g.delta = c->d_delta; g.Dcap = c->caps.maxLambda; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
+		g.delta = c->d_delta; g.Dcap = c->Dcap; g.descA = c->d_descA; g.descC = c->d_descC; g.descWin = c->d_descWin;
 		g.entBasis = c->d_entBasis; g.entGroup = c->d_entGroup; g.groupRow = c->d_groupRow;
 		g.basisCnt = (int) c->basisCnt; g.chunkSize = p.chunkSize; g.nChunks = p.nChunks; g.partV = c->d_partV; g.partI = c->d_partI; g.NP = c->NP;
 		const size_t smem = (size_t) GRP_STAGES * GRP_ROWS * TMA_ROW_BYTES + 2 * GRP_STAGES * sizeof(uint64_t) + GRP_BATCH * (sizeof(double2) + sizeof(int4));
@@ -1915,7 +1915,7 @@ static int sd_launch_sweep(sdgpu_ctx *c, const SdSweepPlan &p, int tiles, const 
 	default: break;
 	}
 	SweepArgs a;
-	a.delta = c->d_delta; a.Dcap = c->caps.maxLambda; a.Q = c->Q;
+	a.delta = c->d_delta; a.Dcap = c->Dcap; a.Q = c->Q;
 	a.descA = c->d_descA; a.descC = c->d_descC; a.descRow = c->d_descRow; a.descWin = c->d_descWin;
 	a.basisCnt = (int) c->basisCnt; a.chunkSize = p.chunkSize; a.nChunks = p.nChunks;
 	a.mask = c->d_mask; a.Bcap = c->caps.maxBasis; a.x = c->d_x; a.rvCOmCols = c->d_rvCOmCols;
@@ -1972,7 +1972,7 @@ static int sd_cut_partial_impl(sdgpu_ctx *c, const double *Xvect, int numSamples
 		m.partV = c->d_partV; m.partI = c->d_partI; m.nChunks = nChunks; m.NP = c->NP; m.lex = lexMerge ? 1 : 0;
 		m.omegaCnt = N; m.pi_eval = pi_eval_flag != 0; m.lb = lb;
 		m.omegaW = c->d_omegaW; m.omega = c->d_omega; m.rvOffset2 = c->rvOffset[2];
-		m.delta = c->d_delta; m.Dcap = c->caps.maxLambda; m.Q = c->Q;
+		m.delta = c->d_delta; m.Dcap = c->Dcap; m.Q = c->Q;
 		m.sigmaPib = c->d_sigmaPib; m.sigmaPiCr = c->d_sigmaPiCr; m.sigmaLam = c->d_sigmaLam; m.sigmaCnt = (int) c->sigmaCnt;
 		m.n1c = c->n1c; m.n1cP = c->n1cP;
 		m.bTermStart = c->d_bTermStart; m.tSigma = c->d_tSigma; m.tOmega = c->d_tOmega;
@@ -2223,7 +2223,7 @@ extern "C" int sdgpu_reform_cuts_batch(sdgpu_ctx *c, int nCuts, const int32_t *i
 	ReformArgs a;
 	a.iStar = iStar ? d_is : c->d_iStar; a.istarStride = istarStride; a.omegaCnt = d_oc; a.nCuts = nCuts; a.observ = d_ob; a.k = k;
 	a.omega = c->d_omega; a.NP = c->NP; a.rvOffset2 = c->rvOffset[2];
-	a.delta = c->d_delta; a.Dcap = c->caps.maxLambda; a.Q = c->Q;
+	a.delta = c->d_delta; a.Dcap = c->Dcap; a.Q = c->Q;
 	a.sigmaPib = c->d_sigmaPib; a.sigmaPiCr = c->d_sigmaPiCr; a.sigmaLam = c->d_sigmaLam; a.n1c = c->n1c; a.n1cP = c->n1cP;
 	a.bTermStart = c->d_bTermStart; a.tSigma = c->d_tSigma; a.tOmega = c->d_tOmega;
 	a.n1 = c->n1; a.lbType = lbType; a.lb = lb; a.CCols = c->d_CCols; a.qCols = c->d_rvCOmCols;      // optimal.c:220 scatters with rvCOmCols

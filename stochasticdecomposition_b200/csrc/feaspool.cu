@@ -155,7 +155,7 @@ extern "C" int sdgpu_feas_cuts(sdgpu_ctx *c, int obsFirst, int obsLast, int basi
 	SD_CUDA(cudaMemcpyAsync(d_p, po.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
 	SD_CUDA(cudaMemcpyAsync(d_p + n, pb.data(), (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
 	k_feas_cuts<<<sd_blocks(n, 128), 128, 0, c->stream>>>(n, d_p, d_p + n, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaPiCr, c->d_sigmaLam,
-			c->n1c, c->n1cP, c->d_delta, c->caps.maxLambda, c->Q, c->d_CCols, c->d_rvCols, c->n1, d_o, d_o + n);
+			c->n1c, c->n1cP, c->d_delta, c->Dcap, c->Q, c->d_CCols, c->d_rvCols, c->n1, d_o, d_o + n);
 	SD_LAUNCH_OK("k_feas_cuts");
 	sd_count_launch(c);
 	SD_CUDA(cudaMemcpyAsync(alpha, d_o, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -204,7 +204,7 @@ static int fp_add_batch(sdgpu_ctx *c, const int32_t *po, const int32_t *pb, int 
 	SD_CUDA(cudaMemcpyAsync(d_p + n, pb, (size_t) n * 4, cudaMemcpyHostToDevice, c->stream));
 	SD_CUDA(cudaMemsetAsync(poolMatch, 0, ((size_t) 4 * n + 2) * 4, c->stream));
 	k_feas_cuts<<<fp_blocks(n, 128), 128, 0, c->stream>>>(n, d_p, d_p + n, c->d_bTermStart, c->d_tSigma, c->d_sigmaPib, c->d_sigmaPiCr, c->d_sigmaLam,
-			c->n1c, c->n1cP, c->d_delta, c->caps.maxLambda, c->Q, c->d_CCols, c->d_rvCols, c->n1, rawA, rawB);
+			c->n1c, c->n1cP, c->d_delta, c->Dcap, c->Q, c->d_CCols, c->d_rvCols, c->n1, rawA, rawB);
 	SD_LAUNCH_OK("k_feas_cuts");
 	if (c->fpCnt > 0) {
 		k_fp_match_pool<<<dim3((unsigned) fp_blocks(c->fpCnt, 256), (unsigned) n), 256, n1p * 8, c->stream>>>(n, rawA, rawB, (int) c->fpCnt, c->d_fpAlpha, c->d_fpBeta, c->n1, tol, poolMatch);

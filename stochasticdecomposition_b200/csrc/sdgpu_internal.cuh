@@ -54,6 +54,7 @@ struct SdHostBasis {
 	std::vector<int32_t> omegaIdx;   // [phiLen+1], slot 0 unused
 };
 
+struct SdVm;
 struct sdgpu_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -130,6 +131,8 @@ struct sdgpu_ctx {
 	double  *d_termA = nullptr, *d_termC = nullptr;     // sigma.pib, piCbarX of the term's sigma
 	int32_t *d_termRow = nullptr, *d_termMeta = nullptr, *d_termBasis = nullptr;   // lambda row; window | last-term << 2 | omegaIdx << 8; basis
 	size_t   tmaGenAttr = 0;
+	SdVm    *vm = nullptr;           // delta table on reserved address space, mapped as it grows (vmem.cu); null: allocated whole
+	int64_t  Dcap = 0;               // row stride of the delta table: caps.maxLambda, rounded up to 512 when the table is mapped on demand
 	size_t   smemAttr[12] = {};      // dynamic shared memory opted in per kernel on this context's device (index: SdSmemSlot)
 	double  *d_partV = nullptr;      // [2][chunks][NP] per-chunk running maxima (old, new)
 	int32_t *d_partI = nullptr;      // [2][chunks][NP]
@@ -264,6 +267,9 @@ __device__ __forceinline__ bool sd_is_last_block(unsigned int *ticket) {
 
 int sd_aux_reserve(sdgpu_ctx *c, size_t bytes);  // grows h_aux / d_aux (pinned, mapped); contents are not preserved
 int sd_scratch_reserve(sdgpu_ctx *c, size_t bytes);  // grows d_scratch (device); contents are not preserved
+int sd_vm_create(sdgpu_ctx *c, size_t rowBytes, int64_t Dcap, int64_t nTiles);   // vmem.cu
+int sd_delta_ensure(sdgpu_ctx *c, int64_t rows, int64_t obs);                    // physical memory under rows [0, rows) x observations [0, obs)
+void sd_vm_destroy(sdgpu_ctx *c);
 int sd_sync_state(sdgpu_ctx *c);                 // D2H of SdDevState + stream sync + mirror update
 int sd_nccl_allreduce(sdgpu_ctx *c, double *buf, int n);
 void sd_nccl_release(sdgpu_ctx *c);              // drops the NCCL communicator only

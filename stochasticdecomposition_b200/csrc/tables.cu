@@ -822,7 +822,19 @@ extern "C" int sdgpu_create(const sdgpu_problem *p, const sdgpu_caps *caps, int 
 	SD_TRY(sd_alloc(&c->d_sigmaPib, (size_t) c->SP)); SD_TRY(sd_alloc(&c->d_sigmaPiCk, (size_t) c->n1cP * c->SP));
 	SD_TRY(sd_alloc(&c->d_sigmaPiCr, (size_t) c->SP * c->n1cP));
 	SD_TRY(sd_alloc(&c->d_sigmaLam, (size_t) c->SP)); SD_TRY(sd_alloc(&c->d_sigmaCk, (size_t) c->SP));
-	SD_TRY(sd_alloc(&c->d_delta, (size_t) c->nTiles * caps->maxLambda * (1 + c->Q) * SD_TILE_W));
+	{   // the delta table: allocated whole, or -- SDGPU_VMM=1, or when its capacity does not fit the free memory -- reserved and mapped as it grows
+		const size_t whole = (size_t) c->nTiles * caps->maxLambda * (1 + c->Q) * SD_TILE_W * 8;
+		size_t freeB = 0, totalB = 0;
+		cudaMemGetInfo(&freeB, &totalB);
+		const char *e = getenv("SDGPU_VMM");
+		const bool onDemand = e ? atoi(e) != 0 : whole > freeB - std::min(freeB, (size_t) 2 << 30);
+		c->Dcap = caps->maxLambda;
+		if (onDemand) {
+			c->Dcap = sd_round_up(caps->maxLambda, 512);
+			if (sd_vm_create(c, (size_t) (1 + c->Q) * SD_TILE_W * 8, c->Dcap, c->nTiles)) { sdgpu_destroy(c); return SDGPU_ERR; }
+		}
+		else SD_TRY(sd_alloc(&c->d_delta, whole / 8));
+	}
 	if (c->rvd > 0) SD_TRY(sd_alloc(&c->d_mask, (size_t) c->nTiles * caps->maxBasis * SD_MASK_WORDS));
 	SD_TRY(sd_alloc(&c->d_bCk, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bFeas, (size_t) c->BP)); SD_TRY(sd_alloc(&c->d_bPhiLen, (size_t) c->BP));
 	SD_TRY(sd_alloc(&c->d_bTermStart, (size_t) c->BP + 1)); SD_TRY(sd_alloc(&c->d_tSigma, (size_t) c->termCap)); SD_TRY(sd_alloc(&c->d_tOmega, (size_t) c->termCap));
@@ -883,6 +895,7 @@ extern "C" void sdgpu_destroy(sdgpu_ctx *c) {
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	sd_nccl_release(c);
 	sd_peer_teardown(c);
+	sd_vm_destroy(c);                                      // (clears d_delta when the table was mapped on demand)
 	void *dev[] = { c->d_CCols, c->d_rvRows, c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_rvCOmCols, c->d_rvCols, c->d_bBarCol,
 		c->d_bBarVal, c->d_cbStart, c->d_cbRow, c->d_cbVal, c->d_omega, c->d_omegaW, c->d_lambda, c->d_sigmaPib, c->d_sigmaPiCk, c->d_sigmaPiCr,
 		c->d_sigmaLam, c->d_sigmaCk, c->d_delta, c->d_mask, c->d_bCk, c->d_bFeas, c->d_bPhiLen, c->d_bTermStart, c->d_tSigma, c->d_tOmega, c->d_state,
@@ -1049,9 +1062,10 @@ static int sd_launch_sigma(sdgpu_ctx *c, int iter, double tol, int64_t sigmaUppe
 
 static int sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) {
 	if (omegaUpper <= 0) return 0;
+	if (sd_delta_ensure(c, forcedRow >= 0 ? forcedRow + 1 : std::min<int64_t>(c->caps.maxLambda, c->lambdaCnt + 1), omegaUpper)) return SDGPU_ERR;
 	if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->R + c->Rb) * 8, "k_delta_row")) return SDGPU_ERR;
 	k_delta_row<<<sd_blocks(omegaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->R + c->Rb) * 8, c->stream>>>(c->d_lambda, c->LP, c->R, c->d_omega, c->NP, c->Rb, c->Q,
-			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedRow);
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->Dcap, c->d_state, forcedRow);
 	SD_LAUNCH_OK("k_delta_row");
 	sd_count_launch(c);
 	return 0;
@@ -1059,9 +1073,10 @@ static int sd_launch_delta_row(sdgpu_ctx *c, int forcedRow, int64_t omegaUpper) 
 
 static int sd_launch_delta_col(sdgpu_ctx *c, int forcedCol, int64_t lambdaUpper) {
 	if (lambdaUpper <= 0) return 0;
+	if (sd_delta_ensure(c, lambdaUpper, std::max<int64_t>(c->omegaCnt, forcedCol + 1))) return SDGPU_ERR;
 	if (sd_smem_optin(c, k_delta_col, SD_SMEM_DELTA_COL, (size_t) DC_BATCH * DC_THREADS * 8, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, "k_delta_col")) return SDGPU_ERR;
 	k_delta_col<<<sd_blocks(lambdaUpper, DC_THREADS), DC_THREADS, (size_t) std::max(1, c->numRV) * 8 + (size_t) std::max(1, c->Rb) * 4, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->numRV, c->Rb, c->Q,
-			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->caps.maxLambda, c->d_state, forcedCol);
+			c->d_bLamPos, c->d_cLamPos, c->d_cListStart, c->d_cList, c->d_delta, c->Dcap, c->d_state, forcedCol);
 	SD_LAUNCH_OK("k_delta_col");
 	sd_count_launch(c);
 	return 0;
@@ -1133,12 +1148,13 @@ static int sd_launch_update_fused(sdgpu_ctx *c, const double *hostPi, double mub
 	const int nbCol = (colObs >= 0 && c->lambdaCnt > 0) ? sd_blocks(c->lambdaCnt, UF_THREADS) : 0;
 	a.colObs = colObs; a.lambdaCntHost = (int) c->lambdaCnt;
 	a.omega = c->d_omega; a.NP = c->NP; a.numRV = c->numRV; a.Rb = c->Rb; a.Q = c->Q; a.bLamPos = c->d_bLamPos; a.cLamPos = c->d_cLamPos;
-	a.cListStart = c->d_cListStart; a.cList = c->d_cList; a.delta = c->d_delta; a.Dcap = c->caps.maxLambda;
+	a.cListStart = c->d_cListStart; a.cList = c->d_cList; a.delta = c->d_delta; a.Dcap = c->Dcap;
 	a.st = c->d_state; a.hst = c->d_hstate;
 	const size_t commitD = (size_t) std::max(1, c->R) + c->rows + 1 + std::max(1, c->bBarCnt) + std::max(1, cbStage) + std::max(1, c->n1c);
 	const size_t colD = (size_t) c->numRV + (size_t) ((c->Rb + 1) / 2 + 1) + (size_t) UF_COLB * UF_THREADS;
 	const size_t smem = std::max(commitD, colD) * 8;
 	if (sd_smem_optin(c, k_update_fused, SD_SMEM_UPD1, 64, smem, "k_update_fused")) return SDGPU_ERR;
+	if (sd_delta_ensure(c, std::min<int64_t>(c->caps.maxLambda, c->lambdaCnt + 1), std::max<int64_t>(c->omegaCnt, colObs + 1))) return SDGPU_ERR;
 	k_update_fused<<<a.nbScan + nbCol, UF_THREADS, smem, c->stream>>>(a, vp);
 	SD_LAUNCH_OK("k_update_fused");
 	sd_count_launch(c);
@@ -1147,7 +1163,7 @@ static int sd_launch_update_fused(sdgpu_ctx *c, const double *hostPi, double mub
 		if (sd_smem_optin(c, k_delta_row, SD_SMEM_DELTA_ROW, (size_t) DC_BATCH * DC_THREADS * 8, rs, "k_delta_row")) return SDGPU_ERR;
 		SD_CUDA(sd_launch(k_delta_row, dim3((unsigned) sd_blocks(c->omegaCnt, DC_THREADS)), dim3(DC_THREADS), rs, c->stream, c->pdl,
 				(const double *) c->d_lambda, c->LP, c->R, (const double *) c->d_omega, c->NP, c->Rb, c->Q, (const int32_t *) c->d_bLamPos, (const int32_t *) c->d_cLamPos,
-				(const int32_t *) c->d_cListStart, (const int32_t *) c->d_cList, c->d_delta, (int64_t) c->caps.maxLambda, (const SdDevState *) c->d_state, -1));
+				(const int32_t *) c->d_cListStart, (const int32_t *) c->d_cList, c->d_delta, (int64_t) c->Dcap, (const SdDevState *) c->d_state, -1));
 		sd_count_launch(c);
 	}
 	return 0;
@@ -1221,6 +1237,7 @@ extern "C" int sdgpu_update_dual_bulk(sdgpu_ctx *c, int64_t n, const double *pis
 		else {
 			// the real find-or-append chain, vector after vector, with no host round trip in between: counts and
 			// flags live in SdDevState, grids are sized by the host's upper bound on the counts
+			if (sd_delta_ensure(c, std::min<int64_t>(c->caps.maxLambda, c->lambdaCnt + m), c->omegaCnt)) { rc = SDGPU_ERR; break; }
 			for (int64_t i = 0; i < m; i++) {
 				const double *d_pi = d_pis + (size_t) i * stride;
 				double mb = mubBar ? mubBar[i0 + i] : 0.0;
@@ -1245,11 +1262,12 @@ extern "C" int sdgpu_calc_delta_block(sdgpu_ctx *c, int64_t l0, int64_t l1, int6
 	if (l0 < 0 || l1 > c->lambdaCnt || o0 < 0 || o1 > c->omegaCnt || l0 > l1 || o0 > o1) return sdgpu_fail("calc_delta_block: block out of range");
 	if (l0 == l1 || o0 == o1) return 0;
 	SD_CUDA(cudaSetDevice(c->device));
+	if (sd_delta_ensure(c, l1, o1)) return SDGPU_ERR;
 	const int64_t maxY = 32768;
 	for (int64_t lb = l0; lb < l1; lb += maxY * DB_L) {
 		int64_t le = std::min(l1, lb + maxY * DB_L);
 		dim3 grid((unsigned) ((o1 - o0 + DB_O - 1) / DB_O), (unsigned) ((le - lb + DB_L - 1) / DB_L));
-		k_delta_block_rhs<<<grid, 256, 0, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->Rb, c->d_bLamPos, c->d_delta, c->caps.maxLambda, c->Q, lb, le, o0, o1);
+		k_delta_block_rhs<<<grid, 256, 0, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->Rb, c->d_bLamPos, c->d_delta, c->Dcap, c->Q, lb, le, o0, o1);
 		sd_count_launch(c);
 	}
 	if (c->Q > 0) {
@@ -1257,7 +1275,7 @@ extern "C" int sdgpu_calc_delta_block(sdgpu_ctx *c, int64_t l0, int64_t l1, int6
 			int64_t le = std::min(l1, lb + maxY);
 			dim3 grid((unsigned) ((o1 - o0 + 127) / 128), (unsigned) (le - lb));
 			k_delta_block_T<<<grid, 128, 0, c->stream>>>(c->d_lambda, c->LP, c->d_omega, c->NP, c->Rb, c->Q, c->d_cLamPos, c->d_cListStart, c->d_cList,
-					c->d_delta, c->caps.maxLambda, lb, le, o0, o1);
+					c->d_delta, c->Dcap, lb, le, o0, o1);
 			sd_count_launch(c);
 		}
 	}
@@ -1452,7 +1470,7 @@ extern "C" int sdgpu_get_delta(sdgpu_ctx *c, int lambdaIdx, int obsIdx, double *
 	if (lambdaIdx < 0 || lambdaIdx >= c->lambdaCnt || obsIdx < 0 || obsIdx >= c->omegaCnt) return sdgpu_fail("get_delta: (%d, %d) out of range", lambdaIdx, obsIdx);
 	SD_CUDA(cudaSetDevice(c->device));
 	SD_CUDA(cudaStreamSynchronize(c->stream));
-	const double *base = c->d_delta + sd_delta_off(c->caps.maxLambda, c->Q, lambdaIdx, 0, obsIdx);
+	const double *base = c->d_delta + sd_delta_off(c->Dcap, c->Q, lambdaIdx, 0, obsIdx);
 	if (pib) SD_CUDA(cudaMemcpy(pib, base, 8, cudaMemcpyDeviceToHost));
 	if (piC && c->Q > 0) SD_CUDA(cudaMemcpy2D(piC + 1, 8, base + SD_TILE_W, (size_t) SD_TILE_W * 8, 8, c->Q, cudaMemcpyDeviceToHost));
 	return 0;
@@ -1468,7 +1486,7 @@ extern "C" int sdgpu_get_delta_block(sdgpu_ctx *c, int64_t l0, int64_t l1, int64
 		int64_t o = o0;
 		while (o < o1) {
 			int64_t tEnd = std::min<int64_t>(o1, (o / SD_TILE_W + 1) * SD_TILE_W);
-			SD_CUDA(cudaMemcpy(out + (size_t) (l - l0) * (o1 - o0) + (o - o0), c->d_delta + sd_delta_off(c->caps.maxLambda, c->Q, l, plane, o),
+			SD_CUDA(cudaMemcpy(out + (size_t) (l - l0) * (o1 - o0) + (o - o0), c->d_delta + sd_delta_off(c->Dcap, c->Q, l, plane, o),
 					(size_t) (tEnd - o) * 8, cudaMemcpyDeviceToHost));
 			o = tEnd;
 		}

@@ -116,3 +116,30 @@ def test_baseline_full_size_64GiB():
     if free < 80 * 2**30:
         pytest.skip("needs 80 GiB of free HBM")
     _check(D=65536, N=131072, rv=256, n1=89, nsample=24)
+
+
+def test_capacity_of_the_8_gpu_table_on_one_gpu():
+    """Capacity 65 536 duals x 1 048 576 observations -- the 512 GiB delta table BASELINE.json's config 5 spreads over eight GPUs --
+    is accepted by one GPU: the address range is reserved, physical memory follows the part in use (csrc/vmem.cu).  8 192 x 65 536
+    in use = 4 GiB mapped; the cut over it equals the cut of a table allocated whole."""
+    import bench
+    from stochasticdecomposition_b200._abi import Caps
+    D, N = 8192, 65536
+    prob, pis, obsv, weights, xs = bench.make_workload(D, N, 64, 40, 0, 4)
+    k = int(weights.sum())
+    whole = bench.load_tables(sd.load_library(), prob, pis, obsv, weights, D, N, k, 4)
+    assert whole.delta_memory()[0] is False
+    ref = whole.sd_cut(xs[0], k, 1, 0.0)
+    whole.close()
+    t = sd.load_library().create(prob, Caps(65536, 65536, 65536, 1048576, 1))
+    on_demand, reserved, mapped = t.delta_memory()
+    assert on_demand and reserved == 8 * 65536 * 1048576 and mapped == 0
+    iters = np.ceil((np.arange(D) + 1) * (k / D)).astype(np.int32)
+    t.omega_append_bulk(obsv[:N], weights)
+    t.update_dual_bulk(pis[:D], None, iters, -1.0)
+    t.calc_delta_block(0, D, 0, N)
+    t.basis_append_bulk(iters, np.arange(D, dtype=np.int32))
+    assert t.delta_memory()[2] == 8 * D * N
+    cut = t.sd_cut(xs[0], k, 1, 0.0)
+    assert np.array_equal(cut.iStar, ref.iStar) and cut.alpha == ref.alpha and np.array_equal(cut.beta, ref.beta)
+    t.close()

@@ -481,3 +481,48 @@ def test_instrumentation_and_collective_selection_errors():
     st = t.stats()
     assert st["last_cut_ms"] > 0 and st["last_sweep_ms"] > 0 and st["last_merge_ms"] > 0 and st["last_collective_ms"] >= 0
     assert abs(st["last_prep_ms"] + st["last_sweep_ms"] + st["last_merge_ms"] + st["last_collective_ms"] - st["last_cut_ms"]) < 0.05 * st["last_cut_ms"] + 1e-3
+
+
+@pytest.mark.parametrize("Q", [0, 2])
+def test_delta_table_mapped_on_demand(Q):
+    """A capacity far beyond the GPU (300 000 duals x 400 000 observations: ~1 TB of delta) is accepted: the table's address range is
+    reserved and physical memory is mapped under the part in use only (csrc/vmem.cu; SURVEY.md section 7 "reserve VA once, map slabs").
+    Bulk build, then single appends that cross a 512-row slab boundary and open a new observation tile; every delta entry, iStar and
+    the cut equal the port's, and the mapped bytes stay what the rows and tiles in use need."""
+    prob = make_problem(23, rows=40, cols=60, n1=14, n1c=11, R=17, Rb=13, Q=Q)
+    rng = np.random.default_rng(77 + Q)
+    D, N = 500, 500
+    pis = rng.uniform(-1, 1, (D + 40, prob.rows + 1)) * (rng.random((D + 40, prob.rows + 1)) > 0.3)
+    obs = rng.normal(0, 1, (N + 40, prob.numRV + 1)); obs[:, 0] = 0
+    weights = (1 + rng.poisson(0.25, N)).astype(np.int32)
+    iters = np.ceil((np.arange(D) + 1) * (1.25 * N) / D).astype(np.int32)
+    to, lo, so = _bulk_tables(oracle_loader.oracle(), prob, pis[:D], np.zeros(D), iters, obs[:N], weights, Caps(D + 50, D + 50, D + 50, N + 50, 1))
+    tg, lg, sg = _bulk_tables(sd.load_library(), prob, pis[:D], np.zeros(D), iters, obs[:N], weights, Caps(300000, 300000, 300000, 400000, 1))
+    on_demand, reserved, mapped = tg.delta_memory()
+    row_bytes = (1 + Q) * 4096
+    assert on_demand and reserved >= 8 * (1 + Q) * 300000 * 400000
+    assert mapped == 1 * 512 * row_bytes, mapped                       # one tile, one slab of 512 rows
+    k = int(weights.sum())
+    for i in range(40):                                                # duals 500..539 cross the 512-row slab, observations 500..539 open tile 1
+        for t in (to, tg):
+            oi, new = t.calc_omega(obs[N + i], 1e-3)
+            assert new and oi == N + i
+            t.calc_delta(True, oi)
+            li, nl, si, ns = t.update_dual(pis[D + i], 0.0, k + i, 1e-3)
+            assert nl and li == D + i
+            t.basis_append(k + i, True, [si])
+    assert tg.delta_memory()[2] == 2 * 1024 * row_bytes                # two tiles x two slabs
+    assert to.counts() == tg.counts()
+    for plane in range(Q + 1):
+        a = to.get_delta_block(0, D + 40, 0, N + 40, plane); b = tg.get_delta_block(0, D + 40, 0, N + 40, plane)
+        assert np.array_equal(a.view(np.int64), b.view(np.int64)), f"delta plane {plane} differs"
+    x = rng.uniform(0, 1, prob.prevCols + 1); x[0] = 0
+    for variant in (1, 2):
+        tg.set_sweep_variant(variant)
+        for pi_eval in (0, 1):
+            co = to.sd_cut(x, k + 40, pi_eval, 0.0); cg = tg.sd_cut(x, k + 40, pi_eval, 0.0)
+            assert np.array_equal(co.iStar, cg.iStar)
+            assert abs(co.alpha - cg.alpha) <= RTOL * abs(co.alpha) and np.abs(co.beta - cg.beta).max() <= RTOL * max(abs(co.alpha), np.abs(co.beta[1:]).max())
+    tg.reset()                                                         # a new replication keeps the mappings (cleanCellType, setup.c:242-246)
+    assert tg.delta_memory()[2] == 2 * 1024 * row_bytes and tg.counts()["lambda"] == 0
+    tg.close()
