@@ -35,7 +35,10 @@ if __name__ == "__main__":
         sys.exit(0)
     api = sd.load_library(LIB)
     fn = api._fn("debug_phase_clocks")
-    for D, N, rv, n1 in ((1000, 1000, 86, 89), (5000, 5000, 86, 89)):
+    shapes = ((1000, 1000, 86, 89), (5000, 5000, 86, 89))
+    if "--full" in sys.argv:                                  # the strong-scaling per-GPU shape and the headline shape
+        shapes = ((8192, 131072, 256, 89), (65536, 131072, 256, 89))
+    for D, N, rv, n1 in shapes:
         prob, pis, obsv, weights, xs = bench.make_workload(D, N, rv, n1, 0, 8)
         k = int(weights.sum())
         t = bench.load_tables(api, prob, pis, obsv, weights, D, N, k, 8)
