@@ -101,6 +101,7 @@ __device__ __forceinline__ double sd_dot_strided(const double *__restrict__ col,
 // own sigma row with the same left-to-right sum, hence the same bits.
 struct SdXParam { double v[256]; };
 
+template <int BATCH>                     // loads in flight per dot: 64 while the grid is a single wave at 146 registers, 32 beyond
 __global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, double *__restrict__ xDevOut, int n1,
 		const double *__restrict__ piCk, int64_t SP, int n1c, const int32_t *__restrict__ CCols, int sigmaCnt, double *__restrict__ piCbarXAll,
 		const int32_t *__restrict__ bCk, const int32_t *__restrict__ bFeas, const int32_t *__restrict__ bTermStart,
@@ -119,7 +120,7 @@ __global__ void k_cut_prep(SdXParam xp, const double *__restrict__ xDevIn, doubl
 	if (piCbarXAll && i < sigmaCnt) piCbarXAll[i] = sd_dot_strided(piCk + i, (size_t) SP, s_x, n1c);
 	if (i < basisCnt) {
 		const int s = tSigma[bTermStart[i]];
-		const double acc = sd_dot_strided<64>(piCk + s, (size_t) SP, s_x, n1c);      // ssn's 89 columns in two round trips
+		const double acc = sd_dot_strided<BATCH>(piCk + s, (size_t) SP, s_x, n1c);   // BATCH = 64: ssn's 89 columns in two round trips
 		const int ck = bCk[i];
 		int win = 0;
 		if (bFeas[i]) {
@@ -1047,19 +1048,21 @@ __device__ __forceinline__ void sd_merge_chunks(const double *__restrict__ pv, c
 	}
 }
 
-// both windows at once (pi_eval): the new window's maxima sit `winOff` elements after the old window's; sixteen loads in flight
+// both windows at once (pi_eval): the new window's maxima sit `winOff` elements after the old window's; twelve loads in flight
+// (six chunks x two windows: one trip for the six chunks a lane owns at real-problem sizes, and few enough registers for two CTAs per SM)
 __device__ __forceinline__ void sd_merge_chunks2(const double *__restrict__ pv, const int32_t *__restrict__ pi, size_t winOff, int c0, int c1, int64_t NP,
 		bool lex, double &oV, int &oI, double &nV, int &nI) {
-	for (int c = c0; c < c1; c += 8) {
-		double v[8], w[8]; int ix[8], iw[8];
+	constexpr int CB = 6;
+	for (int c = c0; c < c1; c += CB) {
+		double v[CB], w[CB]; int ix[CB], iw[CB];
 #pragma unroll
-		for (int u = 0; u < 8; u++) {
+		for (int u = 0; u < CB; u++) {
 			const size_t at = (size_t) min(c + u, c1 - 1) * NP;
 			v[u] = __ldcg(pv + at); ix[u] = __ldcg(pi + at);
 			w[u] = __ldcg(pv + winOff + at); iw[u] = __ldcg(pi + winOff + at);
 		}
 #pragma unroll
-		for (int u = 0; u < 8; u++) {
+		for (int u = 0; u < CB; u++) {
 			if (v[u] > oV || (lex && v[u] == oV && ix[u] >= 0 && ix[u] < oI)) { oV = v[u]; oI = ix[u]; }
 			if (w[u] > nV || (lex && w[u] == nV && iw[u] >= 0 && iw[u] < nI)) { nV = w[u]; nI = iw[u]; }
 		}
@@ -1124,7 +1127,7 @@ __global__ void k_cut_exchange(MergeArgs a) {
 // all loads in flight at once, and lane 0 combines the L shares in lane order (strict '>': the lowest chunk wins ties).  With
 // few observations (real problems: N <= 5 000) this spreads the merge over ~80 SMs instead of 10 and turns eight dependent
 // memory round trips per window into one.
-__global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
+__global__ void __launch_bounds__(MG_THREADS, 2) k_cut_merge(MergeArgs a) {      // two CTAs per SM: 256 CTAs (131 072 observations) stay one wave
 	__shared__ int s_istar[SD_TILE_W];
 	__shared__ int s_w[SD_TILE_W];
 	__shared__ double s_red[4 * 32];
@@ -1238,12 +1241,12 @@ __global__ void __launch_bounds__(MG_THREADS) k_cut_merge(MergeArgs a) {
 			double acc = 0.0;
 			int w = w0;
 			if (!a.randCost) {
-				for (; w < w1; w += 16) {                        // gathers of a batch issued together (the last batch predicated, not
-					double v[16];                                // walked one dependent load at a time), adds still in observation order
+				for (; w < w1; w += 8) {                         // gathers of a batch issued together (the last batch predicated, not
+					double v[8];                                 // walked one dependent load at a time), adds still in observation order
 #pragma unroll
-					for (int u = 0; u < 16; u++) { const int is = w + u < w1 ? s_istar[w + u] : -1; v[u] = is >= 0 ? a.sigmaPiCr[(size_t) is * a.n1cP + k] : 0.0; }
+					for (int u = 0; u < 8; u++) { const int is = w + u < w1 ? s_istar[w + u] : -1; v[u] = is >= 0 ? a.sigmaPiCr[(size_t) is * a.n1cP + k] : 0.0; }
 #pragma unroll
-					for (int u = 0; u < 16; u++) if (w + u < w1 && s_istar[w + u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], (double) s_w[w + u]));
+					for (int u = 0; u < 8; u++) if (w + u < w1 && s_istar[w + u] >= 0) acc = __dadd_rn(acc, __dmul_rn(v[u], (double) s_w[w + u]));
 				}
 			}
 			for (; w < w1; w++) {
@@ -1549,11 +1552,17 @@ static int sd_launch_prep(sdgpu_ctx *c, const double *X, int cutoff, int split, 
 		xDevIn = c->d_x;
 	}
 	const int64_t n = std::max<int64_t>(std::max<int64_t>(c->basisCnt, wantAllPiCbarX ? c->sigmaCnt : 0), 1);
-	if (sd_smem_optin(c, k_cut_prep, SD_SMEM_PREP, 0, (size_t) std::max(1, c->n1c) * 8, "k_cut_prep")) return SDGPU_ERR;
-	k_cut_prep<<<sd_blocks(n, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(xp, xDevIn, c->d_x, c->n1, c->d_sigmaPiCk, c->SP, c->n1c,
-			c->d_CCols, (int) c->sigmaCnt, wantAllPiCbarX ? c->d_piCbarX : nullptr, c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma,
-			c->d_sigmaPib, c->d_sigmaLam, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin,
-			c->d_tOmega, wantTerms ? c->d_termA : nullptr, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis);
+	// the deeper load batch costs 146 registers (three CTAs of 128 threads per SM): only while every CTA of the grid is resident at once
+	// (real-problem sizes: 5 000 bases = 40 CTAs); the 65 536 bases of the bench stay at 32 loads in flight and five CTAs per SM
+	const bool deep = sd_blocks(n, 128) <= (int64_t) sd_sm_count(c) * 3;
+#define SD_PREP_GO(B) do { \
+	if (sd_smem_optin(c, k_cut_prep<B>, (B) == 64 ? SD_SMEM_PREP : SD_SMEM_PREP32, 0, (size_t) std::max(1, c->n1c) * 8, "k_cut_prep")) return SDGPU_ERR; \
+	k_cut_prep<B><<<sd_blocks(n, 128), 128, (size_t) std::max(1, c->n1c) * 8, c->stream>>>(xp, xDevIn, c->d_x, c->n1, c->d_sigmaPiCk, c->SP, c->n1c, \
+			c->d_CCols, (int) c->sigmaCnt, wantAllPiCbarX ? c->d_piCbarX : nullptr, c->d_bCk, c->d_bFeas, c->d_bTermStart, c->d_tSigma, \
+			c->d_sigmaPib, c->d_sigmaLam, (int) c->basisCnt, split, cutoff, c->d_descA, c->d_descC, c->d_descRow, c->d_descWin, \
+			c->d_tOmega, wantTerms ? c->d_termA : nullptr, c->d_termC, c->d_termRow, c->d_termMeta, c->d_termBasis); } while (0)
+	if (deep) SD_PREP_GO(64); else SD_PREP_GO(32);
+#undef SD_PREP_GO
 	SD_LAUNCH_OK("k_cut_prep");
 	sd_count_launch(c);
 	return 0;
@@ -1608,8 +1617,7 @@ static void sd_pick_chunks_for(int smCount, int tiles, int64_t basisCnt, int max
 }
 
 static void sd_pick_chunks(sdgpu_ctx *c, int tiles, int *chunkSize, int *nChunks) {
-	int smCount = 148;
-	cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, c->device);
+	const int smCount = sd_sm_count(c);
 	sd_pick_chunks_for(smCount, tiles, c->basisCnt, c->maxChunks, c->forceChunks, chunkSize, nChunks);      // forceChunks: SDGPU_CHUNKS, experiment knob
 }
 

@@ -133,7 +133,8 @@ struct sdgpu_ctx {
 	size_t   tmaGenAttr = 0;
 	SdVm    *vm = nullptr;           // delta table on reserved address space, mapped as it grows (vmem.cu); null: allocated whole
 	int64_t  Dcap = 0;               // row stride of the delta table: caps.maxLambda, rounded up to 512 when the table is mapped on demand
-	size_t   smemAttr[12] = {};      // dynamic shared memory opted in per kernel on this context's device (index: SdSmemSlot)
+	int      smCount = 0;            // multiprocessors of the device (0: not asked yet; sd_sm_count)
+	size_t   smemAttr[13] = {};      // dynamic shared memory opted in per kernel on this context's device (index: SdSmemSlot)
 	double  *d_partV = nullptr;      // [2][chunks][NP] per-chunk running maxima (old, new)
 	int32_t *d_partI = nullptr;      // [2][chunks][NP]
 	int32_t *d_iStar = nullptr;      // [NP]
@@ -194,10 +195,14 @@ static inline int64_t sd_round_up(int64_t v, int64_t m) { return (v + m - 1) / m
 // Kernels whose dynamic shared memory grows with the problem: opt in above 48 KiB (static + dynamic), fail loudly above the 227 KiB
 // a CTA can have on sm_100 -- a rejected launch must not pass for a finished call.
 enum SdSmemSlot { SD_SMEM_OMEGA, SD_SMEM_LAMBDA, SD_SMEM_DELTA_ROW, SD_SMEM_DELTA_COL, SD_SMEM_MERGE, SD_SMEM_REFORM, SD_SMEM_PREP, SD_SMEM_LDG_FUSED,
-                  SD_SMEM_RC_FUSED, SD_SMEM_UPD1, SD_SMEM_UPD2, SD_SMEM_GRP };
+                  SD_SMEM_RC_FUSED, SD_SMEM_UPD1, SD_SMEM_UPD2, SD_SMEM_GRP, SD_SMEM_PREP32 };
 #define SD_SMEM_LIMIT ((size_t) 227 * 1024)
 #define SD_MAX_Q 512             // random T elements (rvCOmCnt): their x entries sit in 4 KiB of shared memory in the load-based sweeps; the rings
                                  // take a dual row with all its planes into one stage and bow out far earlier (1 + Q planes of 4 KiB each)
+static inline int sd_sm_count(sdgpu_ctx *c) {
+	if (c->smCount <= 0) { c->smCount = 148; cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, c->device); }
+	return c->smCount;
+}
 template <class K>
 static inline int sd_smem_optin(sdgpu_ctx *c, K kernel, int slot, size_t staticBytes, size_t dynBytes, const char *what) {
 	if (staticBytes + dynBytes > SD_SMEM_LIMIT)
