@@ -33,11 +33,15 @@ if __name__ == "__main__":
     if "--build" in sys.argv:
         build()
         sys.exit(0)
+    if "--lib" in sys.argv:
+        LIB = sys.argv[sys.argv.index("--lib") + 1]
     api = sd.load_library(LIB)
     fn = api._fn("debug_phase_clocks")
     shapes = ((1000, 1000, 86, 89), (5000, 5000, 86, 89))
     if "--full" in sys.argv:                                  # the strong-scaling per-GPU shape and the headline shape
         shapes = ((8192, 131072, 256, 89), (65536, 131072, 256, 89))
+    if "--strong1" in sys.argv:                               # the one-GPU shape of the strong-scaling table
+        shapes = ((8192, 1048576, 256, 89),)
     for D, N, rv, n1 in shapes:
         prob, pis, obsv, weights, xs = bench.make_workload(D, N, rv, n1, 0, 8)
         k = int(weights.sum())
@@ -51,7 +55,8 @@ if __name__ == "__main__":
             if s >= 4:
                 acc.append([buf[i] for i in range(16)])
         a = np.median(np.array(acc, dtype=np.float64) - np.array(acc, dtype=np.float64)[:, :1], axis=0)
-        out = {"D": D, "N": N, "cut_dev_us": round(t.stats()["last_cut_ms"] * 1e3, 1), "sweep_us": round(t.stats()["last_sweep_ms"] * 1e3, 1)}
+        out = {"D": D, "N": N, "cut_dev_us": round(t.stats()["last_cut_ms"] * 1e3, 1), "sweep_us": round(t.stats()["last_sweep_ms"] * 1e3, 1),
+               "merge_event_us": round(t.stats().get("last_merge_ms", 0.0) * 1e3, 1)}
         prev = 0.0
         for i in ORDER:
             out[NAMES[i]] = round((a[i] - prev) / 1e3, 2)
